@@ -1,0 +1,1114 @@
+// sm_100a kernels + C ABI of libdfprior_b200.so (see include/dfprior_b200.h).
+//
+// Pipeline of one Renderer.render_batch_ray call (src/utils/Renderer.py:110-255), all on the
+// caller's stream, no host synchronisation, no device allocation:
+//
+//   k_depth_max      per-chunk max(gt_depth)                       (Renderer.py:159,195)
+//   k_sample_z       48 candidate depths per ray, rank-sorted      (Renderer.py:134-221)
+//   k_prep           in-bound flag, TSDF gather, band flag, band compaction
+//   k_decoder_fwd    x3: trilinear feature gather + Fourier embedding + 5-block MLP, one sample per
+//                    thread, decoder weights broadcast from shared memory  (decoder.py:168-203)
+//   k_attn_fwd       attentive fusion MLP over the compacted band samples (decoder.py:240-258)
+//   k_composite_fwd  stage select, out-of-bound override, alpha compositing (common.py:206-251)
+//
+// and of its backward: k_composite_bwd -> k_attn_bwd -> k_decoder_bwd x3 (recompute + backprop,
+// feature-gradient scatter with vector reductions, warp-cooperative weight gradients) -> k_ray_grad.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dfprior_b200.h"
+#include "dfp_math.h"
+
+namespace dfp {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define DFP_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(DFP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define DFP_LAUNCH_CHECK(name)                                                                              \
+    do {                                                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                                                \
+        if (e_ != cudaSuccess) return fail(DFP_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int NT = 256;            // threads per CTA of the per-sample kernels
+constexpr int WARPS = NT / 32;
+constexpr int SINK_FLOATS_PER_WARP = 32 * 32 + 32 * 33;
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_num_sms = n;
+        else
+            g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+// ------------------------------------------------------------------------------------------
+// device-side argument blocks
+// ------------------------------------------------------------------------------------------
+struct PointSrc {                  // where sample s comes from
+    const float* rays_o;           // MODE 0: p = o + d * z[s], ray = s / S
+    const float* rays_d;
+    const double* z;
+    int S;
+    const void* pts;               // MODE 1: f64 [n,3]; MODE 2: f32 [n,3]
+};
+template <int MODE> struct PtT { using T = double; };
+template <> struct PtT<2> { using T = float; };
+
+template <int MODE>
+__device__ __forceinline__ void load_point(const PointSrc& ps, int64_t s, typename PtT<MODE>::T p[3]) {
+    if (MODE == 0) {
+        const int64_t r = s / ps.S;
+        const float o[3] = {ps.rays_o[3 * r], ps.rays_o[3 * r + 1], ps.rays_o[3 * r + 2]};
+        const float d[3] = {ps.rays_d[3 * r], ps.rays_d[3 * r + 1], ps.rays_d[3 * r + 2]};
+        double q[3];
+        ray_point(o, d, ps.z[s], q);
+        p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
+    } else if (MODE == 1) {
+        const double* q = reinterpret_cast<const double*>(ps.pts) + 3 * s;
+        p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
+    } else {
+        const float* q = reinterpret_cast<const float*>(ps.pts) + 3 * s;
+        p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
+    }
+}
+
+struct Bounds { double b[3][2]; };
+
+struct Ws {                        // per-sample workspace arrays (NS samples)
+    double* z;                     // [NS] sorted sample depths (render only)
+    float* depthmax;               // [nchunks][2]: max(gt_depth*1.2), max(gt_depth)
+    float* low; float* high; float* tsdf; float* fused; float* w_attn;   // [NS]
+    float* rgb;                    // [NS][4]  colour decoder output (rgb + its unused 4th channel)
+    int* flags;                    // [NS] bit0 in-bound, bit1 in TSDF band
+    int* band_list;                // [NS] compacted band sample ids
+    int* band_count;               // [4]
+    // backward scratch
+    float* d_low; float* d_high; float* d_fused;    // [NS]
+    float* d_rgb;                  // [NS][4]
+    float* dp;                     // [NS][3] gradient w.r.t. the sample point
+};
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with_z) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
+    w.z = (double*)take(with_z ? ns * sizeof(double) : 0);
+    w.depthmax = (float*)take((nchunks > 0 ? nchunks : 1) * 2 * sizeof(float));
+    w.low = (float*)take(ns * 4); w.high = (float*)take(ns * 4); w.tsdf = (float*)take(ns * 4);
+    w.fused = (float*)take(ns * 4); w.w_attn = (float*)take(ns * 4);
+    w.rgb = (float*)take(ns * 16);
+    w.flags = (int*)take(ns * 4); w.band_list = (int*)take(ns * 4); w.band_count = (int*)take(16);
+    w.d_low = (float*)take(ns * 4); w.d_high = (float*)take(ns * 4); w.d_fused = (float*)take(ns * 4);
+    w.d_rgb = (float*)take(ns * 16);
+    w.dp = (float*)take(ns * 12);
+    return off;
+}
+
+// ------------------------------------------------------------------------------------------
+// sampling kernels
+// ------------------------------------------------------------------------------------------
+__global__ void k_depth_max(const float* __restrict__ gt, int64_t n, int64_t chunk, float* __restrict__ out) {
+    __shared__ float red[32];
+    const int64_t c = blockIdx.x;
+    const int64_t lo = c * chunk, hi = min(n, lo + chunk);
+    float m = -INFINITY;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) m = fmaxf(m, gt[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) {
+            out[2 * c] = __fmul_rn(m, 1.2f);     // max(gt*1.2) == max(gt)*1.2 (monotone rounding)   Renderer.py:159
+            out[2 * c + 1] = m;                  // Renderer.py:195
+        }
+    }
+}
+
+struct SampleArgs {
+    const float* rays_o; const float* rays_d; const float* gt; int64_t n_rays; int64_t chunk;
+    const float* depthmax; double* z; Bounds bound; SampleTables T;
+};
+
+// one thread per (ray, candidate); the ray's candidates are ranked in shared memory
+__global__ void __launch_bounds__(256) k_sample_z(const SampleArgs a) {
+    __shared__ double cand[256];
+    const bool has_depth = a.gt != nullptr;
+    const int S = a.T.n_samples + (has_depth ? a.T.n_surface : 0);
+    const int rpb = 256 / S;
+    const int rl = threadIdx.x / S, i = threadIdx.x - rl * S;
+    const int64_t r = (int64_t)blockIdx.x * rpb + rl;
+    const bool active = rl < rpb && r < a.n_rays;
+    double v = 0.0;
+    if (active) {
+        const float o[3] = {a.rays_o[3 * r], a.rays_o[3 * r + 1], a.rays_o[3 * r + 2]};
+        const float d[3] = {a.rays_d[3 * r], a.rays_d[3 * r + 1], a.rays_d[3 * r + 2]};
+        float max12 = 0.f, maxd = 0.f, gt = 0.f;
+        if (has_depth) {
+            const int64_t c = r / a.chunk;
+            max12 = a.depthmax[2 * c]; maxd = a.depthmax[2 * c + 1];
+            gt = a.gt[r];
+        }
+        const double far = ray_far(o, d, a.bound.b, has_depth, max12);
+        v = z_candidate(i, has_depth, gt, far, maxd, a.T);
+        cand[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (!active) return;
+    int rank = i;
+    if (has_depth && a.T.n_surface > 0) {       // torch.sort of the concatenation (values only)   Renderer.py:220-221
+        rank = 0;
+        const double* row = cand + rl * S;
+        for (int j = 0; j < S; ++j) {
+            const double u = row[j];
+            rank += (u < v) || (u == v && j < i);
+        }
+    }
+    a.z[r * S + rank] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// prep: in-bound flag, TSDF value, band flag + compaction
+// ------------------------------------------------------------------------------------------
+struct PrepArgs {
+    PointSrc ps; int64_t n; Bounds bound; Bounds tsdf_bnds; DfpTsdf tsdf; int need_tsdf;
+    float* tsdf_out; int* flags; float* w_attn; int* band_list; int* band_count; int apply_mask;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_prep(const PrepArgs a) {
+    using PT = typename PtT<MODE>::T;
+    const BoxT<PT> box = make_box<PT>(a.bound.b);
+    const BoxT<PT> tbox = make_box<PT>(a.tsdf_bnds.b);
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < a.n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = base + threadIdx.x;
+        bool band = false;
+        if (s < a.n) {
+            PT p[3];
+            load_point<MODE>(a.ps, s, p);
+            int f = (!a.apply_mask || in_bound(p, box)) ? 1 : 0;
+            if (a.need_tsdf) {
+                float xn[3];
+                normalize(p, tbox, xn);
+                const Tri t = tri_setup(xn, a.tsdf.W, a.tsdf.H, a.tsdf.D);
+                const float tv = tsdf_interp(a.tsdf.data, a.tsdf.sD, a.tsdf.sH, a.tsdf.sW, a.tsdf.W, a.tsdf.H, a.tsdf.D, t);
+                a.tsdf_out[s] = tv;
+                band = in_band(tv);
+                if (band) f |= 2;
+            }
+            a.flags[s] = f;
+            a.w_attn[s] = 1.f;                                 // decoder.py:317,332,349
+        }
+        if (a.need_tsdf) {                                     // warp-aggregated append to the band list
+            const unsigned m = __ballot_sync(0xffffffffu, band);
+            if (m) {
+                int pos = 0;
+                if (lane == __ffs(m) - 1) pos = atomicAdd(a.band_count, __popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1);
+                if (band) a.band_list[pos + __popc(m & ((1u << lane) - 1))] = (int)s;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// trilinear feature gather / scatter on a channels-last grid
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gather_features(const DfpGrid& g, const Tri& t, float* c) {
+    float acc[CDIM];
+#pragma unroll
+    for (int j = 0; j < CDIM; ++j) acc[j] = 0.f;
+#pragma unroll 1
+    for (int cn = 0; cn < 8; ++cn) {
+        int x, y, z;
+        if (!tri_corner(t, cn, g.W, g.H, g.D, x, y, z)) continue;      // index == size: skipped (GridSampler.cuh:225)
+        const float wgt = tri_weight(t, cn);
+        const float4* src = reinterpret_cast<const float4*>(g.data + (((int64_t)z * g.H + y) * g.W + x) * CDIM);
+#pragma unroll
+        for (int q = 0; q < CDIM / 4; ++q) {
+            const float4 v = __ldg(src + q);
+            acc[4 * q + 0] = fmaf(v.x, wgt, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(v.y, wgt, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v.z, wgt, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v.w, wgt, acc[4 * q + 3]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CDIM; ++j) c[j] = acc[j];
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// grid-gradient scatter (dense zero-filled grid, vector reductions) and, optionally, the gradient
+// w.r.t. the normalised coordinates                                (ATen grid_sampler_3d backward)
+__device__ __forceinline__ void scatter_features(const DfpGrid& g, float* ggrid, const Tri& t, const float* d_c,
+                                                 bool want_coord, float gn[3]) {
+    float dc[CDIM];
+#pragma unroll
+    for (int j = 0; j < CDIM; ++j) dc[j] = d_c[j];
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll 1
+    for (int cn = 0; cn < 8; ++cn) {
+        int x, y, z;
+        if (!tri_corner(t, cn, g.W, g.H, g.D, x, y, z)) continue;
+        const int64_t off = (((int64_t)z * g.H + y) * g.W + x) * CDIM;
+        if (ggrid) {
+            const float wgt = tri_weight(t, cn);
+#pragma unroll
+            for (int q = 0; q < CDIM / 4; ++q)
+                red_add_v4(ggrid + off + 4 * q, dc[4 * q] * wgt, dc[4 * q + 1] * wgt, dc[4 * q + 2] * wgt, dc[4 * q + 3] * wgt);
+        }
+        if (want_coord) {
+            const float4* src = reinterpret_cast<const float4*>(g.data + off);
+            float dot = 0.f;
+#pragma unroll
+            for (int q = 0; q < CDIM / 4; ++q) {
+                const float4 v = __ldg(src + q);
+                dot = fmaf(v.x, dc[4 * q], dot); dot = fmaf(v.y, dc[4 * q + 1], dot);
+                dot = fmaf(v.z, dc[4 * q + 2], dot); dot = fmaf(v.w, dc[4 * q + 3], dot);
+            }
+            float dx, dy, dz;
+            tri_weight_grad(t, cn, dx, dy, dz);
+            gx = fmaf(dot, dx, gx); gy = fmaf(dot, dy, gy); gz = fmaf(dot, dz, gz);
+        }
+    }
+    gn[0] = gx * t.gx; gn[1] = gy * t.gy; gn[2] = gz * t.gz;
+}
+
+__device__ __forceinline__ void load_weights_to_smem(float* dst, const float* __restrict__ src, int nfloats) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = threadIdx.x; i < nfloats / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+}
+
+// ------------------------------------------------------------------------------------------
+// decoder forward
+// ------------------------------------------------------------------------------------------
+struct DecArgs {
+    PointSrc ps; int64_t n; Bounds bound;
+    DfpGrid grid;            // this decoder's grid
+    DfpGrid grid_low;        // high decoder only: the low grid it concatenates (decoder.py:182-187)
+    const float* params;     // packed parameters (global)
+    float* out;              // DEC 0/1: [n]; DEC 2: [n][4]
+    // backward only
+    const float* dout;       // DEC 0/1: [n]; DEC 2: [n][4] (4th ignored)
+    float* ggrid;            // gradient of `grid` (NDHWC) or null
+    float* gparams;          // packed parameter gradient or null
+    float* dp;               // [n][3] accumulated, or null
+};
+
+template <int DEC, int MODE>
+__global__ void __launch_bounds__(NT) k_decoder_fwd(const DecArgs a) {
+    constexpr int CD = (DEC == 1) ? 64 : 32;
+    constexpr int NOUT = (DEC == 2) ? 4 : 1;
+    using PT = typename PtT<MODE>::T;
+    extern __shared__ float4 smem4[];
+    float* W = reinterpret_cast<float*>(smem4);
+    load_weights_to_smem(W, a.params + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR)), DecOff<CD>::SIZE);
+    __syncthreads();
+    const BoxT<PT> box = make_box<PT>(a.bound.b);
+    for (int64_t base = (int64_t)blockIdx.x * NT; base < a.n; base += (int64_t)gridDim.x * NT) {
+        const int64_t s = base + threadIdx.x;
+        if (s >= a.n) continue;
+        PT p[3];
+        load_point<MODE>(a.ps, s, p);
+        float xn[3];
+        normalize(p, box, xn);
+        float c[CD];
+        gather_features(a.grid, tri_setup(xn, a.grid.W, a.grid.H, a.grid.D), c);
+        if (DEC == 1) gather_features(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), c + CDIM);
+        const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};       // p.float()   decoder.py:189
+        float out[NOUT];
+        decoder_fwd_thread<CD, NOUT, false>(W, pf, c, out, nullptr);
+        if (NOUT == 1) a.out[s] = out[0];
+        else *reinterpret_cast<float4*>(a.out + 4 * s) = make_float4(out[0], out[NOUT > 1 ? 1 : 0], out[NOUT > 2 ? 2 : 0], out[NOUT > 3 ? 3 : 0]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// warp-cooperative parameter-gradient sink: every lane holds one sample's (a, d) pair; the warp
+// forms sum_samples a[k]*d[j] through a shared-memory transpose and issues one coalesced
+// reduction per (k, 32 j) row.
+// ------------------------------------------------------------------------------------------
+struct WarpSink {
+    float* g;        // packed parameter gradient (global)
+    float* As;       // [32][32]  As[kk*32 + sample]
+    float* Dt;       // [32][33]  Dt[sample*33 + j]
+    int lane;
+
+    __device__ __forceinline__ void stage_d(const float (&d)[32]) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) Dt[lane * 33 + j] = d[j];
+    }
+    template <int KB>
+    __device__ __forceinline__ void block(int woff, int ld, const float* a, int k0, int K) {
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) As[kk * 32 + lane] = (k0 + kk < K) ? a[k0 + kk] : 0.f;
+        __syncwarp();
+        float acc[KB];
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) acc[kk] = 0.f;
+#pragma unroll 2
+        for (int m = 0; m < 32; m += 4) {
+            const float d0 = Dt[(m + 0) * 33 + lane], d1 = Dt[(m + 1) * 33 + lane];
+            const float d2 = Dt[(m + 2) * 33 + lane], d3 = Dt[(m + 3) * 33 + lane];
+#pragma unroll
+            for (int kk = 0; kk < KB; ++kk) {
+                const float4 a4 = *reinterpret_cast<const float4*>(As + kk * 32 + m);
+                acc[kk] = fmaf(a4.x, d0, fmaf(a4.y, d1, fmaf(a4.z, d2, fmaf(a4.w, d3, acc[kk]))));
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk)
+            if (k0 + kk < K) atomicAdd(g + woff + (k0 + kk) * ld + lane, acc[kk]);
+        __syncwarp();
+    }
+    __device__ __forceinline__ void bias_from_staged(int boff) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int m = 0; m < 32; ++m) s += Dt[m * 33 + lane];
+        atomicAdd(g + boff + lane, s);
+    }
+    __device__ __forceinline__ void outer32(int woff, int ld, const float* a, int K, const float (&d)[32], int boff) {
+        stage_d(d);
+        for (int k0 = 0; k0 < K; k0 += 32) block<32>(woff, ld, a, k0, K);
+        if (boff >= 0) bias_from_staged(boff);
+    }
+    __device__ __forceinline__ void outer4(int woff, int ld, const float* a, int K, const float (&d)[32]) {
+        stage_d(d);
+        block<4>(woff, ld, a, 0, K);
+    }
+    __device__ __forceinline__ void bias32(int boff, const float (&d)[32]) {
+        stage_d(d);
+        __syncwarp();
+        bias_from_staged(boff);
+    }
+    __device__ __forceinline__ void scalar(int off, float v) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(g + off, v);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// decoder backward: recompute the forward with saved activations, back-propagate
+// ------------------------------------------------------------------------------------------
+template <int DEC, int MODE, bool WANT_PARAMS>
+__global__ void __launch_bounds__(NT) k_decoder_bwd(const DecArgs a) {
+    constexpr int CD = (DEC == 1) ? 64 : 32;
+    constexpr int NOUT = (DEC == 2) ? 4 : 1;
+    using PT = typename PtT<MODE>::T;
+    using L = DecOff<CD>;
+    extern __shared__ float4 smem4[];
+    float* W = reinterpret_cast<float*>(smem4);
+    constexpr int gbase = (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR));
+    load_weights_to_smem(W, a.params + gbase, L::SIZE);
+    WarpSink sink;
+    sink.lane = threadIdx.x & 31;
+    sink.g = a.gparams;
+    sink.As = W + L::SIZE + (threadIdx.x >> 5) * SINK_FLOATS_PER_WARP;
+    sink.Dt = sink.As + 32 * 32;
+    __syncthreads();
+    const BoxT<PT> box = make_box<PT>(a.bound.b);
+    for (int64_t base = (int64_t)blockIdx.x * NT; base < a.n; base += (int64_t)gridDim.x * NT) {
+        const int64_t s_raw = base + threadIdx.x;
+        const bool valid = s_raw < a.n;
+        const int64_t s = valid ? s_raw : a.n - 1;          // keep the whole warp in the cooperative sink
+        float dout[NOUT];
+        if (NOUT == 1) dout[0] = valid ? a.dout[s] : 0.f;
+        else {
+            const float4 v = *reinterpret_cast<const float4*>(a.dout + 4 * s);
+            dout[0] = valid ? v.x : 0.f; dout[NOUT > 1 ? 1 : 0] = valid ? v.y : 0.f; dout[NOUT > 2 ? 2 : 0] = valid ? v.z : 0.f;
+            dout[NOUT > 3 ? 3 : 0] = 0.f;                   // colour decoder's 4th output is overwritten (decoder.py:352)
+        }
+        bool any = false;
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) any = any || (dout[o] != 0.f);
+        if (!__any_sync(0xffffffffu, any)) continue;         // nothing flows into this warp's samples
+        PT p[3];
+        load_point<MODE>(a.ps, s, p);
+        float xn[3];
+        normalize(p, box, xn);
+        const Tri tri = tri_setup(xn, a.grid.W, a.grid.H, a.grid.D);
+        float c[CD];
+        gather_features(a.grid, tri, c);
+        if (DEC == 1) gather_features(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), c + CDIM);
+        const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
+        DecState st;
+        float out[NOUT];
+        decoder_fwd_thread<CD, NOUT, true>(W, pf, c, out, &st);
+        float d_c[CD];
+        float dpe[3] = {0.f, 0.f, 0.f};
+        decoder_bwd_thread<CD, NOUT, WANT_PARAMS>(W, gbase, pf, c, st, dout, d_c, dpe, sink);
+        if (valid && any) {
+            const bool want_coord = a.dp != nullptr;
+            float gn[3] = {0.f, 0.f, 0.f};
+            if (a.ggrid || want_coord) scatter_features(a.grid, a.ggrid, tri, d_c, want_coord, gn);
+            if (want_coord) {
+                // d p = d xn * 2/(b1-b0)  (common.py:287-289)  +  embedding path (decoder.py:189-191)
+                a.dp[3 * s + 0] += gn[0] * (float)(2.0 / (a.bound.b[0][1] - a.bound.b[0][0])) + dpe[0];
+                a.dp[3 * s + 1] += gn[1] * (float)(2.0 / (a.bound.b[1][1] - a.bound.b[1][0])) + dpe[1];
+                a.dp[3 * s + 2] += gn[2] * (float)(2.0 / (a.bound.b[2][1] - a.bound.b[2][0])) + dpe[2];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// attentive fusion over the compacted band list
+// ------------------------------------------------------------------------------------------
+struct AttArgs {
+    const float* params; const int* band_list; const int* band_count;
+    const float* low; const float* high; const float* tsdf;
+    float* fused; float* w_attn;
+    // backward
+    PointSrc ps; Bounds tsdf_bnds; DfpTsdf vol;
+    const float* d_fused; const float* g_w; float* d_low; float* d_high; float* dp; float* gparams;
+};
+
+__global__ void __launch_bounds__(NT) k_attn_fwd(const AttArgs a) {
+    extern __shared__ float4 smem4[];
+    float* A = reinterpret_cast<float*>(smem4);
+    load_weights_to_smem(A, a.params + OFF_ATT, AttOff::SIZE);
+    __syncthreads();
+    const int count = *a.band_count;
+    for (int i = blockIdx.x * NT + threadIdx.x; i < count; i += gridDim.x * NT) {
+        const int s = a.band_list[i];
+        const float x0 = a.high[s] + a.low[s];                         // decoder.py:326,343
+        const float x1 = tsdf_logit(a.tsdf[s]).inv;
+        AttState st;
+        float w;
+        const float f = attention_fwd_thread(A, x0, x1, w, st);
+        a.fused[s] = f;
+        a.w_attn[s] = w;
+    }
+}
+
+template <int MODE, bool WANT_PARAMS>
+__global__ void __launch_bounds__(NT) k_attn_bwd(const AttArgs a) {
+    using PT = typename PtT<MODE>::T;
+    extern __shared__ float4 smem4[];
+    float* A = reinterpret_cast<float*>(smem4);
+    load_weights_to_smem(A, a.params + OFF_ATT, AttOff::SIZE);
+    WarpSink sink;
+    sink.lane = threadIdx.x & 31;
+    sink.g = a.gparams;
+    sink.As = A + AttOff::SIZE + (threadIdx.x >> 5) * SINK_FLOATS_PER_WARP;
+    sink.Dt = sink.As + 32 * 32;
+    __syncthreads();
+    const int count = *a.band_count;
+    const BoxT<PT> tbox = make_box<PT>(a.tsdf_bnds.b);
+    for (int base = blockIdx.x * NT; base < count; base += gridDim.x * NT) {
+        const int i = base + threadIdx.x;
+        const bool valid = i < count;
+        const int s = a.band_list[valid ? i : count - 1];
+        const float g_out = valid ? a.d_fused[s] : 0.f;
+        const float g_w = (valid && a.g_w) ? a.g_w[s] : 0.f;
+        const bool any = (g_out != 0.f) || (g_w != 0.f);
+        if (!__any_sync(0xffffffffu, any)) continue;
+        const float x0 = a.high[s] + a.low[s];
+        const AttLogit lg = tsdf_logit(a.tsdf[s]);
+        AttState st;
+        float w;
+        attention_fwd_thread(A, x0, lg.inv, w, st);
+        float dx0, dx1;
+        attention_bwd_thread<WANT_PARAMS>(A, OFF_ATT, x0, lg.inv, st, g_out, g_w, dx0, dx1, sink);
+        if (valid) {
+            a.d_low[s] = dx0;                                          // low_occ enters only through high+low on band points
+            a.d_high[s] = dx0;
+            if (a.dp) {
+                const float dt = dx1 * lg.dinv_dtsdf;                  // gradient into the TSDF value gathered at p (decoder.py:241)
+                if (dt != 0.f) {
+                    PT p[3];
+                    load_point<MODE>(a.ps, s, p);
+                    float xn[3];
+                    normalize(p, tbox, xn);
+                    const Tri t = tri_setup(xn, a.vol.W, a.vol.H, a.vol.D);
+                    float gn[3];
+                    tsdf_interp_grad(a.vol.data, a.vol.sD, a.vol.sH, a.vol.sW, a.vol.W, a.vol.H, a.vol.D, t, gn);
+                    for (int k = 0; k < 3; ++k)
+                        a.dp[3 * (int64_t)s + k] += dt * gn[k] * (float)(2.0 / (a.tsdf_bnds.b[k][1] - a.tsdf_bnds.b[k][0]));
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// stage select + compositing
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float final_occ(int stage, int flags, float low, float fused) {
+    float occ = (stage != DFP_STAGE_LOW && (flags & 2)) ? fused : low;   // decoder.py:333-336, 350-352
+    if (!(flags & 1)) occ = 100.f;                                       // Renderer.py:64
+    return occ;
+}
+
+struct CompArgs {
+    int64_t n_rays; int S; int stage;
+    const double* z; const float* low; const float* fused; const float* rgb4; const int* flags; const float* w_attn;
+    double* depth; double* unc; float* color; float* weight; float* raw;
+    // backward
+    const double* g_depth; const double* g_unc; const float* g_color; const float* g_weight;
+    float* d_low; float* d_high; float* d_fused; float* d_rgb4; float* dp;
+};
+
+__global__ void __launch_bounds__(128) k_composite_fwd(const CompArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_rays) return;
+    const int S = a.S;
+    float occ[DFP_MAX_RAY_SAMPLES], rgb[3 * DFP_MAX_RAY_SAMPLES];
+    const bool col = a.stage == DFP_STAGE_COLOR;
+    for (int s = 0; s < S; ++s) {
+        const int64_t i = r * S + s;
+        occ[s] = final_occ(a.stage, a.flags[i], a.low[i], a.fused[i]);
+        if (col) { const float4 v = *reinterpret_cast<const float4*>(a.rgb4 + 4 * i); rgb[3 * s] = v.x; rgb[3 * s + 1] = v.y; rgb[3 * s + 2] = v.z; }
+        a.weight[i] = a.w_attn[i];
+        if (a.raw) *reinterpret_cast<float4*>(a.raw + 4 * i) = make_float4(col ? rgb[3 * s] : 0.f, col ? rgb[3 * s + 1] : 0.f, col ? rgb[3 * s + 2] : 0.f, occ[s]);
+    }
+    double depth, var;
+    float c3[3];
+    composite_ray(S, occ, col ? rgb : nullptr, a.z + r * S, depth, var, c3, nullptr);
+    a.depth[r] = depth; a.unc[r] = var;
+    a.color[3 * r] = c3[0]; a.color[3 * r + 1] = c3[1]; a.color[3 * r + 2] = c3[2];
+}
+
+__global__ void __launch_bounds__(128) k_composite_bwd(const CompArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_rays) return;
+    const int S = a.S;
+    float occ[DFP_MAX_RAY_SAMPLES], rgb[3 * DFP_MAX_RAY_SAMPLES], d_occ[DFP_MAX_RAY_SAMPLES], d_rgb[3 * DFP_MAX_RAY_SAMPLES];
+    const bool col = a.stage == DFP_STAGE_COLOR;
+    for (int s = 0; s < S; ++s) {
+        const int64_t i = r * S + s;
+        occ[s] = final_occ(a.stage, a.flags[i], a.low[i], a.fused[i]);
+        if (col) { const float4 v = *reinterpret_cast<const float4*>(a.rgb4 + 4 * i); rgb[3 * s] = v.x; rgb[3 * s + 1] = v.y; rgb[3 * s + 2] = v.z; }
+    }
+    const float gc[3] = {a.g_color ? a.g_color[3 * r] : 0.f, a.g_color ? a.g_color[3 * r + 1] : 0.f, a.g_color ? a.g_color[3 * r + 2] : 0.f};
+    composite_ray_bwd(S, occ, col ? rgb : nullptr, a.z + r * S, a.g_depth ? a.g_depth[r] : 0.0, a.g_unc ? a.g_unc[r] : 0.0,
+                      gc, d_occ, col ? d_rgb : nullptr);
+    for (int s = 0; s < S; ++s) {
+        const int64_t i = r * S + s;
+        const int f = a.flags[i];
+        const float g = (f & 1) ? d_occ[s] : 0.f;                        // occ overwritten by 100 outside the bound
+        const bool band = a.stage != DFP_STAGE_LOW && (f & 2);
+        a.d_low[i] = band ? 0.f : g;
+        a.d_high[i] = 0.f;
+        a.d_fused[i] = band ? g : 0.f;
+        if (col) *reinterpret_cast<float4*>(a.d_rgb4 + 4 * i) = make_float4(d_rgb[3 * s], d_rgb[3 * s + 1], d_rgb[3 * s + 2], 0.f);
+        if (a.dp) { a.dp[3 * i] = 0.f; a.dp[3 * i + 1] = 0.f; a.dp[3 * i + 2] = 0.f; }
+    }
+}
+
+// rays_o / rays_d gradients: pts = o + d*z  (Renderer.py:223-224)
+__global__ void k_ray_grad(int64_t n_rays, int S, const float* __restrict__ dp, const double* __restrict__ z,
+                           float* __restrict__ d_o, float* __restrict__ d_d) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    double so[3] = {0, 0, 0}, sd[3] = {0, 0, 0};
+    for (int s = 0; s < S; ++s) {
+        const int64_t i = r * S + s;
+        for (int k = 0; k < 3; ++k) { const double g = dp[3 * i + k]; so[k] += g; sd[k] += g * z[i]; }
+    }
+    for (int k = 0; k < 3; ++k) { if (d_o) d_o[3 * r + k] = (float)so[k]; if (d_d) d_d[3 * r + k] = (float)sd[k]; }
+}
+
+// ---- point-query epilogues (DF.forward / eval_points) ----
+struct PtsArgs {
+    int64_t n; int stage;
+    const float* low; const float* fused; const float* rgb4; const int* flags; const float* w_attn;
+    float* raw; float* w;
+    const float* g_raw; const float* g_w; float* d_low; float* d_high; float* d_fused; float* d_rgb4; float* dp;
+};
+__global__ void k_points_finalize(const PtsArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const bool col = a.stage == DFP_STAGE_COLOR;
+    const float occ = final_occ(a.stage, a.flags[i], a.low[i], a.fused[i]);
+    float4 v = make_float4(0.f, 0.f, 0.f, occ);
+    if (col) { const float4 c = *reinterpret_cast<const float4*>(a.rgb4 + 4 * i); v.x = c.x; v.y = c.y; v.z = c.z; }
+    *reinterpret_cast<float4*>(a.raw + 4 * i) = v;
+    if (a.w) a.w[i] = a.w_attn[i];
+}
+__global__ void k_points_seed_bwd(const PtsArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int f = a.flags[i];
+    const float4 gr = a.g_raw ? *reinterpret_cast<const float4*>(a.g_raw + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float g = (f & 1) ? gr.w : 0.f;
+    const bool band = a.stage != DFP_STAGE_LOW && (f & 2);
+    a.d_low[i] = band ? 0.f : g;
+    a.d_high[i] = 0.f;
+    a.d_fused[i] = band ? g : 0.f;
+    if (a.stage == DFP_STAGE_COLOR) *reinterpret_cast<float4*>(a.d_rgb4 + 4 * i) = make_float4(gr.x, gr.y, gr.z, 0.f);
+    if (a.dp) { a.dp[3 * i] = 0.f; a.dp[3 * i + 1] = 0.f; a.dp[3 * i + 2] = 0.f; }
+}
+template <typename PT>
+__global__ void k_points_grad_out(int64_t n, const float* __restrict__ dp, PT* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * n) out[i] = (PT)dp[i];
+}
+
+template <int MODE>
+__global__ void k_tsdf_sample(PointSrc ps, int64_t n, Bounds tb, DfpTsdf vol, float* out) {
+    using PT = typename PtT<MODE>::T;
+    const BoxT<PT> tbox = make_box<PT>(tb.b);
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    PT p[3];
+    load_point<MODE>(ps, s, p);
+    float xn[3];
+    normalize(p, tbox, xn);
+    out[s] = tsdf_interp(vol.data, vol.sD, vol.sH, vol.sW, vol.W, vol.H, vol.D, tri_setup(xn, vol.W, vol.H, vol.D));
+}
+
+// ------------------------------------------------------------------------------------------
+// parameter pack / unpack and grid layout transposes
+// ------------------------------------------------------------------------------------------
+struct PtrTable { const float* p[N_TENSORS]; };
+
+__global__ void k_pack_params(const PtrTable tab, float* __restrict__ packed) {
+    const int t = blockIdx.x;
+    int rows, cols;
+    tensor_shape(t, rows, cols);
+    const float* src = tab.p[t];
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) packed[packed_index(t, i / cols, i % cols)] = src[i];
+}
+struct OffTable { int off[N_TENSORS]; };
+__global__ void k_unpack_grads(const float* __restrict__ packed, float* __restrict__ flat, const OffTable offs) {
+    const int t = blockIdx.x;
+    int rows, cols;
+    tensor_shape(t, rows, cols);
+    float* dst = flat + offs.off[t];
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) dst[i] = packed[packed_index(t, i / cols, i % cols)];
+}
+
+// [C][V] <-> [V][C] with V = D*H*W, C = 32: a 32x32 shared-memory tile per block
+__global__ void k_transpose_c_v(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t V, int to_last) {
+    __shared__ float tile[32][33];
+    const int64_t v0 = (int64_t)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        if (to_last) {            // src [C][V] -> dst [V][C]
+            for (int j = ty; j < 32; j += 8) { const int64_t v = v0 + tx; tile[j][tx] = (v < V && c0 + j < C) ? src[(int64_t)(c0 + j) * V + v] : 0.f; }
+            __syncthreads();
+            for (int j = ty; j < 32; j += 8) { const int64_t v = v0 + j; if (v < V && c0 + tx < C) dst[v * C + c0 + tx] = tile[tx][j]; }
+        } else {                  // src [V][C] -> dst [C][V]
+            for (int j = ty; j < 32; j += 8) { const int64_t v = v0 + j; tile[j][tx] = (v < V && c0 + tx < C) ? src[v * C + c0 + tx] : 0.f; }
+            __syncthreads();
+            for (int j = ty; j < 32; j += 8) { const int64_t v = v0 + tx; if (v < V && c0 + j < C) dst[(int64_t)(c0 + j) * V + v] = tile[tx][j]; }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launch helpers
+// ------------------------------------------------------------------------------------------
+static int check_scene(const DfpScene* sc, int stage) {
+    if (!sc) return fail(DFP_ERR_INVALID, "scene is null");
+    if (stage < DFP_STAGE_LOW || stage > DFP_STAGE_COLOR) return fail(DFP_ERR_INVALID, "bad stage %d", stage);
+    const DfpGrid* gs[3] = {&sc->low, &sc->high, &sc->color};
+    const int need[3] = {1, stage >= DFP_STAGE_HIGH, stage == DFP_STAGE_COLOR};
+    for (int i = 0; i < 3; ++i) {
+        if (!need[i]) continue;
+        if (!gs[i]->data) return fail(DFP_ERR_INVALID, "grid %d is null", i);
+        if (gs[i]->C != DFP_C_DIM) return fail(DFP_ERR_INVALID, "grid %d has C=%d, only %d supported", i, gs[i]->C, DFP_C_DIM);
+        if (gs[i]->D < 1 || gs[i]->H < 1 || gs[i]->W < 1) return fail(DFP_ERR_INVALID, "grid %d has an empty dimension", i);
+        if (((uintptr_t)gs[i]->data) & 15) return fail(DFP_ERR_INVALID, "grid %d is not 16-byte aligned", i);
+    }
+    if (stage >= DFP_STAGE_HIGH) {
+        if (!sc->tsdf.data) return fail(DFP_ERR_INVALID, "tsdf volume is null");
+        if (sc->tsdf.D < 1 || sc->tsdf.H < 1 || sc->tsdf.W < 1) return fail(DFP_ERR_INVALID, "tsdf volume has an empty dimension");
+    }
+    for (int k = 0; k < 3; ++k)
+        if (!(sc->bound[k][1] > sc->bound[k][0])) return fail(DFP_ERR_INVALID, "bound axis %d is empty", k);
+    return DFP_OK;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    DFP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return DFP_OK;
+}
+
+static int grid_for(int64_t n, int per_block, int max_blocks) {
+    int64_t b = (n + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+static Bounds to_bounds(const double b[3][2]) {
+    Bounds r;
+    memcpy(r.b, b, sizeof(r.b));
+    return r;
+}
+
+template <int DEC, int MODE>
+static int launch_decoder_fwd(const DecArgs& a, cudaStream_t st) {
+    constexpr int CD = (DEC == 1) ? 64 : 32;
+    const size_t smem = DecOff<CD>::SIZE * sizeof(float);
+    int rc = set_smem(k_decoder_fwd<DEC, MODE>, smem);
+    if (rc) return rc;
+    const int blocks = grid_for(a.n, NT, 2 * num_sms());
+    k_decoder_fwd<DEC, MODE><<<blocks, NT, smem, st>>>(a);
+    DFP_LAUNCH_CHECK("k_decoder_fwd");
+    return DFP_OK;
+}
+template <int DEC, int MODE>
+static int launch_decoder_bwd(const DecArgs& a, cudaStream_t st) {
+    constexpr int CD = (DEC == 1) ? 64 : 32;
+    const size_t smem = (DecOff<CD>::SIZE + WARPS * SINK_FLOATS_PER_WARP) * sizeof(float);
+    const int blocks = grid_for(a.n, NT, num_sms());
+    if (a.gparams) {
+        int rc = set_smem(k_decoder_bwd<DEC, MODE, true>, smem);
+        if (rc) return rc;
+        k_decoder_bwd<DEC, MODE, true><<<blocks, NT, smem, st>>>(a);
+    } else {
+        int rc = set_smem(k_decoder_bwd<DEC, MODE, false>, smem);
+        if (rc) return rc;
+        k_decoder_bwd<DEC, MODE, false><<<blocks, NT, smem, st>>>(a);
+    }
+    DFP_LAUNCH_CHECK("k_decoder_bwd");
+    return DFP_OK;
+}
+
+// forward of everything between "points are known" and "low/high/rgb/fused/w/flags are in the workspace"
+template <int MODE>
+static int eval_samples_fwd(const DfpScene* sc, const float* params, const PointSrc& ps, int64_t n, int stage,
+                            int apply_mask, const Ws& w, cudaStream_t st) {
+    const bool hi = stage >= DFP_STAGE_HIGH;
+    if (hi) DFP_CUDA(cudaMemsetAsync(w.band_count, 0, 16, st));
+    PrepArgs pa;
+    pa.ps = ps; pa.n = n; pa.bound = to_bounds(sc->bound); pa.tsdf_bnds = to_bounds(sc->tsdf_bnds); pa.tsdf = sc->tsdf;
+    pa.need_tsdf = hi; pa.tsdf_out = w.tsdf; pa.flags = w.flags; pa.w_attn = w.w_attn;
+    pa.band_list = w.band_list; pa.band_count = w.band_count; pa.apply_mask = apply_mask;
+    k_prep<MODE><<<grid_for(n, 256, 8 * num_sms()), 256, 0, st>>>(pa);
+    DFP_LAUNCH_CHECK("k_prep");
+
+    DecArgs da;
+    memset(&da, 0, sizeof(da));
+    da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params;
+    int rc;
+    if (hi) {
+        da.grid = sc->high; da.grid_low = sc->low; da.out = w.high;
+        if ((rc = launch_decoder_fwd<1, MODE>(da, st))) return rc;
+    }
+    if (stage == DFP_STAGE_COLOR) {
+        da.grid = sc->color; da.out = w.rgb;
+        if ((rc = launch_decoder_fwd<2, MODE>(da, st))) return rc;
+    }
+    da.grid = sc->low; da.out = w.low;
+    if ((rc = launch_decoder_fwd<0, MODE>(da, st))) return rc;
+    if (hi) {
+        AttArgs aa;
+        memset(&aa, 0, sizeof(aa));
+        aa.params = params; aa.band_list = w.band_list; aa.band_count = w.band_count;
+        aa.low = w.low; aa.high = w.high; aa.tsdf = w.tsdf; aa.fused = w.fused; aa.w_attn = w.w_attn;
+        const size_t smem = AttOff::SIZE * sizeof(float);
+        if ((rc = set_smem(k_attn_fwd, smem))) return rc;
+        k_attn_fwd<<<grid_for(n, NT, num_sms()), NT, smem, st>>>(aa);
+        DFP_LAUNCH_CHECK("k_attn_fwd");
+    }
+    return DFP_OK;
+}
+
+// backward counterpart: d_low / d_high / d_fused / d_rgb / dp seeded in the workspace
+template <int MODE>
+static int eval_samples_bwd(const DfpScene* sc, const float* params, const PointSrc& ps, int64_t n, int stage,
+                            const float* g_w, const DfpGrads* g, bool want_dp, const Ws& w, cudaStream_t st) {
+    const bool hi = stage >= DFP_STAGE_HIGH;
+    int rc;
+    if (hi) {
+        AttArgs aa;
+        memset(&aa, 0, sizeof(aa));
+        aa.params = params; aa.band_list = w.band_list; aa.band_count = w.band_count;
+        aa.low = w.low; aa.high = w.high; aa.tsdf = w.tsdf;
+        aa.ps = ps; aa.tsdf_bnds = to_bounds(sc->tsdf_bnds); aa.vol = sc->tsdf;
+        aa.d_fused = w.d_fused; aa.g_w = g_w; aa.d_low = w.d_low; aa.d_high = w.d_high;
+        aa.dp = want_dp ? w.dp : nullptr; aa.gparams = g->params_packed;
+        const size_t smem = (AttOff::SIZE + WARPS * SINK_FLOATS_PER_WARP) * sizeof(float);
+        const int blocks = grid_for(n, NT, num_sms());
+        if (g->params_packed) {
+            if ((rc = set_smem(k_attn_bwd<MODE, true>, smem))) return rc;
+            k_attn_bwd<MODE, true><<<blocks, NT, smem, st>>>(aa);
+        } else {
+            if ((rc = set_smem(k_attn_bwd<MODE, false>, smem))) return rc;
+            k_attn_bwd<MODE, false><<<blocks, NT, smem, st>>>(aa);
+        }
+        DFP_LAUNCH_CHECK("k_attn_bwd");
+    }
+    DecArgs da;
+    memset(&da, 0, sizeof(da));
+    da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params;
+    da.gparams = g->params_packed; da.dp = want_dp ? w.dp : nullptr;
+    if (hi) {
+        da.grid = sc->high; da.grid_low = sc->low; da.dout = w.d_high; da.ggrid = g->grid_high;
+        if ((rc = launch_decoder_bwd<1, MODE>(da, st))) return rc;
+    }
+    if (stage == DFP_STAGE_COLOR) {
+        da.grid = sc->color; da.dout = w.d_rgb; da.ggrid = g->grid_color;
+        if ((rc = launch_decoder_bwd<2, MODE>(da, st))) return rc;
+    }
+    da.grid = sc->low; da.dout = w.d_low; da.ggrid = g->grid_low;
+    if ((rc = launch_decoder_bwd<0, MODE>(da, st))) return rc;
+    return DFP_OK;
+}
+
+static int fill_tables(const DfpCfg* cfg, SampleTables& T) {
+    if (cfg->n_importance != 0) return fail(DFP_ERR_UNSUPPORTED, "N_importance must be 0 (the reference branch is dead, Renderer.py:235-252)");
+    if (cfg->n_samples < 1 || cfg->n_surface < 0 || cfg->n_samples + cfg->n_surface > DFP_MAX_RAY_SAMPLES)
+        return fail(DFP_ERR_INVALID, "N_samples + N_surface must be in [1, %d]", DFP_MAX_RAY_SAMPLES);
+    T.n_samples = cfg->n_samples; T.n_surface = cfg->n_surface;
+    memcpy(T.tv, cfg->t_vals, sizeof(T.tv)); memcpy(T.omt, cfg->one_minus_t, sizeof(T.omt));
+    memcpy(T.ts, cfg->t_surf, sizeof(T.ts)); memcpy(T.omts, cfg->one_minus_t_surf, sizeof(T.omts));
+    return DFP_OK;
+}
+
+}  // namespace dfp
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace dfp;
+
+extern "C" {
+
+int dfp_abi_version(void) { return DFP_ABI_VERSION; }
+const char* dfp_last_error(void) { return g_err; }
+int64_t dfp_packed_param_floats(void) { return PACKED_FLOATS; }
+
+int dfp_pack_params(const float* const* tensors79, float* packed, void* stream) {
+    if (!tensors79 || !packed) return fail(DFP_ERR_INVALID, "null argument");
+    PtrTable tab;
+    for (int t = 0; t < N_TENSORS; ++t) {
+        if (!tensors79[t]) return fail(DFP_ERR_INVALID, "parameter tensor %d is null", t);
+        tab.p[t] = tensors79[t];
+    }
+    k_pack_params<<<N_TENSORS, 256, 0, (cudaStream_t)stream>>>(tab, packed);
+    DFP_LAUNCH_CHECK("k_pack_params");
+    return DFP_OK;
+}
+
+int dfp_unpack_param_grads(const float* packed_grad, float* native_flat, void* stream) {
+    if (!packed_grad || !native_flat) return fail(DFP_ERR_INVALID, "null argument");
+    OffTable offs;
+    int off = 0;
+    for (int t = 0; t < N_TENSORS; ++t) {
+        int r, c;
+        tensor_shape(t, r, c);
+        offs.off[t] = off;
+        off += r * c;
+    }
+    k_unpack_grads<<<N_TENSORS, 256, 0, (cudaStream_t)stream>>>(packed_grad, native_flat, offs);
+    DFP_LAUNCH_CHECK("k_unpack_grads");
+    return DFP_OK;
+}
+
+static int transpose_grid(const float* src, float* dst, int32_t C, int32_t D, int32_t H, int32_t W, int to_last, void* stream) {
+    if (!src || !dst) return fail(DFP_ERR_INVALID, "null argument");
+    if (C < 1 || D < 1 || H < 1 || W < 1) return fail(DFP_ERR_INVALID, "empty grid");
+    const int64_t V = (int64_t)D * H * W;
+    k_transpose_c_v<<<(unsigned)((V + 31) / 32), 256, 0, (cudaStream_t)stream>>>(src, dst, C, V, to_last);
+    DFP_LAUNCH_CHECK("k_transpose_c_v");
+    return DFP_OK;
+}
+int dfp_grid_to_ndhwc(const float* s, float* d, int32_t C, int32_t D, int32_t H, int32_t W, void* st) { return transpose_grid(s, d, C, D, H, W, 1, st); }
+int dfp_grid_to_cdhw(const float* s, float* d, int32_t C, int32_t D, int32_t H, int32_t W, void* st) { return transpose_grid(s, d, C, D, H, W, 0, st); }
+
+size_t dfp_render_workspace_bytes(int64_t n_rays, int32_t S, int64_t chunk) {
+    if (n_rays < 0 || S < 1) return 0;
+    if (chunk <= 0) chunk = n_rays > 0 ? n_rays : 1;
+    Ws w;
+    return carve_ws(w, nullptr, n_rays * S, (n_rays + chunk - 1) / chunk, true);
+}
+size_t dfp_points_workspace_bytes(int64_t n) {
+    if (n < 0) return 0;
+    Ws w;
+    return carve_ws(w, nullptr, n, 1, false);
+}
+
+int dfp_render_fwd(const DfpScene* sc, const float* params, const DfpRays* rays, const DfpCfg* cfg,
+                   const DfpRenderOut* out, void* workspace, size_t ws_bytes, void* stream) {
+    if (!rays || !cfg || !out || !params || !workspace) return fail(DFP_ERR_INVALID, "null argument");
+    int rc = check_scene(sc, cfg->stage);
+    if (rc) return rc;
+    if (rays->n_rays < 1) return fail(DFP_ERR_INVALID, "n_rays must be >= 1 (torch.max of an empty depth batch raises upstream too)");
+    if (!rays->rays_o || !rays->rays_d) return fail(DFP_ERR_INVALID, "rays are null");
+    if (!out->depth || !out->uncertainty || !out->color || !out->weight) return fail(DFP_ERR_INVALID, "output pointer is null");
+    SampleTables T;
+    if ((rc = fill_tables(cfg, T))) return rc;
+    const bool has_depth = rays->gt_depth != nullptr;
+    const int S = T.n_samples + (has_depth ? T.n_surface : 0);
+    const int64_t N = rays->n_rays, NS = N * S;
+    if (NS > 0x7fffffffLL) return fail(DFP_ERR_INVALID, "too many samples in one call (%lld)", (long long)NS);
+    const int64_t chunk = rays->chunk > 0 ? rays->chunk : N;
+    const int64_t nchunks = (N + chunk - 1) / chunk;
+    Ws w;
+    const size_t need = carve_ws(w, (char*)workspace, NS, nchunks, true);
+    if (need > ws_bytes) return fail(DFP_ERR_WORKSPACE, "workspace too small: need %zu bytes, have %zu", need, ws_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+
+    if (has_depth) {
+        k_depth_max<<<(unsigned)nchunks, 1024, 0, st>>>(rays->gt_depth, N, chunk, w.depthmax);
+        DFP_LAUNCH_CHECK("k_depth_max");
+    }
+    SampleArgs sa;
+    sa.rays_o = rays->rays_o; sa.rays_d = rays->rays_d; sa.gt = rays->gt_depth; sa.n_rays = N; sa.chunk = chunk;
+    sa.depthmax = w.depthmax; sa.z = w.z; sa.bound = to_bounds(sc->bound); sa.T = T;
+    const int rpb = 256 / S;
+    k_sample_z<<<(unsigned)((N + rpb - 1) / rpb), 256, 0, st>>>(sa);
+    DFP_LAUNCH_CHECK("k_sample_z");
+
+    PointSrc ps;
+    ps.rays_o = rays->rays_o; ps.rays_d = rays->rays_d; ps.z = w.z; ps.S = S; ps.pts = nullptr;
+    if ((rc = eval_samples_fwd<0>(sc, params, ps, NS, cfg->stage, 1, w, st))) return rc;
+
+    CompArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.n_rays = N; ca.S = S; ca.stage = cfg->stage; ca.z = w.z; ca.low = w.low; ca.fused = w.fused; ca.rgb4 = w.rgb;
+    ca.flags = w.flags; ca.w_attn = w.w_attn;
+    ca.depth = out->depth; ca.unc = out->uncertainty; ca.color = out->color; ca.weight = out->weight; ca.raw = out->raw;
+    k_composite_fwd<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(ca);
+    DFP_LAUNCH_CHECK("k_composite_fwd");
+    if (out->z_vals) DFP_CUDA(cudaMemcpyAsync(out->z_vals, w.z, NS * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return DFP_OK;
+}
+
+int dfp_render_bwd(const DfpScene* sc, const float* params, const DfpRays* rays, const DfpCfg* cfg,
+                   const DfpRenderOutGrad* og, const DfpGrads* g, void* workspace, size_t ws_bytes, void* stream) {
+    if (!rays || !cfg || !og || !g || !params || !workspace) return fail(DFP_ERR_INVALID, "null argument");
+    int rc = check_scene(sc, cfg->stage);
+    if (rc) return rc;
+    SampleTables T;
+    if ((rc = fill_tables(cfg, T))) return rc;
+    const bool has_depth = rays->gt_depth != nullptr;
+    const int S = T.n_samples + (has_depth ? T.n_surface : 0);
+    const int64_t N = rays->n_rays, NS = N * S;
+    if (N < 1) return fail(DFP_ERR_INVALID, "n_rays must be >= 1");
+    const int64_t chunk = rays->chunk > 0 ? rays->chunk : N;
+    Ws w;
+    const size_t need = carve_ws(w, (char*)workspace, NS, (N + chunk - 1) / chunk, true);
+    if (need > ws_bytes) return fail(DFP_ERR_WORKSPACE, "workspace too small: need %zu bytes, have %zu", need, ws_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool want_dp = g->rays_o || g->rays_d;
+
+    CompArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.n_rays = N; ca.S = S; ca.stage = cfg->stage; ca.z = w.z; ca.low = w.low; ca.fused = w.fused; ca.rgb4 = w.rgb;
+    ca.flags = w.flags; ca.w_attn = w.w_attn;
+    ca.g_depth = og->depth; ca.g_unc = og->uncertainty; ca.g_color = og->color; ca.g_weight = og->weight;
+    ca.d_low = w.d_low; ca.d_high = w.d_high; ca.d_fused = w.d_fused; ca.d_rgb4 = w.d_rgb; ca.dp = want_dp ? w.dp : nullptr;
+    k_composite_bwd<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(ca);
+    DFP_LAUNCH_CHECK("k_composite_bwd");
+
+    PointSrc ps;
+    ps.rays_o = rays->rays_o; ps.rays_d = rays->rays_d; ps.z = w.z; ps.S = S; ps.pts = nullptr;
+    if ((rc = eval_samples_bwd<0>(sc, params, ps, NS, cfg->stage, og->weight, g, want_dp, w, st))) return rc;
+    if (want_dp) {
+        k_ray_grad<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(N, S, w.dp, w.z, g->rays_o, g->rays_d);
+        DFP_LAUNCH_CHECK("k_ray_grad");
+    }
+    return DFP_OK;
+}
+
+int dfp_points_fwd(const DfpScene* sc, const float* params, const DfpPoints* pts, int32_t stage, float* raw, float* wout,
+                   void* workspace, size_t ws_bytes, void* stream) {
+    if (!pts || !params || !workspace || !raw) return fail(DFP_ERR_INVALID, "null argument");
+    int rc = check_scene(sc, stage);
+    if (rc) return rc;
+    if (pts->n < 1 || !pts->p) return fail(DFP_ERR_INVALID, "no points");
+    if (pts->n > 0x7fffffffLL) return fail(DFP_ERR_INVALID, "too many points in one call");
+    Ws w;
+    const size_t need = carve_ws(w, (char*)workspace, pts->n, 1, false);
+    if (need > ws_bytes) return fail(DFP_ERR_WORKSPACE, "workspace too small: need %zu bytes, have %zu", need, ws_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    PointSrc ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.pts = pts->p; ps.S = 1;
+    if (pts->is_f64) rc = eval_samples_fwd<1>(sc, params, ps, pts->n, stage, pts->apply_bound_mask, w, st);
+    else rc = eval_samples_fwd<2>(sc, params, ps, pts->n, stage, pts->apply_bound_mask, w, st);
+    if (rc) return rc;
+    PtsArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.n = pts->n; pa.stage = stage; pa.low = w.low; pa.fused = w.fused; pa.rgb4 = w.rgb; pa.flags = w.flags; pa.w_attn = w.w_attn;
+    pa.raw = raw; pa.w = wout;
+    k_points_finalize<<<(unsigned)((pts->n + 255) / 256), 256, 0, st>>>(pa);
+    DFP_LAUNCH_CHECK("k_points_finalize");
+    return DFP_OK;
+}
+
+int dfp_points_bwd(const DfpScene* sc, const float* params, const DfpPoints* pts, int32_t stage, const float* g_raw,
+                   const float* g_w, const DfpGrads* g, void* workspace, size_t ws_bytes, void* stream) {
+    if (!pts || !params || !workspace || !g) return fail(DFP_ERR_INVALID, "null argument");
+    int rc = check_scene(sc, stage);
+    if (rc) return rc;
+    if (pts->n < 1 || !pts->p) return fail(DFP_ERR_INVALID, "no points");
+    Ws w;
+    const size_t need = carve_ws(w, (char*)workspace, pts->n, 1, false);
+    if (need > ws_bytes) return fail(DFP_ERR_WORKSPACE, "workspace too small: need %zu bytes, have %zu", need, ws_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool want_dp = g->points != nullptr;
+    PtsArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.n = pts->n; pa.stage = stage; pa.flags = w.flags; pa.g_raw = g_raw; pa.g_w = g_w;
+    pa.d_low = w.d_low; pa.d_high = w.d_high; pa.d_fused = w.d_fused; pa.d_rgb4 = w.d_rgb; pa.dp = want_dp ? w.dp : nullptr;
+    k_points_seed_bwd<<<(unsigned)((pts->n + 255) / 256), 256, 0, st>>>(pa);
+    DFP_LAUNCH_CHECK("k_points_seed_bwd");
+    PointSrc ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.pts = pts->p; ps.S = 1;
+    if (pts->is_f64) rc = eval_samples_bwd<1>(sc, params, ps, pts->n, stage, g_w, g, want_dp, w, st);
+    else rc = eval_samples_bwd<2>(sc, params, ps, pts->n, stage, g_w, g, want_dp, w, st);
+    if (rc) return rc;
+    if (want_dp) {
+        const unsigned blocks = (unsigned)((3 * pts->n + 255) / 256);
+        if (pts->is_f64) k_points_grad_out<double><<<blocks, 256, 0, st>>>(pts->n, w.dp, (double*)g->points);
+        else k_points_grad_out<float><<<blocks, 256, 0, st>>>(pts->n, w.dp, (float*)g->points);
+        DFP_LAUNCH_CHECK("k_points_grad_out");
+    }
+    return DFP_OK;
+}
+
+int dfp_tsdf_sample(const DfpScene* sc, const DfpPoints* pts, float* out, void* stream) {
+    if (!sc || !pts || !out || !pts->p) return fail(DFP_ERR_INVALID, "null argument");
+    if (!sc->tsdf.data) return fail(DFP_ERR_INVALID, "tsdf volume is null");
+    if (pts->n < 1) return fail(DFP_ERR_INVALID, "no points");
+    PointSrc ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.pts = pts->p; ps.S = 1;
+    const unsigned blocks = (unsigned)((pts->n + 255) / 256);
+    if (pts->is_f64) k_tsdf_sample<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(ps, pts->n, to_bounds(sc->tsdf_bnds), sc->tsdf, out);
+    else k_tsdf_sample<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(ps, pts->n, to_bounds(sc->tsdf_bnds), sc->tsdf, out);
+    DFP_LAUNCH_CHECK("k_tsdf_sample");
+    return DFP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,180 @@
+/*
+ * dfprior_b200.h -- C ABI of libdfprior_b200.so
+ *
+ * B200-native (sm_100a) implementation of DF-Prior's per-ray volume-rendering
+ * hot path.  The reference (MachinePerceptionLab/Attentive_DFPrior) is pure
+ * Python/PyTorch and has no FFI layer of its own; its seam for this path is
+ * the set of Python call signatures cited beside each entry point below
+ * (paths relative to the reference checkout).  A binding only needs ctypes
+ * (see INTEGRATION.md); no torch types cross this boundary.
+ *
+ * Conventions
+ *  - every function returns 0 (DFP_OK) or a negative DfpStatus; nothing throws
+ *    or aborts across the boundary; dfp_last_error() gives a thread-local text.
+ *  - all buffers are caller-owned DEVICE pointers unless stated otherwise; the
+ *    library never allocates device memory and never synchronises the stream.
+ *  - kernels are enqueued on the caller's stream (cudaStream_t passed as void*).
+ *  - gradient buffers are ACCUMULATED INTO (caller zeroes them), so a caller
+ *    may chunk a batch over several calls.
+ *  - stateless and re-entrant: forward and backward may come from different
+ *    host threads (autograd engine thread).
+ */
+#ifndef DFPRIOR_B200_H
+#define DFPRIOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFP_ABI_VERSION 1
+
+#define DFP_C_DIM 32            /* configs/df_prior.yaml:102 (model.c_dim) */
+#define DFP_HIDDEN 32           /* src/conv_onet/models/decoder.py:278 */
+#define DFP_EMBED 93            /* decoder.py:129 */
+#define DFP_N_PARAM_TENSORS 79  /* DF.state_dict() */
+#define DFP_N_PARAMS 86029
+#define DFP_MAX_RAY_SAMPLES 64  /* N_samples + N_surface (32 + 16 in every shipped config) */
+
+typedef enum DfpStatus {
+    DFP_OK = 0,
+    DFP_ERR_INVALID = -1,      /* bad argument (null pointer, unsupported shape, ...) */
+    DFP_ERR_CUDA = -2,         /* a CUDA runtime call failed */
+    DFP_ERR_WORKSPACE = -3,    /* workspace too small */
+    DFP_ERR_UNSUPPORTED = -4   /* e.g. N_importance > 0 (dead + broken upstream, Renderer.py:235-252) */
+} DfpStatus;
+
+typedef enum DfpStage { DFP_STAGE_LOW = 0, DFP_STAGE_HIGH = 1, DFP_STAGE_COLOR = 2 } DfpStage;
+
+/* One feature grid.  Logical shape is the reference's [1, C, D, H, W]
+ * (src/DF_Prior.py:243-266) but memory is channels-last: element (z, y, x, c)
+ * lives at ((z*H + y)*W + x)*C + c, i.e. torch.channels_last_3d strides.
+ * dfp_grid_to_ndhwc() converts a channels-first grid. */
+typedef struct DfpGrid {
+    const float* data;
+    int32_t D, H, W, C;        /* C must be DFP_C_DIM */
+} DfpGrid;
+
+/* The fused TSDF prior volume, logical [1,1,D,H,W] = [.,.,Z,Y,X] with explicit
+ * element strides (the reference keeps a non-contiguous permuted view,
+ * get_tsdf.py:95-97). */
+typedef struct DfpTsdf {
+    const float* data;
+    int32_t D, H, W;
+    int64_t sD, sH, sW;
+} DfpTsdf;
+
+typedef struct DfpScene {
+    DfpGrid low, high, color;  /* c['grid_low'|'grid_high'|'grid_color'] */
+    DfpTsdf tsdf;
+    double bound[3][2];        /* slam.bound after rounding, src/DF_Prior.py:185-190 */
+    double tsdf_bnds[3][2];    /* slam.vol_bnds, src/DF_Prior.py:87 */
+} DfpScene;
+
+/* A batch of rays (Renderer.render_batch_ray arguments, src/utils/Renderer.py:110). */
+typedef struct DfpRays {
+    const float* rays_o;       /* [n_rays,3] f32 */
+    const float* rays_d;       /* [n_rays,3] f32 */
+    const float* gt_depth;     /* [n_rays] f32 or NULL (=> N_surface = 0, near = 0.01; Renderer.py:140-142) */
+    int64_t n_rays;
+    int64_t chunk;             /* rays per batch-global max(gt_depth) group: n_rays for one
+                                  render_batch_ray call, ray_batch_size (100000) for render_img
+                                  (Renderer.py:159,195,294-306); 0 means n_rays */
+} DfpRays;
+
+/* cfg['rendering'] (configs/df_prior.yaml:93-98).  The linspace tables are passed in from
+ * torch so that both sides use the very same constants (Renderer.py:183-184, 203). */
+typedef struct DfpCfg {
+    int32_t stage;             /* DfpStage */
+    int32_t n_samples;         /* N_samples (32) */
+    int32_t n_surface;         /* N_surface (16); ignored when gt_depth == NULL */
+    int32_t n_importance;      /* must be 0 */
+    float t_vals[DFP_MAX_RAY_SAMPLES];              /* linspace(0,1,N_samples) f32 */
+    float one_minus_t[DFP_MAX_RAY_SAMPLES];         /* 1 - t_vals, f32 */
+    double t_surf[DFP_MAX_RAY_SAMPLES];             /* linspace(0,1,N_surface) f32 -> f64 */
+    double one_minus_t_surf[DFP_MAX_RAY_SAMPLES];   /* 1 - t_surf, f64 */
+} DfpCfg;
+
+/* render_batch_ray return tuple (Renderer.py:255): depth, uncertainty, color, weight. */
+typedef struct DfpRenderOut {
+    double* depth;             /* [n_rays] f64 */
+    double* uncertainty;       /* [n_rays] f64 */
+    float* color;              /* [n_rays,3] f32 */
+    float* weight;             /* [n_rays,S] f32 attention weight (NOT the compositing weight) */
+    double* z_vals;            /* optional [n_rays,S] f64 sorted sample depths (parity checks); may be NULL */
+    float* raw;                /* optional [n_rays,S,4] f32 pre-sigmoid raw (parity checks); may be NULL */
+} DfpRenderOut;
+
+/* upstream gradients of the four outputs; any pointer may be NULL (= zero) */
+typedef struct DfpRenderOutGrad {
+    const double* depth;       /* [n_rays] */
+    const double* uncertainty; /* [n_rays] */
+    const float* color;        /* [n_rays,3] */
+    const float* weight;       /* [n_rays,S] */
+} DfpRenderOutGrad;
+
+/* gradient sinks; NULL = not needed (the kernels skip that work) */
+typedef struct DfpGrads {
+    float* grid_low;           /* NDHWC, same shape as the grid, accumulated */
+    float* grid_high;
+    float* grid_color;
+    float* params_packed;      /* packed layout (dfp_packed_param_floats() floats), accumulated */
+    float* rays_o;             /* [n_rays,3] f32, overwritten */
+    float* rays_d;             /* [n_rays,3] f32, overwritten */
+    void* points;              /* dfp_points_bwd only: [n,3] in the points' dtype, overwritten */
+} DfpGrads;
+
+/* A batch of query points (Renderer.eval_points / Mesher.eval_points / DF.forward). */
+typedef struct DfpPoints {
+    const void* p;             /* [n,3] */
+    int32_t is_f64;            /* 1: f64 (ray path), 0: f32 (Mesher grid points) */
+    int32_t apply_bound_mask;  /* 1: eval_points semantics (occ=100 outside bound, Renderer.py:51-64);
+                                  0: bare DF.forward (decoder.py:307-353) */
+    int64_t n;
+} DfpPoints;
+
+int dfp_abi_version(void);
+const char* dfp_last_error(void);
+
+/* ---- decoder parameters ------------------------------------------------------------
+ * The 79 tensors of DF.state_dict() in state_dict order (host array of device pointers)
+ * are gathered into one kernel-friendly packed buffer (k-major weights, padded rows);
+ * dfp_unpack_param_grads scatters a packed gradient back into a flat buffer holding
+ * the 79 gradients back to back in native [out,in] layout (DFP_N_PARAMS floats). */
+int64_t dfp_packed_param_floats(void);
+int dfp_pack_params(const float* const* tensors79, float* packed, void* stream);
+int dfp_unpack_param_grads(const float* packed_grad, float* native_flat, void* stream);
+
+/* channels-first [C,D,H,W] <-> channels-last [D,H,W,C] feature grid transposes */
+int dfp_grid_to_ndhwc(const float* src_cdhw, float* dst_dhwc, int32_t C, int32_t D, int32_t H, int32_t W, void* stream);
+int dfp_grid_to_cdhw(const float* src_dhwc, float* dst_cdhw, int32_t C, int32_t D, int32_t H, int32_t W, void* stream);
+
+/* ---- Renderer.render_batch_ray / render_img  (src/utils/Renderer.py:110-255, 258-327) ----
+ * The workspace written by the forward call is what the backward call reads; keep it
+ * alive (and unmodified) between the two. */
+size_t dfp_render_workspace_bytes(int64_t n_rays, int32_t samples_per_ray, int64_t chunk);
+int dfp_render_fwd(const DfpScene* scene, const float* params_packed, const DfpRays* rays, const DfpCfg* cfg,
+                   const DfpRenderOut* out, void* workspace, size_t workspace_bytes, void* stream);
+int dfp_render_bwd(const DfpScene* scene, const float* params_packed, const DfpRays* rays, const DfpCfg* cfg,
+                   const DfpRenderOutGrad* out_grad, const DfpGrads* grads,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Renderer.eval_points / Mesher.eval_points / DF.forward --------------------------
+ * (src/utils/Renderer.py:27-71, src/utils/Mesher.py:286-326, decoder.py:307-353)
+ * raw [n,4] f32, w [n] f32. */
+size_t dfp_points_workspace_bytes(int64_t n_points);
+int dfp_points_fwd(const DfpScene* scene, const float* params_packed, const DfpPoints* pts, int32_t stage,
+                   float* raw, float* w, void* workspace, size_t workspace_bytes, void* stream);
+int dfp_points_bwd(const DfpScene* scene, const float* params_packed, const DfpPoints* pts, int32_t stage,
+                   const float* grad_raw, const float* grad_w, const DfpGrads* grads,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Renderer.eval_points_tsdf / sample_grid_tsdf (Renderer.py:73-107) ---------------- */
+int dfp_tsdf_sample(const DfpScene* scene, const DfpPoints* pts, float* tsdf_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFPRIOR_B200_H */
