@@ -18,8 +18,7 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "../../include/dfprior_b200.h"
-#include "dfp_math.h"
+#include "dfp_device.cuh"
 
 namespace dfp {
 
@@ -28,7 +27,7 @@ namespace dfp {
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -46,12 +45,9 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(DFP_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
     } while (0)
 
-constexpr int NT = 256;            // threads per CTA of the per-sample kernels
-constexpr int WARPS = NT / 32;
-constexpr int SINK_FLOATS_PER_WARP = 32 * 32 + 32 * 33;
 
 static int g_num_sms = 0;
-static int num_sms() {
+int num_sms() {
     if (g_num_sms == 0) {
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) == cudaSuccess &&
@@ -63,52 +59,6 @@ static int num_sms() {
     return g_num_sms;
 }
 
-// ------------------------------------------------------------------------------------------
-// device-side argument blocks
-// ------------------------------------------------------------------------------------------
-struct PointSrc {                  // where sample s comes from
-    const float* rays_o;           // MODE 0: p = o + d * z[s], ray = s / S
-    const float* rays_d;
-    const double* z;
-    int S;
-    const void* pts;               // MODE 1: f64 [n,3]; MODE 2: f32 [n,3]
-};
-template <int MODE> struct PtT { using T = double; };
-template <> struct PtT<2> { using T = float; };
-
-template <int MODE>
-__device__ __forceinline__ void load_point(const PointSrc& ps, int64_t s, typename PtT<MODE>::T p[3]) {
-    if (MODE == 0) {
-        const int64_t r = s / ps.S;
-        const float o[3] = {ps.rays_o[3 * r], ps.rays_o[3 * r + 1], ps.rays_o[3 * r + 2]};
-        const float d[3] = {ps.rays_d[3 * r], ps.rays_d[3 * r + 1], ps.rays_d[3 * r + 2]};
-        double q[3];
-        ray_point(o, d, ps.z[s], q);
-        p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
-    } else if (MODE == 1) {
-        const double* q = reinterpret_cast<const double*>(ps.pts) + 3 * s;
-        p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
-    } else {
-        const float* q = reinterpret_cast<const float*>(ps.pts) + 3 * s;
-        p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
-    }
-}
-
-struct Bounds { double b[3][2]; };
-
-struct Ws {                        // per-sample workspace arrays (NS samples)
-    double* z;                     // [NS] sorted sample depths (render only)
-    float* depthmax;               // [nchunks][2]: max(gt_depth*1.2), max(gt_depth)
-    float* low; float* high; float* tsdf; float* fused; float* w_attn;   // [NS]
-    float* rgb;                    // [NS][4]  colour decoder output (rgb + its unused 4th channel)
-    int* flags;                    // [NS] bit0 in-bound, bit1 in TSDF band
-    int* band_list;                // [NS] compacted band sample ids
-    int* band_count;               // [4]
-    // backward scratch
-    float* d_low; float* d_high; float* d_fused;    // [NS]
-    float* d_rgb;                  // [NS][4]
-    float* dp;                     // [NS][3] gradient w.r.t. the sample point
-};
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -126,6 +76,7 @@ static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with
     w.dp = (float*)take(ns * 12);
     return off;
 }
+
 
 // ------------------------------------------------------------------------------------------
 // sampling kernels
@@ -236,330 +187,6 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs a) {
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// trilinear feature gather / scatter on a channels-last grid
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gather_features(const DfpGrid& g, const Tri& t, float* c) {
-    float acc[CDIM];
-#pragma unroll
-    for (int j = 0; j < CDIM; ++j) acc[j] = 0.f;
-#pragma unroll 1
-    for (int cn = 0; cn < 8; ++cn) {
-        int x, y, z;
-        if (!tri_corner(t, cn, g.W, g.H, g.D, x, y, z)) continue;      // index == size: skipped (GridSampler.cuh:225)
-        const float wgt = tri_weight(t, cn);
-        const float4* src = reinterpret_cast<const float4*>(g.data + (((int64_t)z * g.H + y) * g.W + x) * CDIM);
-#pragma unroll
-        for (int q = 0; q < CDIM / 4; ++q) {
-            const float4 v = __ldg(src + q);
-            acc[4 * q + 0] = fmaf(v.x, wgt, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(v.y, wgt, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(v.z, wgt, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(v.w, wgt, acc[4 * q + 3]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < CDIM; ++j) c[j] = acc[j];
-}
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-// grid-gradient scatter (dense zero-filled grid, vector reductions) and, optionally, the gradient
-// w.r.t. the normalised coordinates                                (ATen grid_sampler_3d backward)
-__device__ __forceinline__ void scatter_features(const DfpGrid& g, float* ggrid, const Tri& t, const float* d_c,
-                                                 bool want_coord, float gn[3]) {
-    float dc[CDIM];
-#pragma unroll
-    for (int j = 0; j < CDIM; ++j) dc[j] = d_c[j];
-    float gx = 0.f, gy = 0.f, gz = 0.f;
-#pragma unroll 1
-    for (int cn = 0; cn < 8; ++cn) {
-        int x, y, z;
-        if (!tri_corner(t, cn, g.W, g.H, g.D, x, y, z)) continue;
-        const int64_t off = (((int64_t)z * g.H + y) * g.W + x) * CDIM;
-        if (ggrid) {
-            const float wgt = tri_weight(t, cn);
-#pragma unroll
-            for (int q = 0; q < CDIM / 4; ++q)
-                red_add_v4(ggrid + off + 4 * q, dc[4 * q] * wgt, dc[4 * q + 1] * wgt, dc[4 * q + 2] * wgt, dc[4 * q + 3] * wgt);
-        }
-        if (want_coord) {
-            const float4* src = reinterpret_cast<const float4*>(g.data + off);
-            float dot = 0.f;
-#pragma unroll
-            for (int q = 0; q < CDIM / 4; ++q) {
-                const float4 v = __ldg(src + q);
-                dot = fmaf(v.x, dc[4 * q], dot); dot = fmaf(v.y, dc[4 * q + 1], dot);
-                dot = fmaf(v.z, dc[4 * q + 2], dot); dot = fmaf(v.w, dc[4 * q + 3], dot);
-            }
-            float dx, dy, dz;
-            tri_weight_grad(t, cn, dx, dy, dz);
-            gx = fmaf(dot, dx, gx); gy = fmaf(dot, dy, gy); gz = fmaf(dot, dz, gz);
-        }
-    }
-    gn[0] = gx * t.gx; gn[1] = gy * t.gy; gn[2] = gz * t.gz;
-}
-
-__device__ __forceinline__ void load_weights_to_smem(float* dst, const float* __restrict__ src, int nfloats) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int i = threadIdx.x; i < nfloats / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
-}
-
-// ------------------------------------------------------------------------------------------
-// decoder forward
-// ------------------------------------------------------------------------------------------
-struct DecArgs {
-    PointSrc ps; int64_t n; Bounds bound;
-    DfpGrid grid;            // this decoder's grid
-    DfpGrid grid_low;        // high decoder only: the low grid it concatenates (decoder.py:182-187)
-    const float* params;     // packed parameters (global)
-    float* out;              // DEC 0/1: [n]; DEC 2: [n][4]
-    // backward only
-    const float* dout;       // DEC 0/1: [n]; DEC 2: [n][4] (4th ignored)
-    float* ggrid;            // gradient of `grid` (NDHWC) or null
-    float* gparams;          // packed parameter gradient or null
-    float* dp;               // [n][3] accumulated, or null
-};
-
-template <int DEC, int MODE>
-__global__ void __launch_bounds__(NT) k_decoder_fwd(const DecArgs a) {
-    constexpr int CD = (DEC == 1) ? 64 : 32;
-    constexpr int NOUT = (DEC == 2) ? 4 : 1;
-    using PT = typename PtT<MODE>::T;
-    extern __shared__ float4 smem4[];
-    float* W = reinterpret_cast<float*>(smem4);
-    load_weights_to_smem(W, a.params + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR)), DecOff<CD>::SIZE);
-    __syncthreads();
-    const BoxT<PT> box = make_box<PT>(a.bound.b);
-    for (int64_t base = (int64_t)blockIdx.x * NT; base < a.n; base += (int64_t)gridDim.x * NT) {
-        const int64_t s = base + threadIdx.x;
-        if (s >= a.n) continue;
-        PT p[3];
-        load_point<MODE>(a.ps, s, p);
-        float xn[3];
-        normalize(p, box, xn);
-        float c[CD];
-        gather_features(a.grid, tri_setup(xn, a.grid.W, a.grid.H, a.grid.D), c);
-        if (DEC == 1) gather_features(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), c + CDIM);
-        const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};       // p.float()   decoder.py:189
-        float out[NOUT];
-        decoder_fwd_thread<CD, NOUT, false>(W, pf, c, out, nullptr);
-        if (NOUT == 1) a.out[s] = out[0];
-        else *reinterpret_cast<float4*>(a.out + 4 * s) = make_float4(out[0], out[NOUT > 1 ? 1 : 0], out[NOUT > 2 ? 2 : 0], out[NOUT > 3 ? 3 : 0]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// warp-cooperative parameter-gradient sink: every lane holds one sample's (a, d) pair; the warp
-// forms sum_samples a[k]*d[j] through a shared-memory transpose and issues one coalesced
-// reduction per (k, 32 j) row.
-// ------------------------------------------------------------------------------------------
-struct WarpSink {
-    float* g;        // packed parameter gradient (global)
-    float* As;       // [32][32]  As[kk*32 + sample]
-    float* Dt;       // [32][33]  Dt[sample*33 + j]
-    int lane;
-
-    __device__ __forceinline__ void stage_d(const float (&d)[32]) {
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) Dt[lane * 33 + j] = d[j];
-    }
-    template <int KB>
-    __device__ __forceinline__ void block(int woff, int ld, const float* a, int k0, int K) {
-#pragma unroll
-        for (int kk = 0; kk < KB; ++kk) As[kk * 32 + lane] = (k0 + kk < K) ? a[k0 + kk] : 0.f;
-        __syncwarp();
-        float acc[KB];
-#pragma unroll
-        for (int kk = 0; kk < KB; ++kk) acc[kk] = 0.f;
-#pragma unroll 2
-        for (int m = 0; m < 32; m += 4) {
-            const float d0 = Dt[(m + 0) * 33 + lane], d1 = Dt[(m + 1) * 33 + lane];
-            const float d2 = Dt[(m + 2) * 33 + lane], d3 = Dt[(m + 3) * 33 + lane];
-#pragma unroll
-            for (int kk = 0; kk < KB; ++kk) {
-                const float4 a4 = *reinterpret_cast<const float4*>(As + kk * 32 + m);
-                acc[kk] = fmaf(a4.x, d0, fmaf(a4.y, d1, fmaf(a4.z, d2, fmaf(a4.w, d3, acc[kk]))));
-            }
-        }
-#pragma unroll
-        for (int kk = 0; kk < KB; ++kk)
-            if (k0 + kk < K) atomicAdd(g + woff + (k0 + kk) * ld + lane, acc[kk]);
-        __syncwarp();
-    }
-    __device__ __forceinline__ void bias_from_staged(int boff) {
-        float s = 0.f;
-#pragma unroll 8
-        for (int m = 0; m < 32; ++m) s += Dt[m * 33 + lane];
-        atomicAdd(g + boff + lane, s);
-    }
-    __device__ __forceinline__ void outer32(int woff, int ld, const float* a, int K, const float (&d)[32], int boff) {
-        stage_d(d);
-        for (int k0 = 0; k0 < K; k0 += 32) block<32>(woff, ld, a, k0, K);
-        if (boff >= 0) bias_from_staged(boff);
-    }
-    __device__ __forceinline__ void outer4(int woff, int ld, const float* a, int K, const float (&d)[32]) {
-        stage_d(d);
-        block<4>(woff, ld, a, 0, K);
-    }
-    __device__ __forceinline__ void bias32(int boff, const float (&d)[32]) {
-        stage_d(d);
-        __syncwarp();
-        bias_from_staged(boff);
-    }
-    __device__ __forceinline__ void scalar(int off, float v) {
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) atomicAdd(g + off, v);
-    }
-};
-
-// ------------------------------------------------------------------------------------------
-// decoder backward: recompute the forward with saved activations, back-propagate
-// ------------------------------------------------------------------------------------------
-template <int DEC, int MODE, bool WANT_PARAMS>
-__global__ void __launch_bounds__(NT) k_decoder_bwd(const DecArgs a) {
-    constexpr int CD = (DEC == 1) ? 64 : 32;
-    constexpr int NOUT = (DEC == 2) ? 4 : 1;
-    using PT = typename PtT<MODE>::T;
-    using L = DecOff<CD>;
-    extern __shared__ float4 smem4[];
-    float* W = reinterpret_cast<float*>(smem4);
-    constexpr int gbase = (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR));
-    load_weights_to_smem(W, a.params + gbase, L::SIZE);
-    WarpSink sink;
-    sink.lane = threadIdx.x & 31;
-    sink.g = a.gparams;
-    sink.As = W + L::SIZE + (threadIdx.x >> 5) * SINK_FLOATS_PER_WARP;
-    sink.Dt = sink.As + 32 * 32;
-    __syncthreads();
-    const BoxT<PT> box = make_box<PT>(a.bound.b);
-    for (int64_t base = (int64_t)blockIdx.x * NT; base < a.n; base += (int64_t)gridDim.x * NT) {
-        const int64_t s_raw = base + threadIdx.x;
-        const bool valid = s_raw < a.n;
-        const int64_t s = valid ? s_raw : a.n - 1;          // keep the whole warp in the cooperative sink
-        float dout[NOUT];
-        if (NOUT == 1) dout[0] = valid ? a.dout[s] : 0.f;
-        else {
-            const float4 v = *reinterpret_cast<const float4*>(a.dout + 4 * s);
-            dout[0] = valid ? v.x : 0.f; dout[NOUT > 1 ? 1 : 0] = valid ? v.y : 0.f; dout[NOUT > 2 ? 2 : 0] = valid ? v.z : 0.f;
-            dout[NOUT > 3 ? 3 : 0] = 0.f;                   // colour decoder's 4th output is overwritten (decoder.py:352)
-        }
-        bool any = false;
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) any = any || (dout[o] != 0.f);
-        if (!__any_sync(0xffffffffu, any)) continue;         // nothing flows into this warp's samples
-        PT p[3];
-        load_point<MODE>(a.ps, s, p);
-        float xn[3];
-        normalize(p, box, xn);
-        const Tri tri = tri_setup(xn, a.grid.W, a.grid.H, a.grid.D);
-        float c[CD];
-        gather_features(a.grid, tri, c);
-        if (DEC == 1) gather_features(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), c + CDIM);
-        const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
-        DecState st;
-        float out[NOUT];
-        decoder_fwd_thread<CD, NOUT, true>(W, pf, c, out, &st);
-        float d_c[CD];
-        float dpe[3] = {0.f, 0.f, 0.f};
-        decoder_bwd_thread<CD, NOUT, WANT_PARAMS>(W, gbase, pf, c, st, dout, d_c, dpe, sink);
-        if (valid && any) {
-            const bool want_coord = a.dp != nullptr;
-            float gn[3] = {0.f, 0.f, 0.f};
-            if (a.ggrid || want_coord) scatter_features(a.grid, a.ggrid, tri, d_c, want_coord, gn);
-            if (want_coord) {
-                // d p = d xn * 2/(b1-b0)  (common.py:287-289)  +  embedding path (decoder.py:189-191)
-                a.dp[3 * s + 0] += gn[0] * (float)(2.0 / (a.bound.b[0][1] - a.bound.b[0][0])) + dpe[0];
-                a.dp[3 * s + 1] += gn[1] * (float)(2.0 / (a.bound.b[1][1] - a.bound.b[1][0])) + dpe[1];
-                a.dp[3 * s + 2] += gn[2] * (float)(2.0 / (a.bound.b[2][1] - a.bound.b[2][0])) + dpe[2];
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// attentive fusion over the compacted band list
-// ------------------------------------------------------------------------------------------
-struct AttArgs {
-    const float* params; const int* band_list; const int* band_count;
-    const float* low; const float* high; const float* tsdf;
-    float* fused; float* w_attn;
-    // backward
-    PointSrc ps; Bounds tsdf_bnds; DfpTsdf vol;
-    const float* d_fused; const float* g_w; float* d_low; float* d_high; float* dp; float* gparams;
-};
-
-__global__ void __launch_bounds__(NT) k_attn_fwd(const AttArgs a) {
-    extern __shared__ float4 smem4[];
-    float* A = reinterpret_cast<float*>(smem4);
-    load_weights_to_smem(A, a.params + OFF_ATT, AttOff::SIZE);
-    __syncthreads();
-    const int count = *a.band_count;
-    for (int i = blockIdx.x * NT + threadIdx.x; i < count; i += gridDim.x * NT) {
-        const int s = a.band_list[i];
-        const float x0 = a.high[s] + a.low[s];                         // decoder.py:326,343
-        const float x1 = tsdf_logit(a.tsdf[s]).inv;
-        AttState st;
-        float w;
-        const float f = attention_fwd_thread(A, x0, x1, w, st);
-        a.fused[s] = f;
-        a.w_attn[s] = w;
-    }
-}
-
-template <int MODE, bool WANT_PARAMS>
-__global__ void __launch_bounds__(NT) k_attn_bwd(const AttArgs a) {
-    using PT = typename PtT<MODE>::T;
-    extern __shared__ float4 smem4[];
-    float* A = reinterpret_cast<float*>(smem4);
-    load_weights_to_smem(A, a.params + OFF_ATT, AttOff::SIZE);
-    WarpSink sink;
-    sink.lane = threadIdx.x & 31;
-    sink.g = a.gparams;
-    sink.As = A + AttOff::SIZE + (threadIdx.x >> 5) * SINK_FLOATS_PER_WARP;
-    sink.Dt = sink.As + 32 * 32;
-    __syncthreads();
-    const int count = *a.band_count;
-    const BoxT<PT> tbox = make_box<PT>(a.tsdf_bnds.b);
-    for (int base = blockIdx.x * NT; base < count; base += gridDim.x * NT) {
-        const int i = base + threadIdx.x;
-        const bool valid = i < count;
-        const int s = a.band_list[valid ? i : count - 1];
-        const float g_out = valid ? a.d_fused[s] : 0.f;
-        const float g_w = (valid && a.g_w) ? a.g_w[s] : 0.f;
-        const bool any = (g_out != 0.f) || (g_w != 0.f);
-        if (!__any_sync(0xffffffffu, any)) continue;
-        const float x0 = a.high[s] + a.low[s];
-        const AttLogit lg = tsdf_logit(a.tsdf[s]);
-        AttState st;
-        float w;
-        attention_fwd_thread(A, x0, lg.inv, w, st);
-        float dx0, dx1;
-        attention_bwd_thread<WANT_PARAMS>(A, OFF_ATT, x0, lg.inv, st, g_out, g_w, dx0, dx1, sink);
-        if (valid) {
-            a.d_low[s] = dx0;                                          // low_occ enters only through high+low on band points
-            a.d_high[s] = dx0;
-            if (a.dp) {
-                const float dt = dx1 * lg.dinv_dtsdf;                  // gradient into the TSDF value gathered at p (decoder.py:241)
-                if (dt != 0.f) {
-                    PT p[3];
-                    load_point<MODE>(a.ps, s, p);
-                    float xn[3];
-                    normalize(p, tbox, xn);
-                    const Tri t = tri_setup(xn, a.vol.W, a.vol.H, a.vol.D);
-                    float gn[3];
-                    tsdf_interp_grad(a.vol.data, a.vol.sD, a.vol.sH, a.vol.sW, a.vol.W, a.vol.H, a.vol.D, t, gn);
-                    for (int k = 0; k < 3; ++k)
-                        a.dp[3 * (int64_t)s + k] += dt * gn[k] * (float)(2.0 / (a.tsdf_bnds.b[k][1] - a.tsdf_bnds.b[k][0]));
-                }
-            }
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------
 // stage select + compositing
@@ -728,6 +355,7 @@ __global__ void k_transpose_c_v(const float* __restrict__ src, float* __restrict
     }
 }
 
+
 // ------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ------------------------------------------------------------------------------------------
@@ -749,54 +377,6 @@ static int check_scene(const DfpScene* sc, int stage) {
     }
     for (int k = 0; k < 3; ++k)
         if (!(sc->bound[k][1] > sc->bound[k][0])) return fail(DFP_ERR_INVALID, "bound axis %d is empty", k);
-    return DFP_OK;
-}
-
-template <typename K>
-static int set_smem(K kernel, size_t bytes) {
-    DFP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return DFP_OK;
-}
-
-static int grid_for(int64_t n, int per_block, int max_blocks) {
-    int64_t b = (n + per_block - 1) / per_block;
-    if (b < 1) b = 1;
-    if (b > max_blocks) b = max_blocks;
-    return (int)b;
-}
-
-static Bounds to_bounds(const double b[3][2]) {
-    Bounds r;
-    memcpy(r.b, b, sizeof(r.b));
-    return r;
-}
-
-template <int DEC, int MODE>
-static int launch_decoder_fwd(const DecArgs& a, cudaStream_t st) {
-    constexpr int CD = (DEC == 1) ? 64 : 32;
-    const size_t smem = DecOff<CD>::SIZE * sizeof(float);
-    int rc = set_smem(k_decoder_fwd<DEC, MODE>, smem);
-    if (rc) return rc;
-    const int blocks = grid_for(a.n, NT, 2 * num_sms());
-    k_decoder_fwd<DEC, MODE><<<blocks, NT, smem, st>>>(a);
-    DFP_LAUNCH_CHECK("k_decoder_fwd");
-    return DFP_OK;
-}
-template <int DEC, int MODE>
-static int launch_decoder_bwd(const DecArgs& a, cudaStream_t st) {
-    constexpr int CD = (DEC == 1) ? 64 : 32;
-    const size_t smem = (DecOff<CD>::SIZE + WARPS * SINK_FLOATS_PER_WARP) * sizeof(float);
-    const int blocks = grid_for(a.n, NT, num_sms());
-    if (a.gparams) {
-        int rc = set_smem(k_decoder_bwd<DEC, MODE, true>, smem);
-        if (rc) return rc;
-        k_decoder_bwd<DEC, MODE, true><<<blocks, NT, smem, st>>>(a);
-    } else {
-        int rc = set_smem(k_decoder_bwd<DEC, MODE, false>, smem);
-        if (rc) return rc;
-        k_decoder_bwd<DEC, MODE, false><<<blocks, NT, smem, st>>>(a);
-    }
-    DFP_LAUNCH_CHECK("k_decoder_bwd");
     return DFP_OK;
 }
 
@@ -832,10 +412,7 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
         memset(&aa, 0, sizeof(aa));
         aa.params = params; aa.band_list = w.band_list; aa.band_count = w.band_count;
         aa.low = w.low; aa.high = w.high; aa.tsdf = w.tsdf; aa.fused = w.fused; aa.w_attn = w.w_attn;
-        const size_t smem = AttOff::SIZE * sizeof(float);
-        if ((rc = set_smem(k_attn_fwd, smem))) return rc;
-        k_attn_fwd<<<grid_for(n, NT, num_sms()), NT, smem, st>>>(aa);
-        DFP_LAUNCH_CHECK("k_attn_fwd");
+        if ((rc = launch_attn_fwd(aa, n, st))) return rc;
     }
     return DFP_OK;
 }
@@ -854,16 +431,7 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
         aa.ps = ps; aa.tsdf_bnds = to_bounds(sc->tsdf_bnds); aa.vol = sc->tsdf;
         aa.d_fused = w.d_fused; aa.g_w = g_w; aa.d_low = w.d_low; aa.d_high = w.d_high;
         aa.dp = want_dp ? w.dp : nullptr; aa.gparams = g->params_packed;
-        const size_t smem = (AttOff::SIZE + WARPS * SINK_FLOATS_PER_WARP) * sizeof(float);
-        const int blocks = grid_for(n, NT, num_sms());
-        if (g->params_packed) {
-            if ((rc = set_smem(k_attn_bwd<MODE, true>, smem))) return rc;
-            k_attn_bwd<MODE, true><<<blocks, NT, smem, st>>>(aa);
-        } else {
-            if ((rc = set_smem(k_attn_bwd<MODE, false>, smem))) return rc;
-            k_attn_bwd<MODE, false><<<blocks, NT, smem, st>>>(aa);
-        }
-        DFP_LAUNCH_CHECK("k_attn_bwd");
+        if ((rc = launch_attn_bwd<MODE>(aa, n, st))) return rc;
     }
     DecArgs da;
     memset(&da, 0, sizeof(da));
@@ -891,6 +459,7 @@ static int fill_tables(const DfpCfg* cfg, SampleTables& T) {
     memcpy(T.ts, cfg->t_surf, sizeof(T.ts)); memcpy(T.omts, cfg->one_minus_t_surf, sizeof(T.omts));
     return DFP_OK;
 }
+
 
 }  // namespace dfp
 

@@ -1,0 +1,274 @@
+// Internal header shared by the translation units of libdfprior_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/dfprior_b200.h"
+#include "dfp_math.h"
+
+namespace dfp {
+
+// ---- error plumbing (defined in dfp_api.cu)
+int fail(int code, const char* fmt, ...);
+#define DFP_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(DFP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define DFP_LAUNCH_CHECK(name)                                                                              \
+    do {                                                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                                                \
+        if (e_ != cudaSuccess) return fail(DFP_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+int num_sms();
+
+constexpr int NT = 256;            // threads per CTA of the per-sample kernels
+constexpr int WARPS = NT / 32;
+constexpr int SINK_FLOATS_PER_WARP = 32 * 32 + 32 * 33;
+
+// ------------------------------------------------------------------------------------------
+// device-side argument blocks
+// ------------------------------------------------------------------------------------------
+struct PointSrc {                  // where sample s comes from
+    const float* rays_o;           // MODE 0: p = o + d * z[s], ray = s / S
+    const float* rays_d;
+    const double* z;
+    int S;
+    const void* pts;               // MODE 1: f64 [n,3]; MODE 2: f32 [n,3]
+};
+template <int MODE> struct PtT { using T = double; };
+template <> struct PtT<2> { using T = float; };
+
+template <int MODE>
+__device__ __forceinline__ void load_point(const PointSrc& ps, int64_t s, typename PtT<MODE>::T p[3]) {
+    if (MODE == 0) {
+        const int64_t r = s / ps.S;
+        const float o[3] = {ps.rays_o[3 * r], ps.rays_o[3 * r + 1], ps.rays_o[3 * r + 2]};
+        const float d[3] = {ps.rays_d[3 * r], ps.rays_d[3 * r + 1], ps.rays_d[3 * r + 2]};
+        double q[3];
+        ray_point(o, d, ps.z[s], q);
+        p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
+    } else if (MODE == 1) {
+        const double* q = reinterpret_cast<const double*>(ps.pts) + 3 * s;
+        p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
+    } else {
+        const float* q = reinterpret_cast<const float*>(ps.pts) + 3 * s;
+        p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
+    }
+}
+
+struct Bounds { double b[3][2]; };
+
+struct Ws {                        // per-sample workspace arrays (NS samples)
+    double* z;                     // [NS] sorted sample depths (render only)
+    float* depthmax;               // [nchunks][2]: max(gt_depth*1.2), max(gt_depth)
+    float* low; float* high; float* tsdf; float* fused; float* w_attn;   // [NS]
+    float* rgb;                    // [NS][4]  colour decoder output (rgb + its unused 4th channel)
+    int* flags;                    // [NS] bit0 in-bound, bit1 in TSDF band
+    int* band_list;                // [NS] compacted band sample ids
+    int* band_count;               // [4]
+    // backward scratch
+    float* d_low; float* d_high; float* d_fused;    // [NS]
+    float* d_rgb;                  // [NS][4]
+    float* dp;                     // [NS][3] gradient w.r.t. the sample point
+};
+
+
+// ------------------------------------------------------------------------------------------
+// trilinear feature gather / scatter on a channels-last grid
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gather_features(const DfpGrid& g, const Tri& t, float* c) {
+    float acc[CDIM];
+#pragma unroll
+    for (int j = 0; j < CDIM; ++j) acc[j] = 0.f;
+#pragma unroll 1
+    for (int cn = 0; cn < 8; ++cn) {
+        int x, y, z;
+        if (!tri_corner(t, cn, g.W, g.H, g.D, x, y, z)) continue;      // index == size: skipped (GridSampler.cuh:225)
+        const float wgt = tri_weight(t, cn);
+        const float4* src = reinterpret_cast<const float4*>(g.data + (((int64_t)z * g.H + y) * g.W + x) * CDIM);
+#pragma unroll
+        for (int q = 0; q < CDIM / 4; ++q) {
+            const float4 v = __ldg(src + q);
+            acc[4 * q + 0] = fmaf(v.x, wgt, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(v.y, wgt, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v.z, wgt, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v.w, wgt, acc[4 * q + 3]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CDIM; ++j) c[j] = acc[j];
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// grid-gradient scatter (dense zero-filled grid, vector reductions) and, optionally, the gradient
+// w.r.t. the normalised coordinates                                (ATen grid_sampler_3d backward)
+__device__ __forceinline__ void scatter_features(const DfpGrid& g, float* ggrid, const Tri& t, const float* d_c,
+                                                 bool want_coord, float gn[3]) {
+    float dc[CDIM];
+#pragma unroll
+    for (int j = 0; j < CDIM; ++j) dc[j] = d_c[j];
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll 1
+    for (int cn = 0; cn < 8; ++cn) {
+        int x, y, z;
+        if (!tri_corner(t, cn, g.W, g.H, g.D, x, y, z)) continue;
+        const int64_t off = (((int64_t)z * g.H + y) * g.W + x) * CDIM;
+        if (ggrid) {
+            const float wgt = tri_weight(t, cn);
+#pragma unroll
+            for (int q = 0; q < CDIM / 4; ++q)
+                red_add_v4(ggrid + off + 4 * q, dc[4 * q] * wgt, dc[4 * q + 1] * wgt, dc[4 * q + 2] * wgt, dc[4 * q + 3] * wgt);
+        }
+        if (want_coord) {
+            const float4* src = reinterpret_cast<const float4*>(g.data + off);
+            float dot = 0.f;
+#pragma unroll
+            for (int q = 0; q < CDIM / 4; ++q) {
+                const float4 v = __ldg(src + q);
+                dot = fmaf(v.x, dc[4 * q], dot); dot = fmaf(v.y, dc[4 * q + 1], dot);
+                dot = fmaf(v.z, dc[4 * q + 2], dot); dot = fmaf(v.w, dc[4 * q + 3], dot);
+            }
+            float dx, dy, dz;
+            tri_weight_grad(t, cn, dx, dy, dz);
+            gx = fmaf(dot, dx, gx); gy = fmaf(dot, dy, gy); gz = fmaf(dot, dz, gz);
+        }
+    }
+    gn[0] = gx * t.gx; gn[1] = gy * t.gy; gn[2] = gz * t.gz;
+}
+
+__device__ __forceinline__ void load_weights_to_smem(float* dst, const float* __restrict__ src, int nfloats) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = threadIdx.x; i < nfloats / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// decoder forward
+// ------------------------------------------------------------------------------------------
+struct DecArgs {
+    PointSrc ps; int64_t n; Bounds bound;
+    DfpGrid grid;            // this decoder's grid
+    DfpGrid grid_low;        // high decoder only: the low grid it concatenates (decoder.py:182-187)
+    const float* params;     // packed parameters (global)
+    float* out;              // DEC 0/1: [n]; DEC 2: [n][4]
+    // backward only
+    const float* dout;       // DEC 0/1: [n]; DEC 2: [n][4] (4th ignored)
+    float* ggrid;            // gradient of `grid` (NDHWC) or null
+    float* gparams;          // packed parameter gradient or null
+    float* dp;               // [n][3] accumulated, or null
+};
+
+
+// ------------------------------------------------------------------------------------------
+// attentive fusion over the compacted band list
+// ------------------------------------------------------------------------------------------
+struct AttArgs {
+    const float* params; const int* band_list; const int* band_count;
+    const float* low; const float* high; const float* tsdf;
+    float* fused; float* w_attn;
+    // backward
+    PointSrc ps; Bounds tsdf_bnds; DfpTsdf vol;
+    const float* d_fused; const float* g_w; float* d_low; float* d_high; float* dp; float* gparams;
+};
+
+
+// ------------------------------------------------------------------------------------------
+// warp-cooperative parameter-gradient sink: every lane holds one sample's (a, d) pair; the warp
+// forms sum_samples a[k]*d[j] through a shared-memory transpose and issues one coalesced
+// reduction per (k, 32 j) row.
+// ------------------------------------------------------------------------------------------
+struct WarpSink {
+    float* g;        // packed parameter gradient (global)
+    float* As;       // [32][32]  As[kk*32 + sample]
+    float* Dt;       // [32][33]  Dt[sample*33 + j]
+    int lane;
+
+    __device__ __forceinline__ void stage_d(const float (&d)[32]) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) Dt[lane * 33 + j] = d[j];
+    }
+    template <int KB>
+    __device__ __forceinline__ void block(int woff, int ld, const float* a, int k0, int K) {
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) As[kk * 32 + lane] = (k0 + kk < K) ? a[k0 + kk] : 0.f;
+        __syncwarp();
+        float acc[KB];
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) acc[kk] = 0.f;
+#pragma unroll 2
+        for (int m = 0; m < 32; m += 4) {
+            const float d0 = Dt[(m + 0) * 33 + lane], d1 = Dt[(m + 1) * 33 + lane];
+            const float d2 = Dt[(m + 2) * 33 + lane], d3 = Dt[(m + 3) * 33 + lane];
+#pragma unroll
+            for (int kk = 0; kk < KB; ++kk) {
+                const float4 a4 = *reinterpret_cast<const float4*>(As + kk * 32 + m);
+                acc[kk] = fmaf(a4.x, d0, fmaf(a4.y, d1, fmaf(a4.z, d2, fmaf(a4.w, d3, acc[kk]))));
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk)
+            if (k0 + kk < K) atomicAdd(g + woff + (k0 + kk) * ld + lane, acc[kk]);
+        __syncwarp();
+    }
+    __device__ __forceinline__ void bias_from_staged(int boff) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int m = 0; m < 32; ++m) s += Dt[m * 33 + lane];
+        atomicAdd(g + boff + lane, s);
+    }
+    __device__ __forceinline__ void outer32(int woff, int ld, const float* a, int K, const float (&d)[32], int boff) {
+        stage_d(d);
+        for (int k0 = 0; k0 < K; k0 += 32) block<32>(woff, ld, a, k0, K);
+        if (boff >= 0) bias_from_staged(boff);
+    }
+    __device__ __forceinline__ void outer4(int woff, int ld, const float* a, int K, const float (&d)[32]) {
+        stage_d(d);
+        block<4>(woff, ld, a, 0, K);
+    }
+    __device__ __forceinline__ void bias32(int boff, const float (&d)[32]) {
+        stage_d(d);
+        __syncwarp();
+        bias_from_staged(boff);
+    }
+    __device__ __forceinline__ void scalar(int off, float v) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(g + off, v);
+    }
+};
+
+
+template <typename K>
+inline int set_smem(K kernel, size_t bytes) {
+    DFP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return DFP_OK;
+}
+
+inline int grid_for(int64_t n, int per_block, int max_blocks) {
+    int64_t b = (n + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+inline Bounds to_bounds(const double b[3][2]) {
+    Bounds r;
+    memcpy(r.b, b, sizeof(r.b));
+    return r;
+}
+
+
+// launchers defined in the per-kernel translation units
+template <int DEC, int MODE> int launch_decoder_fwd(const DecArgs& a, cudaStream_t st);
+template <int DEC, int MODE> int launch_decoder_bwd(const DecArgs& a, cudaStream_t st);
+int launch_attn_fwd(const AttArgs& a, int64_t n, cudaStream_t st);
+template <int MODE> int launch_attn_bwd(const AttArgs& a, int64_t n, cudaStream_t st);
+
+}  // namespace dfp

@@ -1,0 +1,352 @@
+"""autograd glue between PyTorch tensors and the C ABI (include/dfprior_b200.h).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; all arithmetic of
+the hot path happens in libdfprior_b200.so.  Differentiable inputs: the three feature grids,
+the 79 decoder tensors, ``rays_o`` / ``rays_d`` (or the query points).  ``tsdf_volume``, bounds
+and ``gt_depth`` never receive gradients.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+
+GRID_KEYS = ("grid_low", "grid_high", "grid_color")
+
+
+# ----------------------------------------------------------------------------------------
+# small caches (all keyed on data_ptr + version so in-place optimiser updates invalidate them)
+# ----------------------------------------------------------------------------------------
+class _BoundsCache:
+    """[3,2] bound tensors -> python floats without a device sync on every call."""
+
+    def __init__(self):
+        self.d = {}
+
+    def get(self, t: torch.Tensor):
+        key = (t.data_ptr(), t._version, str(t.device))
+        v = self.d.get(key)
+        if v is None:
+            if len(self.d) > 64:
+                self.d.clear()
+            v = t.detach().to("cpu").double().reshape(3, 2).tolist()
+            self.d[key] = v
+        return v
+
+
+_bounds = _BoundsCache()
+_tables = {}
+
+
+def _cfg_struct(stage: str, n_samples: int, n_surface: int, n_importance: int = 0) -> L.DfpCfg:
+    key = (n_samples, n_surface)
+    tab = _tables.get(key)
+    if tab is None:
+        tv = torch.linspace(0., 1., steps=n_samples)                       # Renderer.py:203
+        ts = torch.linspace(0., 1., steps=max(n_surface, 1)).double()      # Renderer.py:183-184
+        tab = (tv.tolist(), (1. - tv).tolist(), ts.tolist(), (1. - ts).tolist())
+        _tables[key] = tab
+    cfg = L.DfpCfg()
+    cfg.stage = L.STAGES[stage]
+    cfg.n_samples, cfg.n_surface, cfg.n_importance = n_samples, n_surface, n_importance
+    for i in range(n_samples):
+        cfg.t_vals[i] = tab[0][i]
+        cfg.one_minus_t[i] = tab[1][i]
+    for i in range(n_surface):
+        cfg.t_surf[i] = tab[2][i]
+        cfg.one_minus_t_surf[i] = tab[3][i]
+    return cfg
+
+
+def _is_ndhwc(g: torch.Tensor) -> bool:
+    return g.dim() == 5 and g.shape[0] == 1 and g.is_contiguous(memory_format=torch.channels_last_3d)
+
+
+def _grid_ndhwc(g: torch.Tensor) -> torch.Tensor:
+    """Return a tensor whose memory is [D,H,W,C] for the logical [1,C,D,H,W] grid ``g``.
+
+    Grids allocated with ``memory_format=torch.channels_last_3d`` are used in place (the fast path
+    INTEGRATION.md recommends); channels-first grids are transposed by dfp_grid_to_ndhwc."""
+    if g.dtype != torch.float32 or g.dim() != 5 or g.shape[0] != 1:
+        raise ValueError("feature grids must be float32 [1,C,D,H,W]")
+    gd = g.detach()
+    if _is_ndhwc(gd):
+        return gd
+    src = gd.contiguous()
+    _, Cc, D, H, W = src.shape
+    dst = torch.empty((1, Cc, D, H, W), device=g.device, dtype=torch.float32,
+                      memory_format=torch.channels_last_3d)
+    L.check(L.lib().dfp_grid_to_ndhwc(src.data_ptr(), dst.data_ptr(), Cc, D, H, W,
+                                      torch.cuda.current_stream().cuda_stream))
+    return dst
+
+
+def _scene_struct(grids_cl: Dict[str, Optional[torch.Tensor]], tsdf_volume, tsdf_bnds, bound) -> L.DfpScene:
+    sc = L.DfpScene()
+    for key in GRID_KEYS:
+        g = grids_cl.get(key)
+        if g is None:
+            continue
+        s = getattr(sc, key[5:])
+        s.data = g.data_ptr()
+        s.C, s.D, s.H, s.W = g.shape[1], g.shape[2], g.shape[3], g.shape[4]
+    if tsdf_volume is not None:
+        if tsdf_volume.dtype != torch.float32 or tsdf_volume.dim() != 5:
+            raise ValueError("tsdf_volume must be float32 [1,1,Z,Y,X]")
+        sc.tsdf.data = tsdf_volume.data_ptr()
+        sc.tsdf.D, sc.tsdf.H, sc.tsdf.W = tsdf_volume.shape[2:]
+        sc.tsdf.sD, sc.tsdf.sH, sc.tsdf.sW = tsdf_volume.stride()[2:]
+    b = _bounds.get(bound)
+    tb = _bounds.get(tsdf_bnds) if tsdf_bnds is not None else b
+    for k in range(3):
+        sc.bound[k][0], sc.bound[k][1] = b[k][0], b[k][1]
+        sc.tsdf_bnds[k][0], sc.tsdf_bnds[k][1] = tb[k][0], tb[k][1]
+    return sc
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.DfpError("attentive_dfprior_b200 runs on CUDA tensors only (there is no CPU fallback)")
+
+
+class _Ctx:
+    """Non-tensor arguments of one call."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _needed_grids(stage):
+    return {"low": ("grid_low",), "high": ("grid_low", "grid_high"),
+            "color": ("grid_low", "grid_high", "grid_color")}[stage]
+
+
+def _grads_struct(ctx, needs_grid, need_params, dev):
+    """Allocate zeroed gradient sinks and the C struct pointing at them."""
+    g = L.DfpGrads()
+    ggrids = {}
+    for key in GRID_KEYS:
+        if needs_grid.get(key) and ctx.grids_cl.get(key) is not None:
+            t = torch.zeros_like(ctx.grids_cl[key], memory_format=torch.preserve_format)
+            ggrids[key] = t
+            setattr(g, key, t.data_ptr())
+    gp = None
+    if need_params:
+        gp = torch.zeros(int(L.lib().dfp_packed_param_floats()), device=dev, dtype=torch.float32)
+        g.params_packed = gp.data_ptr()
+    return g, ggrids, gp
+
+
+def _param_grads(gp, params, needs):
+    """Packed gradient -> 79 views of one flat native-layout buffer."""
+    if gp is None:
+        return [None] * len(params)
+    flat = torch.empty(L.N_PARAMS, device=gp.device, dtype=torch.float32)
+    L.check(L.lib().dfp_unpack_param_grads(gp.data_ptr(), flat.data_ptr(), _stream()))
+    out, off = [], 0
+    for p, need in zip(params, needs):
+        n = p.numel()
+        out.append(flat[off:off + n].view(p.shape).to(p.dtype) if need else None)
+        off += n
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# Renderer.render_batch_ray
+# ----------------------------------------------------------------------------------------
+class _RenderBatchRay(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, aux, rays_o, rays_d, grid_low, grid_high, grid_color, *params):
+        lib = L.lib()
+        dev = rays_o.device
+        ro = rays_o.detach().float().contiguous()
+        rd = rays_d.detach().float().contiguous()
+        gt = aux.gt_depth
+        N = ro.shape[0]
+        S = aux.n_samples + (aux.n_surface if gt is not None else 0)
+        given = {"grid_low": grid_low, "grid_high": grid_high, "grid_color": grid_color}
+        grids_cl = {k: (_grid_ndhwc(given[k]) if k in _needed_grids(aux.stage) else None) for k in GRID_KEYS}
+        packed = aux.pack.get(list(params))
+        scene = _scene_struct(grids_cl, aux.tsdf_volume, aux.tsdf_bnds, aux.bound)
+        cfg = _cfg_struct(aux.stage, aux.n_samples, aux.n_surface, aux.n_importance)
+        rays = L.DfpRays(ro.data_ptr(), rd.data_ptr(), _ptr(gt), N, aux.chunk)
+        depth = torch.empty(N, device=dev, dtype=torch.float64)
+        unc = torch.empty(N, device=dev, dtype=torch.float64)
+        color = torch.empty(N, 3, device=dev, dtype=torch.float32)
+        weight = torch.empty(N, S, 1, device=dev, dtype=torch.float32)
+        z = torch.empty(N, S, device=dev, dtype=torch.float64) if aux.want_aux else None
+        raw = torch.empty(N, S, 4, device=dev, dtype=torch.float32) if aux.want_aux else None
+        ws_bytes = int(lib.dfp_render_workspace_bytes(N, S, aux.chunk))
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        out = L.DfpRenderOut(depth.data_ptr(), unc.data_ptr(), color.data_ptr(), weight.data_ptr(), _ptr(z), _ptr(raw))
+        L.check(lib.dfp_render_fwd(C.byref(scene), packed.data_ptr(), C.byref(rays), C.byref(cfg), C.byref(out),
+                                   ws.data_ptr(), ws_bytes, _stream()))
+        if aux.want_aux:
+            aux.z_vals, aux.raw = z, raw
+        ctx.aux = aux
+        ctx.keep = _Ctx(ro=ro, rd=rd, grids_cl=grids_cl, packed=packed, ws=ws, ws_bytes=ws_bytes, N=N, S=S,
+                        params=params, tsdf=aux.tsdf_volume)
+        return depth, unc, color, weight
+
+    @staticmethod
+    def backward(ctx, g_depth, g_unc, g_color, g_weight):
+        lib = L.lib()
+        aux, k = ctx.aux, ctx.keep
+        dev = k.ro.device
+        need = ctx.needs_input_grad           # (aux, rays_o, rays_d, low, high, color, *params)
+        needs_grid = {"grid_low": need[3], "grid_high": need[4], "grid_color": need[5]}
+        need_params = any(need[6:])
+        with torch.cuda.device(dev):
+            g, ggrids, gp = _grads_struct(k, needs_grid, need_params, dev)
+            d_o = torch.empty_like(k.ro) if (need[1] or need[2]) else None
+            d_d = torch.empty_like(k.rd) if (need[1] or need[2]) else None
+            g.rays_o, g.rays_d = _ptr(d_o), _ptr(d_d)
+            keep_alive = []
+
+            def prep(t, dtype):
+                if t is None:
+                    return None
+                t = t.detach().to(dtype).contiguous()
+                keep_alive.append(t)
+                return t.data_ptr()
+
+            og = L.DfpRenderOutGrad(prep(g_depth, torch.float64), prep(g_unc, torch.float64),
+                                    prep(g_color, torch.float32), prep(g_weight, torch.float32))
+            scene = _scene_struct(k.grids_cl, k.tsdf, aux.tsdf_bnds, aux.bound)
+            cfg = _cfg_struct(aux.stage, aux.n_samples, aux.n_surface, aux.n_importance)
+            rays = L.DfpRays(k.ro.data_ptr(), k.rd.data_ptr(), _ptr(aux.gt_depth), k.N, aux.chunk)
+            L.check(lib.dfp_render_bwd(C.byref(scene), k.packed.data_ptr(), C.byref(rays), C.byref(cfg), C.byref(og),
+                                       C.byref(g), k.ws.data_ptr(), k.ws_bytes, _stream()))
+            pgrads = _param_grads(gp, k.params, need[6:])
+        return (None, d_o if need[1] else None, d_d if need[2] else None,
+                ggrids.get("grid_low"), ggrids.get("grid_high"), ggrids.get("grid_color"), *pgrads)
+
+
+def render_batch_ray(c, decoders, rays_d, rays_o, tsdf_volume, tsdf_bnds, bound, stage, gt_depth=None,
+                     n_samples=32, n_surface=16, n_importance=0, chunk=0, want_aux=False):
+    """Functional form of Renderer.render_batch_ray (src/utils/Renderer.py:110-255).
+
+    Returns ``(depth [N] f64, uncertainty [N] f64, color [N,3] f32, weight [N,S,1] f32)``; with
+    ``want_aux`` also a dict holding the sorted sample depths and the pre-sigmoid raw values."""
+    from .decoder import decoder_param_list, param_pack_of
+    _require_cuda(rays_o, rays_d, tsdf_volume)
+    if stage not in L.STAGES:
+        raise ValueError(f"unknown stage {stage!r}")
+    if rays_o.shape[0] == 0:
+        raise ValueError("render_batch_ray needs at least one ray")
+    params = decoder_param_list(decoders)
+    gt = None if gt_depth is None else gt_depth.detach().reshape(-1).float().contiguous()
+    aux = _Ctx(stage=stage, n_samples=int(n_samples), n_surface=int(n_surface), n_importance=int(n_importance),
+               chunk=int(chunk), gt_depth=gt, tsdf_volume=tsdf_volume.detach() if tsdf_volume is not None else None,
+               tsdf_bnds=tsdf_bnds, bound=bound, pack=param_pack_of(decoders), want_aux=want_aux)
+    dummy = rays_o.new_zeros(())
+    gl = c.get("grid_low")
+    gh = c.get("grid_high") if stage != "low" else None
+    gc = c.get("grid_color") if stage == "color" else None
+    with torch.cuda.device(rays_o.device):
+        out = _RenderBatchRay.apply(aux, rays_o, rays_d, gl, gh if gh is not None else dummy,
+                                    gc if gc is not None else dummy, *params)
+    if want_aux:
+        return out, {"z": aux.z_vals, "raw": aux.raw}
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# Renderer.eval_points / Mesher.eval_points / DF.forward
+# ----------------------------------------------------------------------------------------
+class _EvalPoints(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, aux, pts, grid_low, grid_high, grid_color, *params):
+        lib = L.lib()
+        dev = pts.device
+        p = pts.detach()
+        if p.dtype not in (torch.float32, torch.float64):
+            p = p.float()
+        p = p.contiguous()
+        n = p.shape[0]
+        given = {"grid_low": grid_low, "grid_high": grid_high, "grid_color": grid_color}
+        grids_cl = {k: (_grid_ndhwc(given[k]) if k in _needed_grids(aux.stage) else None) for k in GRID_KEYS}
+        packed = aux.pack.get(list(params))
+        scene = _scene_struct(grids_cl, aux.tsdf_volume, aux.tsdf_bnds, aux.bound)
+        P = L.DfpPoints(p.data_ptr(), 1 if p.dtype == torch.float64 else 0, 1 if aux.apply_bound_mask else 0, n)
+        raw = torch.empty(n, 4, device=dev, dtype=torch.float32)
+        w = torch.empty(n, device=dev, dtype=torch.float32)
+        ws_bytes = int(lib.dfp_points_workspace_bytes(n))
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        L.check(lib.dfp_points_fwd(C.byref(scene), packed.data_ptr(), C.byref(P), L.STAGES[aux.stage],
+                                   raw.data_ptr(), w.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
+        ctx.aux = aux
+        ctx.keep = _Ctx(p=p, grids_cl=grids_cl, packed=packed, ws=ws, ws_bytes=ws_bytes, n=n, params=params,
+                        tsdf=aux.tsdf_volume)
+        return raw, w
+
+    @staticmethod
+    def backward(ctx, g_raw, g_w):
+        lib = L.lib()
+        aux, k = ctx.aux, ctx.keep
+        dev = k.p.device
+        need = ctx.needs_input_grad           # (aux, pts, low, high, color, *params)
+        needs_grid = {"grid_low": need[2], "grid_high": need[3], "grid_color": need[4]}
+        need_params = any(need[5:])
+        with torch.cuda.device(dev):
+            g, ggrids, gp = _grads_struct(k, needs_grid, need_params, dev)
+            d_p = torch.empty_like(k.p) if need[1] else None
+            g.points = _ptr(d_p)
+            gr = g_raw.detach().float().contiguous() if g_raw is not None else None
+            gw = g_w.detach().float().contiguous() if g_w is not None else None
+            scene = _scene_struct(k.grids_cl, k.tsdf, aux.tsdf_bnds, aux.bound)
+            P = L.DfpPoints(k.p.data_ptr(), 1 if k.p.dtype == torch.float64 else 0, 1 if aux.apply_bound_mask else 0, k.n)
+            L.check(lib.dfp_points_bwd(C.byref(scene), k.packed.data_ptr(), C.byref(P), L.STAGES[aux.stage],
+                                       _ptr(gr), _ptr(gw), C.byref(g), k.ws.data_ptr(), k.ws_bytes, _stream()))
+            pgrads = _param_grads(gp, k.params, need[5:])
+        return (None, d_p, ggrids.get("grid_low"), ggrids.get("grid_high"), ggrids.get("grid_color"), *pgrads)
+
+
+def eval_points(p, decoders, c, tsdf_volume, tsdf_bnds, bound, stage="color", apply_bound_mask=True):
+    """Point query: ``raw [P,4]``, ``w [P]``.  With ``apply_bound_mask`` it is Renderer/Mesher.eval_points
+    (occupancy 100 outside the bound, Renderer.py:51-64); without, the bare DF.forward (decoder.py:307-353)."""
+    from .decoder import decoder_param_list, param_pack_of
+    _require_cuda(p, tsdf_volume)
+    if stage not in L.STAGES:
+        raise ValueError(f"unknown stage {stage!r}")
+    if p.shape[0] == 0:
+        raise ValueError("eval_points needs at least one point")
+    params = decoder_param_list(decoders)
+    aux = _Ctx(stage=stage, tsdf_volume=tsdf_volume.detach() if tsdf_volume is not None else None,
+               tsdf_bnds=tsdf_bnds, bound=bound, pack=param_pack_of(decoders), apply_bound_mask=apply_bound_mask)
+    dummy = p.new_zeros((), dtype=torch.float32)
+    gl = c.get("grid_low")
+    gh = c.get("grid_high") if stage != "low" else None
+    gc = c.get("grid_color") if stage == "color" else None
+    with torch.cuda.device(p.device):
+        return _EvalPoints.apply(aux, p, gl, gh if gh is not None else dummy, gc if gc is not None else dummy, *params)
+
+
+def sample_tsdf(p, tsdf_volume, tsdf_bnds):
+    """Trilinear TSDF values at ``p`` -- Renderer.sample_grid_tsdf (Renderer.py:73-81).  Returns [P] f32."""
+    _require_cuda(p, tsdf_volume)
+    pp = p.detach().reshape(-1, 3)
+    if pp.dtype not in (torch.float32, torch.float64):
+        pp = pp.float()
+    pp = pp.contiguous()
+    n = pp.shape[0]
+    out = torch.empty(n, device=pp.device, dtype=torch.float32)
+    if n == 0:
+        return out
+    scene = _scene_struct({}, tsdf_volume.detach(), tsdf_bnds, tsdf_bnds)
+    P = L.DfpPoints(pp.data_ptr(), 1 if pp.dtype == torch.float64 else 0, 0, n)
+    with torch.cuda.device(pp.device):
+        L.check(L.lib().dfp_tsdf_sample(C.byref(scene), C.byref(P), out.data_ptr(), _stream()))
+    return out
