@@ -4,7 +4,7 @@ Public surface mirrors the reference's seam for this path:
 
 * ``Renderer``                  -- src/utils/Renderer.py (render_batch_ray, render_img, eval_points, eval_points_tsdf)
 * ``DF`` / ``get_model``        -- src/conv_onet/models/decoder.py, src/conv_onet/config.py
-* ``MesherQuery``               -- the dense point query of src/utils/Mesher.py (eval_points, get_grid_uniform)
+* ``Mesher``                    -- the dense point query of src/utils/Mesher.py (eval_points, get_grid_uniform, query loop)
 * ``functional``                -- the same operations as plain functions
 * ``dist``                      -- ray / voxel-block sharding across GPUs
 
@@ -13,7 +13,9 @@ There is no CPU fallback: importing is cheap, but any call raises if the library
 """
 from . import _lib, common, functional  # noqa: F401
 from .decoder import DF, MLP, DenseLayer, GaussianFourierFeatureTransform, get_model, mlp_tsdf  # noqa: F401
+from .mesher import Mesher  # noqa: F401
 from .renderer import Renderer  # noqa: F401
+from . import dist  # noqa: F401
 
-__all__ = ["Renderer", "DF", "MLP", "mlp_tsdf", "DenseLayer", "GaussianFourierFeatureTransform", "get_model",
+__all__ = ["Renderer", "Mesher", "dist", "DF", "MLP", "mlp_tsdf", "DenseLayer", "GaussianFourierFeatureTransform", "get_model",
            "functional", "common"]

@@ -39,7 +39,7 @@ class DfpScene(C.Structure):
 
 class DfpRays(C.Structure):
     _fields_ = [("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("gt_depth", C.c_void_p),
-                ("n_rays", C.c_int64), ("chunk", C.c_int64)]
+                ("n_rays", C.c_int64), ("chunk", C.c_int64), ("depth_max", C.c_void_p)]
 
 
 class DfpCfg(C.Structure):
@@ -86,6 +86,9 @@ SYMBOLS = {
     "dfp_points_bwd": (C.c_int, [C.POINTER(DfpScene), C.c_void_p, C.POINTER(DfpPoints), C.c_int32, C.c_void_p,
                                  C.c_void_p, C.POINTER(DfpGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
     "dfp_tsdf_sample": (C.c_int, [C.POINTER(DfpScene), C.POINTER(DfpPoints), C.c_void_p, C.c_void_p]),
+    "dfp_launch_count": (C.c_int64, []),
+    "dfp_timing_enable": (C.c_int, [C.c_int]),
+    "dfp_timing_collect": (C.c_int, [C.c_char_p, C.c_size_t]),
 }
 
 _lib = None
@@ -131,3 +134,27 @@ def fill_bounds(dst, t):
     for k in range(3):
         dst[k][0] = vals[k][0]
         dst[k][1] = vals[k][1]
+
+
+def launch_count() -> int:
+    return int(lib().dfp_launch_count())
+
+
+def kernel_times(fn, *args, **kw):
+    """Run ``fn`` with per-kernel CUDA-event timing on; returns {kernel: (launches, total_ms)}."""
+    import torch
+    l = lib()
+    torch.cuda.synchronize()
+    l.dfp_timing_enable(1)
+    try:
+        fn(*args, **kw)
+        torch.cuda.synchronize()
+    finally:
+        l.dfp_timing_enable(0)
+    buf = C.create_string_buffer(1 << 16)
+    check(l.dfp_timing_collect(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out

@@ -18,6 +18,12 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "dfp_device.cuh"
 
 namespace dfp {
@@ -45,6 +51,29 @@ int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(DFP_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
     } while (0)
 
+
+// ---- launch counter and opt-in per-kernel timing with CUDA events on the launching stream
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_timing{0};
+struct TimedRec { const char* name; cudaEvent_t a, b; };
+static std::vector<TimedRec> g_recs;
+static std::mutex g_rec_mu;
+
+void timing_begin(const char* name, cudaStream_t st) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_timing.load(std::memory_order_relaxed)) return;
+    TimedRec r;
+    r.name = name;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    std::lock_guard<std::mutex> lk(g_rec_mu);
+    g_recs.push_back(r);
+}
+void timing_end(cudaStream_t st) {
+    if (!g_timing.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_rec_mu);
+    if (!g_recs.empty()) cudaEventRecord(g_recs.back().b, st);
+}
 
 static int g_num_sms = 0;
 int num_sms() {
@@ -98,6 +127,11 @@ __global__ void k_depth_max(const float* __restrict__ gt, int64_t n, int64_t chu
             out[2 * c + 1] = m;                  // Renderer.py:195
         }
     }
+}
+
+__global__ void k_depth_max_given(const float* __restrict__ mx, int64_t nchunks, float* __restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nchunks) { out[2 * c] = __fmul_rn(mx[0], 1.2f); out[2 * c + 1] = mx[0]; }
 }
 
 struct SampleArgs {
@@ -390,7 +424,7 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
     pa.ps = ps; pa.n = n; pa.bound = to_bounds(sc->bound); pa.tsdf_bnds = to_bounds(sc->tsdf_bnds); pa.tsdf = sc->tsdf;
     pa.need_tsdf = hi; pa.tsdf_out = w.tsdf; pa.flags = w.flags; pa.w_attn = w.w_attn;
     pa.band_list = w.band_list; pa.band_count = w.band_count; pa.apply_mask = apply_mask;
-    k_prep<MODE><<<grid_for(n, 256, 8 * num_sms()), 256, 0, st>>>(pa);
+    DFP_TIMED("k_prep", st, k_prep<MODE><<<grid_for(n, 256, 8 * num_sms()), 256, 0, st>>>(pa));
     DFP_LAUNCH_CHECK("k_prep");
 
     DecArgs da;
@@ -474,6 +508,43 @@ int dfp_abi_version(void) { return DFP_ABI_VERSION; }
 const char* dfp_last_error(void) { return g_err; }
 int64_t dfp_packed_param_floats(void) { return PACKED_FLOATS; }
 
+int64_t dfp_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int dfp_timing_enable(int on) {
+    g_timing.store(on ? 1 : 0);
+    return DFP_OK;
+}
+
+// Synchronises the recorded events and writes one line per kernel name: "<name> <launches> <total_ms>\n".
+int dfp_timing_collect(char* buf, size_t buf_bytes) {
+    if (!buf || buf_bytes == 0) return fail(DFP_ERR_INVALID, "null buffer");
+    std::vector<TimedRec> recs;
+    {
+        std::lock_guard<std::mutex> lk(g_rec_mu);
+        recs.swap(g_recs);
+    }
+    std::map<std::string, std::pair<long long, double>> agg;
+    for (auto& r : recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            auto& e = agg[r.name];
+            e.first += 1;
+            e.second += ms;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    std::string out;
+    for (auto& kv : agg) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (out.size() + 1 > buf_bytes) return fail(DFP_ERR_INVALID, "timing buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return DFP_OK;
+}
+
 int dfp_pack_params(const float* const* tensors79, float* packed, void* stream) {
     if (!tensors79 || !packed) return fail(DFP_ERR_INVALID, "null argument");
     PtrTable tab;
@@ -481,7 +552,7 @@ int dfp_pack_params(const float* const* tensors79, float* packed, void* stream) 
         if (!tensors79[t]) return fail(DFP_ERR_INVALID, "parameter tensor %d is null", t);
         tab.p[t] = tensors79[t];
     }
-    k_pack_params<<<N_TENSORS, 256, 0, (cudaStream_t)stream>>>(tab, packed);
+    DFP_TIMED("k_pack_params", (cudaStream_t)stream, k_pack_params<<<N_TENSORS, 256, 0, (cudaStream_t)stream>>>(tab, packed));
     DFP_LAUNCH_CHECK("k_pack_params");
     return DFP_OK;
 }
@@ -496,7 +567,7 @@ int dfp_unpack_param_grads(const float* packed_grad, float* native_flat, void* s
         offs.off[t] = off;
         off += r * c;
     }
-    k_unpack_grads<<<N_TENSORS, 256, 0, (cudaStream_t)stream>>>(packed_grad, native_flat, offs);
+    DFP_TIMED("k_unpack_grads", (cudaStream_t)stream, k_unpack_grads<<<N_TENSORS, 256, 0, (cudaStream_t)stream>>>(packed_grad, native_flat, offs));
     DFP_LAUNCH_CHECK("k_unpack_grads");
     return DFP_OK;
 }
@@ -505,7 +576,7 @@ static int transpose_grid(const float* src, float* dst, int32_t C, int32_t D, in
     if (!src || !dst) return fail(DFP_ERR_INVALID, "null argument");
     if (C < 1 || D < 1 || H < 1 || W < 1) return fail(DFP_ERR_INVALID, "empty grid");
     const int64_t V = (int64_t)D * H * W;
-    k_transpose_c_v<<<(unsigned)((V + 31) / 32), 256, 0, (cudaStream_t)stream>>>(src, dst, C, V, to_last);
+    DFP_TIMED("k_transpose_c_v", (cudaStream_t)stream, k_transpose_c_v<<<(unsigned)((V + 31) / 32), 256, 0, (cudaStream_t)stream>>>(src, dst, C, V, to_last));
     DFP_LAUNCH_CHECK("k_transpose_c_v");
     return DFP_OK;
 }
@@ -545,15 +616,18 @@ int dfp_render_fwd(const DfpScene* sc, const float* params, const DfpRays* rays,
     if (need > ws_bytes) return fail(DFP_ERR_WORKSPACE, "workspace too small: need %zu bytes, have %zu", need, ws_bytes);
     cudaStream_t st = (cudaStream_t)stream;
 
-    if (has_depth) {
-        k_depth_max<<<(unsigned)nchunks, 1024, 0, st>>>(rays->gt_depth, N, chunk, w.depthmax);
+    if (has_depth && rays->depth_max) {
+        DFP_TIMED("k_depth_max_given", st, k_depth_max_given<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(rays->depth_max, nchunks, w.depthmax));
+        DFP_LAUNCH_CHECK("k_depth_max_given");
+    } else if (has_depth) {
+        DFP_TIMED("k_depth_max", st, k_depth_max<<<(unsigned)nchunks, 1024, 0, st>>>(rays->gt_depth, N, chunk, w.depthmax));
         DFP_LAUNCH_CHECK("k_depth_max");
     }
     SampleArgs sa;
     sa.rays_o = rays->rays_o; sa.rays_d = rays->rays_d; sa.gt = rays->gt_depth; sa.n_rays = N; sa.chunk = chunk;
     sa.depthmax = w.depthmax; sa.z = w.z; sa.bound = to_bounds(sc->bound); sa.T = T;
     const int rpb = 256 / S;
-    k_sample_z<<<(unsigned)((N + rpb - 1) / rpb), 256, 0, st>>>(sa);
+    DFP_TIMED("k_sample_z", st, k_sample_z<<<(unsigned)((N + rpb - 1) / rpb), 256, 0, st>>>(sa));
     DFP_LAUNCH_CHECK("k_sample_z");
 
     PointSrc ps;
@@ -565,7 +639,7 @@ int dfp_render_fwd(const DfpScene* sc, const float* params, const DfpRays* rays,
     ca.n_rays = N; ca.S = S; ca.stage = cfg->stage; ca.z = w.z; ca.low = w.low; ca.fused = w.fused; ca.rgb4 = w.rgb;
     ca.flags = w.flags; ca.w_attn = w.w_attn;
     ca.depth = out->depth; ca.unc = out->uncertainty; ca.color = out->color; ca.weight = out->weight; ca.raw = out->raw;
-    k_composite_fwd<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(ca);
+    DFP_TIMED("k_composite_fwd", st, k_composite_fwd<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(ca));
     DFP_LAUNCH_CHECK("k_composite_fwd");
     if (out->z_vals) DFP_CUDA(cudaMemcpyAsync(out->z_vals, w.z, NS * sizeof(double), cudaMemcpyDeviceToDevice, st));
     return DFP_OK;
@@ -595,14 +669,14 @@ int dfp_render_bwd(const DfpScene* sc, const float* params, const DfpRays* rays,
     ca.flags = w.flags; ca.w_attn = w.w_attn;
     ca.g_depth = og->depth; ca.g_unc = og->uncertainty; ca.g_color = og->color; ca.g_weight = og->weight;
     ca.d_low = w.d_low; ca.d_high = w.d_high; ca.d_fused = w.d_fused; ca.d_rgb4 = w.d_rgb; ca.dp = want_dp ? w.dp : nullptr;
-    k_composite_bwd<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(ca);
+    DFP_TIMED("k_composite_bwd", st, k_composite_bwd<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(ca));
     DFP_LAUNCH_CHECK("k_composite_bwd");
 
     PointSrc ps;
     ps.rays_o = rays->rays_o; ps.rays_d = rays->rays_d; ps.z = w.z; ps.S = S; ps.pts = nullptr;
     if ((rc = eval_samples_bwd<0>(sc, params, ps, NS, cfg->stage, og->weight, g, want_dp, w, st))) return rc;
     if (want_dp) {
-        k_ray_grad<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(N, S, w.dp, w.z, g->rays_o, g->rays_d);
+        DFP_TIMED("k_ray_grad", st, k_ray_grad<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(N, S, w.dp, w.z, g->rays_o, g->rays_d));
         DFP_LAUNCH_CHECK("k_ray_grad");
     }
     return DFP_OK;
@@ -629,7 +703,7 @@ int dfp_points_fwd(const DfpScene* sc, const float* params, const DfpPoints* pts
     memset(&pa, 0, sizeof(pa));
     pa.n = pts->n; pa.stage = stage; pa.low = w.low; pa.fused = w.fused; pa.rgb4 = w.rgb; pa.flags = w.flags; pa.w_attn = w.w_attn;
     pa.raw = raw; pa.w = wout;
-    k_points_finalize<<<(unsigned)((pts->n + 255) / 256), 256, 0, st>>>(pa);
+    DFP_TIMED("k_points_finalize", st, k_points_finalize<<<(unsigned)((pts->n + 255) / 256), 256, 0, st>>>(pa));
     DFP_LAUNCH_CHECK("k_points_finalize");
     return DFP_OK;
 }
@@ -649,7 +723,7 @@ int dfp_points_bwd(const DfpScene* sc, const float* params, const DfpPoints* pts
     memset(&pa, 0, sizeof(pa));
     pa.n = pts->n; pa.stage = stage; pa.flags = w.flags; pa.g_raw = g_raw; pa.g_w = g_w;
     pa.d_low = w.d_low; pa.d_high = w.d_high; pa.d_fused = w.d_fused; pa.d_rgb4 = w.d_rgb; pa.dp = want_dp ? w.dp : nullptr;
-    k_points_seed_bwd<<<(unsigned)((pts->n + 255) / 256), 256, 0, st>>>(pa);
+    DFP_TIMED("k_points_seed_bwd", st, k_points_seed_bwd<<<(unsigned)((pts->n + 255) / 256), 256, 0, st>>>(pa));
     DFP_LAUNCH_CHECK("k_points_seed_bwd");
     PointSrc ps;
     memset(&ps, 0, sizeof(ps));
@@ -659,8 +733,8 @@ int dfp_points_bwd(const DfpScene* sc, const float* params, const DfpPoints* pts
     if (rc) return rc;
     if (want_dp) {
         const unsigned blocks = (unsigned)((3 * pts->n + 255) / 256);
-        if (pts->is_f64) k_points_grad_out<double><<<blocks, 256, 0, st>>>(pts->n, w.dp, (double*)g->points);
-        else k_points_grad_out<float><<<blocks, 256, 0, st>>>(pts->n, w.dp, (float*)g->points);
+        if (pts->is_f64) DFP_TIMED("k_points_grad_out", st, k_points_grad_out<double><<<blocks, 256, 0, st>>>(pts->n, w.dp, (double*)g->points));
+        else DFP_TIMED("k_points_grad_out", st, k_points_grad_out<float><<<blocks, 256, 0, st>>>(pts->n, w.dp, (float*)g->points));
         DFP_LAUNCH_CHECK("k_points_grad_out");
     }
     return DFP_OK;
@@ -674,8 +748,8 @@ int dfp_tsdf_sample(const DfpScene* sc, const DfpPoints* pts, float* out, void* 
     memset(&ps, 0, sizeof(ps));
     ps.pts = pts->p; ps.S = 1;
     const unsigned blocks = (unsigned)((pts->n + 255) / 256);
-    if (pts->is_f64) k_tsdf_sample<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(ps, pts->n, to_bounds(sc->tsdf_bnds), sc->tsdf, out);
-    else k_tsdf_sample<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(ps, pts->n, to_bounds(sc->tsdf_bnds), sc->tsdf, out);
+    if (pts->is_f64) DFP_TIMED("k_tsdf_sample", (cudaStream_t)stream, k_tsdf_sample<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(ps, pts->n, to_bounds(sc->tsdf_bnds), sc->tsdf, out));
+    else DFP_TIMED("k_tsdf_sample", (cudaStream_t)stream, k_tsdf_sample<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(ps, pts->n, to_bounds(sc->tsdf_bnds), sc->tsdf, out));
     DFP_LAUNCH_CHECK("k_tsdf_sample");
     return DFP_OK;
 }

@@ -76,7 +76,7 @@ int launch_attn_fwd(const AttArgs& aa, int64_t n, cudaStream_t st) {
     const size_t smem = AttOff::SIZE * sizeof(float);
     int rc = set_smem(k_attn_fwd, smem);
     if (rc) return rc;
-    k_attn_fwd<<<grid_for(n, NT, num_sms()), NT, smem, st>>>(aa);
+    DFP_TIMED("k_attn_fwd", st, k_attn_fwd<<<grid_for(n, NT, num_sms()), NT, smem, st>>>(aa));
     DFP_LAUNCH_CHECK("k_attn_fwd");
     return DFP_OK;
 }
@@ -88,10 +88,10 @@ int launch_attn_bwd(const AttArgs& aa, int64_t n, cudaStream_t st) {
     int rc;
     if (aa.gparams) {
         if ((rc = set_smem(k_attn_bwd<MODE, true>, smem))) return rc;
-        k_attn_bwd<MODE, true><<<blocks, NT, smem, st>>>(aa);
+        DFP_TIMED("k_attn_bwd", st, k_attn_bwd<MODE, true><<<blocks, NT, smem, st>>>(aa));
     } else {
         if ((rc = set_smem(k_attn_bwd<MODE, false>, smem))) return rc;
-        k_attn_bwd<MODE, false><<<blocks, NT, smem, st>>>(aa);
+        DFP_TIMED("k_attn_bwd", st, k_attn_bwd<MODE, false><<<blocks, NT, smem, st>>>(aa));
     }
     DFP_LAUNCH_CHECK("k_attn_bwd");
     return DFP_OK;

@@ -76,11 +76,11 @@ int launch_decoder_bwd(const DecArgs& a, cudaStream_t st) {
     if (a.gparams) {
         int rc = set_smem(k_decoder_bwd<DEC, MODE, true>, smem);
         if (rc) return rc;
-        k_decoder_bwd<DEC, MODE, true><<<blocks, NT, smem, st>>>(a);
+        DFP_TIMED("k_decoder_bwd", st, k_decoder_bwd<DEC, MODE, true><<<blocks, NT, smem, st>>>(a));
     } else {
         int rc = set_smem(k_decoder_bwd<DEC, MODE, false>, smem);
         if (rc) return rc;
-        k_decoder_bwd<DEC, MODE, false><<<blocks, NT, smem, st>>>(a);
+        DFP_TIMED("k_decoder_bwd", st, k_decoder_bwd<DEC, MODE, false><<<blocks, NT, smem, st>>>(a));
     }
     DFP_LAUNCH_CHECK("k_decoder_bwd");
     return DFP_OK;

@@ -39,7 +39,7 @@ int launch_decoder_fwd(const DecArgs& a, cudaStream_t st) {
     int rc = set_smem(k_decoder_fwd<DEC, MODE>, smem);
     if (rc) return rc;
     const int blocks = grid_for(a.n, NT, 2 * num_sms());
-    k_decoder_fwd<DEC, MODE><<<blocks, NT, smem, st>>>(a);
+    DFP_TIMED("k_decoder_fwd", st, k_decoder_fwd<DEC, MODE><<<blocks, NT, smem, st>>>(a));
     DFP_LAUNCH_CHECK("k_decoder_fwd");
     return DFP_OK;
 }

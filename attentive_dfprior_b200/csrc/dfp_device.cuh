@@ -24,6 +24,16 @@ int fail(int code, const char* fmt, ...);
 
 int num_sms();
 
+// launch accounting / optional per-kernel CUDA-event timing (dfp_launch_count, dfp_timing_*)
+void timing_begin(const char* name, cudaStream_t st);
+void timing_end(cudaStream_t st);
+#define DFP_TIMED(name, st, ...)     \
+    do {                             \
+        ::dfp::timing_begin(name, st); \
+        __VA_ARGS__;                 \
+        ::dfp::timing_end(st);       \
+    } while (0)
+
 constexpr int NT = 256;            // threads per CTA of the per-sample kernels
 constexpr int WARPS = NT / 32;
 constexpr int SINK_FLOATS_PER_WARP = 32 * 32 + 32 * 33;

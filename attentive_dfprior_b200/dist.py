@@ -1,0 +1,101 @@
+"""Multi-GPU use of the hot path: one process per GPU (torch.distributed, NCCL over NVLink).
+
+The reference has no distributed code at all.  Rays and query points are
+independent given replicated read-only state (grids, decoders, TSDF), so
+
+* mapping (render_batch_ray fwd+bwd): rays are sharded; two collectives per step -- an all-reduce(max)
+  of max(gt_depth) before sampling (the far clamp and the depth==0 sampling use the batch-global
+  maximum, src/utils/Renderer.py:159,195) and an all-reduce(sum) of the grid + packed decoder
+  gradients inside the backward;
+* render_img and the Mesher dense query shard by chunk / voxel block with no data-path collective;
+  results are gathered on request.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import functional as Fn
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous [lo, hi) slice of n items owned by ``rank`` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def chunk_aligned_range(n: int, chunk: int, rank: int, world: int):
+    """Like shard_range but on whole chunks, so per-chunk depth maxima stay exact (render_img)."""
+    nchunks = (n + chunk - 1) // chunk
+    lo, hi = shard_range(nchunks, rank, world)
+    return min(lo * chunk, n), min(hi * chunk, n)
+
+
+def global_depth_max(gt_depth: torch.Tensor, group) -> torch.Tensor:
+    import torch.distributed as dist
+    m = gt_depth.detach().float().max().reshape(1)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    return m
+
+
+def render_batch_ray_sharded(renderer, c, decoders, rays_d, rays_o, tsdf_volume, tsdf_bnds, stage, gt_depth=None,
+                             group=None):
+    """``renderer.render_batch_ray`` on this rank's shard of a batch that is spread over ``group``.
+
+    Outputs are the shard's; gradients of grids and decoders come back already summed over the ranks
+    (identical on every rank, so identical optimiser steps keep the replicas in sync)."""
+    if group is None:
+        return renderer.render_batch_ray(c, decoders, rays_d, rays_o, rays_o.device, tsdf_volume, tsdf_bnds, stage,
+                                         gt_depth=gt_depth)
+    dmax = global_depth_max(gt_depth, group) if gt_depth is not None else None
+    return Fn.render_batch_ray(c, decoders, rays_d, rays_o, tsdf_volume, tsdf_bnds, renderer.bound, stage,
+                               gt_depth=gt_depth, n_samples=renderer.N_samples, n_surface=renderer.N_surface,
+                               n_importance=renderer.N_importance, depth_max=dmax, group=group)
+
+
+def gather_concat(x: torch.Tensor, sizes, group, dst: Optional[int] = None):
+    """Concatenate per-rank pieces of different lengths (dim 0) on every rank (dst=None) or on ``dst`` only."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    mx = max(sizes)
+    pad = x.new_zeros((mx,) + tuple(x.shape[1:]))
+    pad[:x.shape[0]] = x
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    if dst is not None and dist.get_rank(group) != dst:
+        return None
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+
+
+def render_img_sharded(renderer, c, decoders, c2w, device, tsdf_volume, tsdf_bnds, stage, gt_depth, group=None,
+                       gather=True):
+    """Full-frame render with the reference's ray_batch_size chunks dealt out to the ranks (chunk-exact)."""
+    from .common import get_rays
+    if group is None:
+        return renderer.render_img(c, decoders, c2w, device, tsdf_volume, tsdf_bnds, stage, gt_depth=gt_depth)
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    H, W = renderer.H, renderer.W
+    with torch.no_grad():
+        rays_o, rays_d = get_rays(H, W, renderer.fx, renderer.fy, renderer.cx, renderer.cy, c2w, device)
+        rays_o, rays_d, gt = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), gt_depth.reshape(-1)
+        n = rays_d.shape[0]
+        lo, hi = chunk_aligned_range(n, renderer.ray_batch_size, rank, world)
+        if hi > lo:
+            d, u, col, _ = Fn.render_batch_ray(c, decoders, rays_d[lo:hi], rays_o[lo:hi], tsdf_volume, tsdf_bnds,
+                                               renderer.bound, stage, gt_depth=gt[lo:hi], n_samples=renderer.N_samples,
+                                               n_surface=renderer.N_surface, chunk=renderer.ray_batch_size)
+        else:
+            d = torch.empty(0, device=device, dtype=torch.float64)
+            u = torch.empty(0, device=device, dtype=torch.float64)
+            col = torch.empty(0, 3, device=device)
+        if not gather:
+            return (lo, hi), d, u, col
+        sizes = [chunk_aligned_range(n, renderer.ray_batch_size, r, world) for r in range(world)]
+        sizes = [b - a for a, b in sizes]
+        d = gather_concat(d, sizes, group)
+        u = gather_concat(u, sizes, group)
+        col = gather_concat(col, sizes, group)
+        return d.reshape(H, W), u.reshape(H, W), col.reshape(H, W, 3)

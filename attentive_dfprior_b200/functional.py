@@ -181,7 +181,7 @@ class _RenderBatchRay(torch.autograd.Function):
         packed = aux.pack.get(list(params))
         scene = _scene_struct(grids_cl, aux.tsdf_volume, aux.tsdf_bnds, aux.bound)
         cfg = _cfg_struct(aux.stage, aux.n_samples, aux.n_surface, aux.n_importance)
-        rays = L.DfpRays(ro.data_ptr(), rd.data_ptr(), _ptr(gt), N, aux.chunk)
+        rays = L.DfpRays(ro.data_ptr(), rd.data_ptr(), _ptr(gt), N, aux.chunk, _ptr(aux.depth_max))
         depth = torch.empty(N, device=dev, dtype=torch.float64)
         unc = torch.empty(N, device=dev, dtype=torch.float64)
         color = torch.empty(N, 3, device=dev, dtype=torch.float32)
@@ -226,16 +226,24 @@ class _RenderBatchRay(torch.autograd.Function):
                                     prep(g_color, torch.float32), prep(g_weight, torch.float32))
             scene = _scene_struct(k.grids_cl, k.tsdf, aux.tsdf_bnds, aux.bound)
             cfg = _cfg_struct(aux.stage, aux.n_samples, aux.n_surface, aux.n_importance)
-            rays = L.DfpRays(k.ro.data_ptr(), k.rd.data_ptr(), _ptr(aux.gt_depth), k.N, aux.chunk)
+            rays = L.DfpRays(k.ro.data_ptr(), k.rd.data_ptr(), _ptr(aux.gt_depth), k.N, aux.chunk, _ptr(aux.depth_max))
             L.check(lib.dfp_render_bwd(C.byref(scene), k.packed.data_ptr(), C.byref(rays), C.byref(cfg), C.byref(og),
                                        C.byref(g), k.ws.data_ptr(), k.ws_bytes, _stream()))
+            if aux.group is not None:
+                # ray-sharded data parallelism: sum the replicated state's gradients over the ranks (NCCL)
+                import torch.distributed as dist
+                works = [dist.all_reduce(t, group=aux.group, async_op=True) for t in ggrids.values()]
+                if gp is not None:
+                    works.append(dist.all_reduce(gp, group=aux.group, async_op=True))
+                for wk in works:
+                    wk.wait()
             pgrads = _param_grads(gp, k.params, need[6:])
         return (None, d_o if need[1] else None, d_d if need[2] else None,
                 ggrids.get("grid_low"), ggrids.get("grid_high"), ggrids.get("grid_color"), *pgrads)
 
 
 def render_batch_ray(c, decoders, rays_d, rays_o, tsdf_volume, tsdf_bnds, bound, stage, gt_depth=None,
-                     n_samples=32, n_surface=16, n_importance=0, chunk=0, want_aux=False):
+                     n_samples=32, n_surface=16, n_importance=0, chunk=0, want_aux=False, depth_max=None, group=None):
     """Functional form of Renderer.render_batch_ray (src/utils/Renderer.py:110-255).
 
     Returns ``(depth [N] f64, uncertainty [N] f64, color [N,3] f32, weight [N,S,1] f32)``; with
@@ -250,7 +258,9 @@ def render_batch_ray(c, decoders, rays_d, rays_o, tsdf_volume, tsdf_bnds, bound,
     gt = None if gt_depth is None else gt_depth.detach().reshape(-1).float().contiguous()
     aux = _Ctx(stage=stage, n_samples=int(n_samples), n_surface=int(n_surface), n_importance=int(n_importance),
                chunk=int(chunk), gt_depth=gt, tsdf_volume=tsdf_volume.detach() if tsdf_volume is not None else None,
-               tsdf_bnds=tsdf_bnds, bound=bound, pack=param_pack_of(decoders), want_aux=want_aux)
+               tsdf_bnds=tsdf_bnds, bound=bound, pack=param_pack_of(decoders), want_aux=want_aux,
+               depth_max=None if depth_max is None else depth_max.detach().reshape(-1)[:1].float().contiguous(),
+               group=group)
     dummy = rays_o.new_zeros(())
     gl = c.get("grid_low")
     gh = c.get("grid_high") if stage != "low" else None

@@ -1,0 +1,83 @@
+"""The dense point query of the reference's Mesher (src/utils/Mesher.py) on the sm_100a kernels.
+
+Covered: ``get_grid_uniform`` (:365-393), ``eval_points`` (:286-326), ``eval_points_tsdf`` /
+``sample_grid_tsdf`` (:328-363) and the query loop of ``get_mesh`` (:437-447) as
+``query_occupancy`` -- optionally sharded by voxel block across GPUs with no communication on the
+data path.  Marching cubes, convex-hull culling and PLY export (:58-284, :449-542) are CPU geometry
+code built on open3d / skimage / trimesh; they consume the occupancy array this class returns and
+are outside the hot path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import functional as Fn
+from .dist import shard_range
+
+
+class Mesher(object):
+    def __init__(self, cfg, args, slam, points_batch_size=500000, ray_batch_size=100000):
+        self.points_batch_size = points_batch_size
+        self.ray_batch_size = ray_batch_size
+        self.scale = cfg["scale"]
+        self.occupancy = cfg["occupancy"]
+        self.resolution = cfg["meshing"]["resolution"]
+        self.level_set = cfg["meshing"].get("level_set", 0)
+        self.bound = slam.bound
+        self.tsdf_bnds = slam.vol_bnds
+        mcb = cfg.get("mapping", {}).get("marching_cubes_bound")
+        self.marching_cubes_bound = (torch.from_numpy(np.array(mcb) * self.scale) if mcb is not None
+                                     else slam.bound.clone())
+
+    # -- Mesher.py:365-393
+    def get_grid_uniform(self, resolution):
+        bound = self.marching_cubes_bound
+        padding = 0.05
+        axes = [np.linspace(float(bound[k][0]) - padding, float(bound[k][1]) + padding, resolution) for k in range(3)]
+        xx, yy, zz = np.meshgrid(*axes)                       # numpy's default 'xy' indexing, as upstream
+        pts = torch.tensor(np.vstack([xx.ravel(), yy.ravel(), zz.ravel()]).T, dtype=torch.float)
+        return {"grid_points": pts, "xyz": axes}
+
+    # -- Mesher.py:286-326
+    def eval_points(self, p, decoders, tsdf_volume, tsdf_bnds, c=None, stage="color", device="cuda:0"):
+        rets = []
+        for pi in torch.split(p, self.points_batch_size):
+            ret, _ = Fn.eval_points(pi, decoders, c, tsdf_volume, tsdf_bnds, self.bound, stage, apply_bound_mask=True)
+            rets.append(ret)
+        return rets[0] if len(rets) == 1 else torch.cat(rets, dim=0)
+
+    # -- Mesher.py:328-363
+    def sample_grid_tsdf(self, p, tsdf_volume, device="cuda:0"):
+        return Fn.sample_tsdf(p, tsdf_volume, self.tsdf_bnds).reshape(1, 1, -1)
+
+    def eval_points_tsdf(self, p, tsdf_volume, device="cuda:0"):
+        vals = [Fn.sample_tsdf(pi, tsdf_volume, self.tsdf_bnds).reshape(1, -1)
+                for pi in torch.split(p, self.points_batch_size)]
+        return torch.cat(vals, dim=1)
+
+    # -- the query loop of get_mesh, Mesher.py:437-447
+    def query_occupancy(self, c, decoders, tsdf_volume, device="cuda:0", points=None, inside_mask=None, group=None,
+                        gather=True):
+        """Stage-`high` occupancy of the resolution^3 marching-cubes lattice (``ret[:, -1]``); points whose
+        ``inside_mask`` entry is False get 100 (Mesher.py:448).  With ``group`` each rank evaluates one
+        contiguous voxel block and the blocks are concatenated only if ``gather``."""
+        with torch.no_grad():
+            if points is None:
+                points = self.get_grid_uniform(self.resolution)["grid_points"]
+            n = points.shape[0]
+            lo, hi = 0, n
+            if group is not None:
+                import torch.distributed as dist
+                lo, hi = shard_range(n, dist.get_rank(group), dist.get_world_size(group))
+            z = self.eval_points(points[lo:hi].to(device), decoders, tsdf_volume, self.tsdf_bnds, c, "high", device)[:, -1]
+            if inside_mask is not None:
+                m = torch.as_tensor(inside_mask[lo:hi]).to(device)
+                z = torch.where(m, z, torch.full_like(z, 100.0))
+            if group is not None and gather:
+                import torch.distributed as dist
+                from .dist import gather_concat
+                world = dist.get_world_size(group)
+                sizes = [b - a for a, b in (shard_range(n, r, world) for r in range(world))]
+                z = gather_concat(z.contiguous(), sizes, group)
+            return z

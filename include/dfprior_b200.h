@@ -82,6 +82,9 @@ typedef struct DfpRays {
     int64_t chunk;             /* rays per batch-global max(gt_depth) group: n_rays for one
                                   render_batch_ray call, ray_batch_size (100000) for render_img
                                   (Renderer.py:159,195,294-306); 0 means n_rays */
+    const float* depth_max;    /* optional device scalar: max(gt_depth) of the WHOLE batch when this call
+                                  holds only a shard of it (ray-sharded multi-GPU: all-reduce(max) first);
+                                  NULL = computed from gt_depth per chunk */
 } DfpRays;
 
 /* cfg['rendering'] (configs/df_prior.yaml:93-98).  The linspace tables are passed in from
@@ -173,6 +176,14 @@ int dfp_points_bwd(const DfpScene* scene, const float* params_packed, const DfpP
 
 /* ---- Renderer.eval_points_tsdf / sample_grid_tsdf (Renderer.py:73-107) ---------------- */
 int dfp_tsdf_sample(const DfpScene* scene, const DfpPoints* pts, float* tsdf_out, void* stream);
+
+/* ---- diagnostics (used by bench.py; not part of the reference seam) ---------------------
+ * dfp_launch_count: kernels launched by this library since load.  dfp_timing_enable(1) makes
+ * every launch be bracketed by CUDA events on its own stream; dfp_timing_collect waits for them
+ * and writes "<kernel> <launches> <total_ms>\n" per kernel name into buf. */
+int64_t dfp_launch_count(void);
+int dfp_timing_enable(int on);
+int dfp_timing_collect(char* buf, size_t buf_bytes);
 
 #ifdef __cplusplus
 }
