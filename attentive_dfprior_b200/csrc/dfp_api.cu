@@ -508,6 +508,11 @@ int dfp_abi_version(void) { return DFP_ABI_VERSION; }
 const char* dfp_last_error(void) { return g_err; }
 int64_t dfp_packed_param_floats(void) { return PACKED_FLOATS; }
 
+int dfp_selftest_tc(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t split, void* stream) {
+    if (!A || !W || !D) return fail(DFP_ERR_INVALID, "null argument");
+    return launch_tc_selftest(A, W, D, K, N, split, (cudaStream_t)stream);
+}
+
 int64_t dfp_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int dfp_timing_enable(int on) {

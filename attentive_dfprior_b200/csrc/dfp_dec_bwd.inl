@@ -7,7 +7,7 @@ namespace dfp {
 // decoder backward: recompute the forward with saved activations, back-propagate
 // ------------------------------------------------------------------------------------------
 template <int DEC, int MODE, bool WANT_PARAMS>
-__global__ void __launch_bounds__(NT) k_decoder_bwd(const DecArgs a) {
+__global__ void __launch_bounds__(NT_BWD, 1) k_decoder_bwd(const DecArgs a) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
     constexpr int NOUT = (DEC == 2) ? 4 : 1;
     using PT = typename PtT<MODE>::T;
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(NT) k_decoder_bwd(const DecArgs a) {
     sink.Dt = sink.As + 32 * 32;
     __syncthreads();
     const BoxT<PT> box = make_box<PT>(a.bound.b);
-    for (int64_t base = (int64_t)blockIdx.x * NT; base < a.n; base += (int64_t)gridDim.x * NT) {
+    for (int64_t base = (int64_t)blockIdx.x * NT_BWD; base < a.n; base += (int64_t)gridDim.x * NT_BWD) {
         const int64_t s_raw = base + threadIdx.x;
         const bool valid = s_raw < a.n;
         const int64_t s = valid ? s_raw : a.n - 1;          // keep the whole warp in the cooperative sink
@@ -71,16 +71,16 @@ __global__ void __launch_bounds__(NT) k_decoder_bwd(const DecArgs a) {
 template <int DEC, int MODE>
 int launch_decoder_bwd(const DecArgs& a, cudaStream_t st) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
-    const size_t smem = (DecOff<CD>::SIZE + WARPS * SINK_FLOATS_PER_WARP) * sizeof(float);
-    const int blocks = grid_for(a.n, NT, num_sms());
+    const size_t smem = (DecOff<CD>::SIZE + WARPS_BWD * SINK_FLOATS_PER_WARP) * sizeof(float);
+    const int blocks = grid_for(a.n, NT_BWD, num_sms());
     if (a.gparams) {
         int rc = set_smem(k_decoder_bwd<DEC, MODE, true>, smem);
         if (rc) return rc;
-        DFP_TIMED("k_decoder_bwd", st, k_decoder_bwd<DEC, MODE, true><<<blocks, NT, smem, st>>>(a));
+        DFP_TIMED("k_decoder_bwd", st, k_decoder_bwd<DEC, MODE, true><<<blocks, NT_BWD, smem, st>>>(a));
     } else {
         int rc = set_smem(k_decoder_bwd<DEC, MODE, false>, smem);
         if (rc) return rc;
-        DFP_TIMED("k_decoder_bwd", st, k_decoder_bwd<DEC, MODE, false><<<blocks, NT, smem, st>>>(a));
+        DFP_TIMED("k_decoder_bwd", st, k_decoder_bwd<DEC, MODE, false><<<blocks, NT_BWD, smem, st>>>(a));
     }
     DFP_LAUNCH_CHECK("k_decoder_bwd");
     return DFP_OK;

@@ -4,7 +4,7 @@
 namespace dfp {
 
 template <int DEC, int MODE>
-__global__ void __launch_bounds__(NT) k_decoder_fwd(const DecArgs a) {
+__global__ void __launch_bounds__(NT, 2) k_decoder_fwd(const DecArgs a) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
     constexpr int NOUT = (DEC == 2) ? 4 : 1;
     using PT = typename PtT<MODE>::T;

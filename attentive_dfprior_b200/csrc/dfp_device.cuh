@@ -34,8 +34,10 @@ void timing_end(cudaStream_t st);
         ::dfp::timing_end(st);       \
     } while (0)
 
-constexpr int NT = 256;            // threads per CTA of the per-sample kernels
+constexpr int NT = 256;            // threads per CTA of the forward / attention per-sample kernels
 constexpr int WARPS = NT / 32;
+constexpr int NT_BWD = 512;        // decoder backward: 16 warps, 1 CTA/SM (128 registers/thread)
+constexpr int WARPS_BWD = NT_BWD / 32;
 constexpr int SINK_FLOATS_PER_WARP = 32 * 32 + 32 * 33;
 
 // ------------------------------------------------------------------------------------------
@@ -280,5 +282,6 @@ template <int DEC, int MODE> int launch_decoder_fwd(const DecArgs& a, cudaStream
 template <int DEC, int MODE> int launch_decoder_bwd(const DecArgs& a, cudaStream_t st);
 int launch_attn_fwd(const AttArgs& a, int64_t n, cudaStream_t st);
 template <int MODE> int launch_attn_bwd(const AttArgs& a, int64_t n, cudaStream_t st);
+int launch_tc_selftest(const float* A, const float* W, float* D, int K, int N, int split, cudaStream_t st);
 
 }  // namespace dfp

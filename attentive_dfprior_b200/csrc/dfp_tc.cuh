@@ -1,0 +1,163 @@
+// tcgen05 / TMEM building blocks (sm_100a inline PTX) for the tensor-core MLP kernels.
+//
+// Scheme used by every tensor-core kernel in this library ("TS" form of tcgen05.mma):
+//   * one thread owns one sample = one TMEM lane (row of the M=128 tile);
+//   * the A operand (activations) is written by its owner thread straight into TMEM with
+//     tcgen05.st (32x32b shape: lane = row, consecutive columns = consecutive K elements);
+//   * the B operand (weights, [N][K]) sits in shared memory in the canonical K-major, no-swizzle
+//     layout: 16-byte chunk ck = k/4 of row n at byte  ck*(N*16) + n*16   (core matrix = 8 rows x 16 B,
+//     SBO = 128 B between 8-row groups, LBO = N*16 B between K chunks);
+//   * the accumulator D [128 x N] f32 lives in TMEM and is read back by the owner threads with
+//     tcgen05.ld for the epilogue (bias, ReLU, feature term, split for the next layer).
+// fp32 accuracy is kept with the 3xTF32 split: x = hi + lo (both exactly representable in TF32),
+// D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, accumulated in f32 by the tensor core.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dfp {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- TMEM allocation (one full warp executes alloc / dealloc) ----
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- ordering ----
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// ---- mbarrier ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// all previously issued tcgen05.mma of this thread arrive on `bar` when they complete
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- descriptors ----
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (see header comment for the layout)
+__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor: kind::tf32, f32 accumulate, A and B K-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_tf32_m128(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T, one K=8 step
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+
+// ---- TF32 split ----
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    const float h = tf32_rna(x);
+    hi = __float_as_uint(h);
+    lo = __float_as_uint(tf32_rna(x - h));
+}
+
+// ---- TMEM <-> registers, 32x32b shape: thread t of warp w touches lane 32*(w%4)+t ----
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+// split 32 activations and store them as the (hi, lo) A-operand column blocks
+__device__ __forceinline__ void tmem_store_split32(uint32_t taddr_hi, uint32_t taddr_lo, const float (&x)[32]) {
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) split_tf32(x[i], hi[i], lo[i]);
+    tmem_st32(taddr_hi, hi);
+    tmem_st32(taddr_lo, lo);
+}
+
+// canonical B-operand position (in floats) of element (n, k) of an [N][K] matrix
+__host__ __device__ __forceinline__ int b_index(int n, int k, int N) { return (k >> 2) * (N * 4) + n * 4 + (k & 3); }
+
+// D[128 x N] (+)= A[128 x K] * B[N x K]^T with the 3xTF32 split.  a_hi / a_lo: TMEM column addresses of the split A
+// (lane field 0); b_hi / b_lo: shared addresses of the split canonical B; one thread calls this.
+__device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int K,
+                                           int N, bool accumulate) {
+    const uint32_t idesc = idesc_tf32_m128(N);
+    const uint32_t lbo = (uint32_t)N * 16u, sbo = 128u;
+    uint32_t acc = accumulate ? 1u : 0u;
+    for (int ks = 0; ks < K / 8; ++ks) {
+        const uint64_t dh = smem_desc_kmajor(b_hi + ks * 2 * lbo, lbo, sbo);
+        const uint64_t dl = smem_desc_kmajor(b_lo + ks * 2 * lbo, lbo, sbo);
+        mma_tf32_ts(d_tmem, a_lo + ks * 8, dh, idesc, acc);      // small terms first
+        mma_tf32_ts(d_tmem, a_hi + ks * 8, dl, idesc, 1u);
+        mma_tf32_ts(d_tmem, a_hi + ks * 8, dh, idesc, 1u);
+        acc = 1u;
+    }
+}
+
+}  // namespace tc
+}  // namespace dfp
