@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -73,6 +74,18 @@ void timing_end(cudaStream_t st) {
     if (!g_timing.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lk(g_rec_mu);
     if (!g_recs.empty()) cudaEventRecord(g_recs.back().b, st);
+}
+
+// tensor-core (tcgen05) MLP path: on by default, DFP_TENSOR_CORES=0 or dfp_set_tensor_cores(0) selects the fp32 SIMT kernels
+static std::atomic<int> g_tc{-1};
+bool use_tensor_cores() {
+    int v = g_tc.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("DFP_TENSOR_CORES");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_tc.store(v);
+    }
+    return v != 0;
 }
 
 static int g_num_sms = 0;
@@ -431,16 +444,17 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
     memset(&da, 0, sizeof(da));
     da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params;
     int rc;
+    const bool tcp = use_tensor_cores();
     if (hi) {
         da.grid = sc->high; da.grid_low = sc->low; da.out = w.high;
-        if ((rc = launch_decoder_fwd<1, MODE>(da, st))) return rc;
+        if ((rc = tcp ? launch_decoder_fwd_tc<1, MODE>(da, st) : launch_decoder_fwd<1, MODE>(da, st))) return rc;
     }
     if (stage == DFP_STAGE_COLOR) {
         da.grid = sc->color; da.out = w.rgb;
-        if ((rc = launch_decoder_fwd<2, MODE>(da, st))) return rc;
+        if ((rc = tcp ? launch_decoder_fwd_tc<2, MODE>(da, st) : launch_decoder_fwd<2, MODE>(da, st))) return rc;
     }
     da.grid = sc->low; da.out = w.low;
-    if ((rc = launch_decoder_fwd<0, MODE>(da, st))) return rc;
+    if ((rc = tcp ? launch_decoder_fwd_tc<0, MODE>(da, st) : launch_decoder_fwd<0, MODE>(da, st))) return rc;
     if (hi) {
         AttArgs aa;
         memset(&aa, 0, sizeof(aa));
@@ -511,6 +525,11 @@ int64_t dfp_packed_param_floats(void) { return PACKED_FLOATS; }
 int dfp_selftest_tc(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t split, void* stream) {
     if (!A || !W || !D) return fail(DFP_ERR_INVALID, "null argument");
     return launch_tc_selftest(A, W, D, K, N, split, (cudaStream_t)stream);
+}
+
+int dfp_set_tensor_cores(int on) {
+    g_tc.store(on ? 1 : 0);
+    return DFP_OK;
 }
 
 int64_t dfp_launch_count(void) { return (int64_t)g_launches.load(); }

@@ -1,0 +1,225 @@
+// Tensor-core decoder forward (tcgen05 + TMEM, 3xTF32): the grid-conditioned MLP of
+// src/conv_onet/models/decoder.py:177-203 for tiles of 128 samples.
+//
+// One thread owns one sample = one TMEM lane.  It gathers the trilinear features and produces the
+// Fourier embedding on the CUDA cores (accurate sinf on f32 arguments of several hundred radians stays
+// there), writes those activations straight into TMEM as the A operand, and the five 32-wide blocks run as
+// tcgen05.mma with the weights resident in shared memory (canonical K-major layout, hi/lo TF32 split).
+// Epilogues (bias, ReLU, feature term, split for the next layer) read the accumulators back with tcgen05.ld.
+// A CTA runs two independent 128-sample groups (one for the 64-feature high decoder) so that one group's
+// epilogue overlaps the other group's MMAs.
+#include "dfp_device.cuh"
+#include "dfp_tc.cuh"
+
+namespace dfp {
+
+template <int CD>
+struct TcLayout {                                   // shared memory, in floats
+    static constexpr int W03 = 0;                   // B [64][96]  rows 0..31 pts_linears.0, 32..63 pts_linears.3[:, :93]
+    static constexpr int WH = W03 + 64 * 96;        // B 4 x [32][32]
+    static constexpr int WC = WH + 4 * 32 * 32;     // B 5 x [32][CD]
+    static constexpr int BSIZE = WC + 5 * 32 * CD;  // one split half
+    static constexpr int SMALL = 2 * BSIZE;         // biases etc. (plain f32)
+    static constexpr int S_BP = SMALL;              // [5][32]
+    static constexpr int S_BC = S_BP + 160;         // [5][32]
+    static constexpr int S_B = S_BC + 160;          // [3][96] embedding matrix
+    static constexpr int S_WO = S_B + 288;          // [4][32]
+    static constexpr int S_BO = S_WO + 128;         // [4]
+    static constexpr int FLOATS = S_BO + 4;
+    static constexpr int GROUPS = (CD == 32) ? 2 : 1;
+    // TMEM columns of one group
+    static constexpr int T_C_HI = 0, T_C_LO = CD, T_X_HI = 2 * CD, T_X_LO = 2 * CD + 32;
+    static constexpr int T_D03 = 2 * CD + 64, T_DH = 2 * CD + 128, T_DC = 2 * CD + 160;
+    static constexpr int T_COLS = 2 * CD + 192;     // 256 (CD=32) / 320 (CD=64)
+};
+
+template <int CD>
+__device__ __forceinline__ void stage_weights_tc(float* sm, const float* __restrict__ P /* packed decoder params */) {
+    using L = DecOff<CD>;
+    using T = TcLayout<CD>;
+    float* hi = sm;
+    float* lo = sm + T::BSIZE;
+    const int nt = blockDim.x;
+    for (int i = threadIdx.x; i < 64 * 96; i += nt) {               // W03: packed [k][64]
+        const int n = i & 63, k = i >> 6;
+        const float w = (k < EMB) ? P[L::W03 + k * 64 + n] : 0.f;
+        const float h = tc::tf32_rna(w);
+        hi[T::W03 + tc::b_index(n, k, 64)] = h;
+        lo[T::W03 + tc::b_index(n, k, 64)] = tc::tf32_rna(w - h);
+    }
+    for (int i = threadIdx.x; i < 4 * 1024; i += nt) {              // WH: packed [slot][k][32]
+        const int slot = i >> 10, k = (i >> 5) & 31, n = i & 31;
+        const float w = P[L::WH + i];
+        const float h = tc::tf32_rna(w);
+        hi[T::WH + slot * 1024 + tc::b_index(n, k, 32)] = h;
+        lo[T::WH + slot * 1024 + tc::b_index(n, k, 32)] = tc::tf32_rna(w - h);
+    }
+    for (int i = threadIdx.x; i < 5 * CD * 32; i += nt) {           // WC: packed [layer][k][32]
+        const int layer = i / (CD * 32), r = i % (CD * 32), k = r >> 5, n = r & 31;
+        const float w = P[L::WC + i];
+        const float h = tc::tf32_rna(w);
+        hi[T::WC + layer * CD * 32 + tc::b_index(n, k, 32)] = h;
+        lo[T::WC + layer * CD * 32 + tc::b_index(n, k, 32)] = tc::tf32_rna(w - h);
+    }
+    for (int i = threadIdx.x; i < 160; i += nt) { sm[T::S_BP + i] = P[L::BP + i]; sm[T::S_BC + i] = P[L::BC + i]; }
+    for (int i = threadIdx.x; i < 288; i += nt) sm[T::S_B + i] = P[L::B + i];
+    for (int i = threadIdx.x; i < 128; i += nt) sm[T::S_WO + i] = P[L::WO + i];
+    if (threadIdx.x < 4) sm[T::S_BO + threadIdx.x] = P[L::BO + threadIdx.x];
+}
+
+template <int DEC, int MODE>
+__global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 1) k_decoder_fwd_tc(const DecArgs a) {
+    constexpr int CD = (DEC == 1) ? 64 : 32;
+    constexpr int NOUT = (DEC == 2) ? 4 : 1;
+    using PT = typename PtT<MODE>::T;
+    using T = TcLayout<CD>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sm = reinterpret_cast<float*>(smem_raw);
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int grp = tid >> 7, gt = tid & 127;                        // group and row within the group's tile
+    stage_weights_tc<CD>(sm, a.params + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR)));
+    if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+    if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_mbar_init(); }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+
+    const uint32_t tb = tmem_base_s + (uint32_t)(grp * T::T_COLS);                 // this group's columns, lane 0
+    const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16);                  // ... at this warp's lanes
+    uint64_t* bar = &bars[grp];
+    uint32_t parity = 0;
+    const uint32_t bhi = tc::smem_u32(sm), blo = tc::smem_u32(sm + T::BSIZE);
+    const BoxT<PT> box = make_box<PT>(a.bound.b);
+    const int64_t tiles = (a.n + 127) / 128;
+    const bool issuer = (gt == 0);
+
+    for (int64_t tile = (int64_t)blockIdx.x * T::GROUPS + grp; tile < tiles; tile += (int64_t)gridDim.x * T::GROUPS) {
+        const int64_t s_raw = tile * 128 + gt;
+        const bool valid = s_raw < a.n;
+        const int64_t s = valid ? s_raw : a.n - 1;
+        PT p[3];
+        load_point<MODE>(a.ps, s, p);
+        float xn[3];
+        normalize(p, box, xn);
+        const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
+        {   // trilinear features -> A_C
+            float c[32];
+            gather_features(a.grid, tri_setup(xn, a.grid.W, a.grid.H, a.grid.D), c);
+            tc::tmem_store_split32(tl + T::T_C_HI, tl + T::T_C_LO, c);
+            if (DEC == 1) {
+                gather_features(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), c);
+                tc::tmem_store_split32(tl + T::T_C_HI + 32, tl + T::T_C_LO + 32, c);
+            }
+        }
+        // Fourier embedding in three 32-wide K chunks, each accumulated into D03 = [z0 | skip part of z3]
+#pragma unroll 1
+        for (int ch = 0; ch < 3; ++ch) {
+            float e[32];
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) {
+                const int k = ch * 32 + kk;
+                e[kk] = (k < EMB) ? sinf(embed_arg(sm + T::S_B, pf, k)) : 0.f;
+            }
+            if (ch > 0) { tc::mbar_wait(bar, parity); parity ^= 1; tc::fence_after_sync(); }   // previous chunk consumed A_X
+            tc::tmem_store_split32(tl + T::T_X_HI, tl + T::T_X_LO, e);
+            tc::wait_st();
+            tc::fence_before_sync();
+            tc::named_bar_sync(1 + grp, 128);
+            if (issuer) {
+                tc::fence_after_sync();
+                const uint32_t koff = (uint32_t)ch * 8u * (64u * 16u);             // 8 K-chunks of 16 B per 32 k, LBO = N*16
+                tc::mma_3xtf32(tb + T::T_D03, tb + T::T_X_HI, tb + T::T_X_LO, bhi + T::W03 * 4 + koff, blo + T::W03 * 4 + koff,
+                               32, 64, ch > 0);
+                if (ch == 2)                                                         // fc_c[0](c)
+                    tc::mma_3xtf32(tb + T::T_DC, tb + T::T_C_HI, tb + T::T_C_LO, bhi + T::WC * 4, blo + T::WC * 4, CD, 32, false);
+                tc::mma_commit(bar);
+            }
+        }
+        tc::mbar_wait(bar, parity); parity ^= 1;
+        tc::fence_after_sync();
+        float h[32];
+        {
+            float z[32], f[32];
+            tc::tmem_ld32(tl + T::T_D03, z);
+            tc::tmem_ld32(tl + T::T_DC, f);
+            tc::wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = fmaxf(z[j] + sm[T::S_BP + j], 0.f) + (f[j] + sm[T::S_BC + j]);
+        }
+#pragma unroll 1
+        for (int i = 1; i < 5; ++i) {
+            tc::tmem_store_split32(tl + T::T_X_HI, tl + T::T_X_LO, h);
+            tc::wait_st();
+            tc::fence_before_sync();
+            tc::named_bar_sync(1 + grp, 128);
+            if (issuer) {
+                tc::fence_after_sync();
+                tc::mma_3xtf32(tb + T::T_DH, tb + T::T_X_HI, tb + T::T_X_LO, bhi + (T::WH + (i - 1) * 1024) * 4,
+                               blo + (T::WH + (i - 1) * 1024) * 4, 32, 32, false);
+                tc::mma_3xtf32(tb + T::T_DC, tb + T::T_C_HI, tb + T::T_C_LO, bhi + (T::WC + i * CD * 32) * 4,
+                               blo + (T::WC + i * CD * 32) * 4, CD, 32, false);
+                tc::mma_commit(bar);
+            }
+            tc::mbar_wait(bar, parity); parity ^= 1;
+            tc::fence_after_sync();
+            float z[32], f[32];
+            tc::tmem_ld32(tl + T::T_DH, z);
+            tc::tmem_ld32(tl + T::T_DC, f);
+            if (i == 3) {
+                float z3[32];
+                tc::tmem_ld32(tl + T::T_D03 + 32, z3);
+                tc::wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) z[j] += z3[j];
+            } else {
+                tc::wait_ld();
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = fmaxf(z[j] + sm[T::S_BP + i * 32 + j], 0.f) + (f[j] + sm[T::S_BC + i * 32 + j]);
+        }
+        float out[NOUT];
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+            float acc = sm[T::S_BO + o];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc = fmaf(sm[T::S_WO + o * 32 + j], h[j], acc);
+            out[o] = acc;
+        }
+        if (valid) {
+            if (NOUT == 1) a.out[s] = out[0];
+            else *reinterpret_cast<float4*>(a.out + 4 * s) = make_float4(out[0], out[NOUT > 1 ? 1 : 0], out[NOUT > 2 ? 2 : 0], out[NOUT > 3 ? 3 : 0]);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+template <int DEC, int MODE>
+int launch_decoder_fwd_tc(const DecArgs& a, cudaStream_t st) {
+    constexpr int CD = (DEC == 1) ? 64 : 32;
+    using T = TcLayout<CD>;
+    const size_t smem = T::FLOATS * sizeof(float);
+    int rc = set_smem(k_decoder_fwd_tc<DEC, MODE>, smem);
+    if (rc) return rc;
+    const int64_t tiles = (a.n + 127) / 128;
+    const int blocks = grid_for(tiles, T::GROUPS, num_sms());
+    DFP_TIMED("k_decoder_fwd_tc", st, k_decoder_fwd_tc<DEC, MODE><<<blocks, T::GROUPS * 128, smem, st>>>(a));
+    DFP_LAUNCH_CHECK("k_decoder_fwd_tc");
+    return DFP_OK;
+}
+template int launch_decoder_fwd_tc<0, 0>(const DecArgs&, cudaStream_t);
+template int launch_decoder_fwd_tc<1, 0>(const DecArgs&, cudaStream_t);
+template int launch_decoder_fwd_tc<2, 0>(const DecArgs&, cudaStream_t);
+template int launch_decoder_fwd_tc<0, 1>(const DecArgs&, cudaStream_t);
+template int launch_decoder_fwd_tc<1, 1>(const DecArgs&, cudaStream_t);
+template int launch_decoder_fwd_tc<2, 1>(const DecArgs&, cudaStream_t);
+template int launch_decoder_fwd_tc<0, 2>(const DecArgs&, cudaStream_t);
+template int launch_decoder_fwd_tc<1, 2>(const DecArgs&, cudaStream_t);
+template int launch_decoder_fwd_tc<2, 2>(const DecArgs&, cudaStream_t);
+
+}  // namespace dfp

@@ -36,7 +36,7 @@ void timing_end(cudaStream_t st);
 
 constexpr int NT = 256;            // threads per CTA of the forward / attention per-sample kernels
 constexpr int WARPS = NT / 32;
-constexpr int NT_BWD = 512;        // decoder backward: 16 warps, 1 CTA/SM (128 registers/thread)
+constexpr int NT_BWD = 256;        // decoder backward: 8 warps, 1 CTA/SM (512 threads at 128 registers measured 50% slower)
 constexpr int WARPS_BWD = NT_BWD / 32;
 constexpr int SINK_FLOATS_PER_WARP = 32 * 32 + 32 * 33;
 
@@ -280,6 +280,8 @@ inline Bounds to_bounds(const double b[3][2]) {
 // launchers defined in the per-kernel translation units
 template <int DEC, int MODE> int launch_decoder_fwd(const DecArgs& a, cudaStream_t st);
 template <int DEC, int MODE> int launch_decoder_bwd(const DecArgs& a, cudaStream_t st);
+template <int DEC, int MODE> int launch_decoder_fwd_tc(const DecArgs& a, cudaStream_t st);   // tcgen05 path
+bool use_tensor_cores();
 int launch_attn_fwd(const AttArgs& a, int64_t n, cudaStream_t st);
 template <int MODE> int launch_attn_bwd(const AttArgs& a, int64_t n, cudaStream_t st);
 int launch_tc_selftest(const float* A, const float* W, float* D, int K, int N, int split, cudaStream_t st);

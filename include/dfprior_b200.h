@@ -182,6 +182,8 @@ int dfp_tsdf_sample(const DfpScene* scene, const DfpPoints* pts, float* tsdf_out
  * every launch be bracketed by CUDA events on its own stream; dfp_timing_collect waits for them
  * and writes "<kernel> <launches> <total_ms>\n" per kernel name into buf. */
 int64_t dfp_launch_count(void);
+/* 1 (default): MLP layers on the tcgen05 tensor cores (3xTF32); 0: fp32 SIMT kernels.  Env DFP_TENSOR_CORES=0 too. */
+int dfp_set_tensor_cores(int on);
 /* tensor-core self test: D[128,N] = A[128,K] * W[N,K]^T through the tcgen05/TMEM path (split=1: 3xTF32) */
 int dfp_selftest_tc(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t split, void* stream);
 int dfp_timing_enable(int on);

@@ -22,3 +22,31 @@ def test_tc_selftest_3xtf32(K, N):
         assert err <= tol, (K, N, split, err)
         if split == 0:
             assert err > 1e-6, "single-pass TF32 should be visibly less accurate than the 3x split"
+
+
+@pytest.mark.parametrize("stage", ["low", "high", "color"])
+def test_tensor_core_and_simt_paths_agree(stage):
+    """The tcgen05 (3xTF32) decoder path and the fp32 SIMT path give the same point query within 1e-5."""
+    import attentive_dfprior_b200 as A
+    from attentive_dfprior_b200 import _lib as L
+    from attentive_dfprior_b200 import functional as Fn
+    from attentive_dfprior_b200 import synth
+    torch.manual_seed(1)
+    scene = synth.make_scene("small", seed=5, device="cuda", high_std=1e-2, channels_last=True)
+    model = A.DF().cuda()
+    model.bound = scene.bound
+    g = torch.Generator().manual_seed(3)
+    lo, hi = scene.bound[:, 0], scene.bound[:, 1]
+    p = (torch.rand(5000, 3, generator=g, dtype=torch.float64) * (hi - lo) + lo).cuda()
+    lib = L.lib()
+    try:
+        with torch.no_grad():
+            lib.dfp_set_tensor_cores(1)
+            raw_tc, w_tc = Fn.eval_points(p, model, scene.grids, scene.tsdf_volume, scene.tsdf_bnds, scene.bound, stage)
+            lib.dfp_set_tensor_cores(0)
+            raw_sm, w_sm = Fn.eval_points(p, model, scene.grids, scene.tsdf_volume, scene.tsdf_bnds, scene.bound, stage)
+    finally:
+        lib.dfp_set_tensor_cores(1)
+    scale = float(raw_sm[:, 3][raw_sm[:, 3] != 100].abs().max())
+    assert float((raw_tc - raw_sm).abs().max()) <= 1e-5 * max(scale, 1.0)
+    assert float((w_tc - w_sm).abs().max()) <= 1e-5
