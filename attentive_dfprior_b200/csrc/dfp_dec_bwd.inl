@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(NT_BWD, 1) k_decoder_bwd(const DecArgs a) {
     sink.Dt = sink.As + 32 * 32;
     __syncthreads();
     const BoxT<PT> box = make_box<PT>(a.bound.b);
+    const float bmax = embed_bmax(W + DecOff<CD>::B);
     for (int64_t base = (int64_t)blockIdx.x * NT_BWD; base < a.n; base += (int64_t)gridDim.x * NT_BWD) {
         const int64_t s_raw = base + threadIdx.x;
         const bool valid = s_raw < a.n;
@@ -49,10 +50,10 @@ __global__ void __launch_bounds__(NT_BWD, 1) k_decoder_bwd(const DecArgs a) {
         const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
         DecState st;
         float out[NOUT];
-        decoder_fwd_thread<CD, NOUT, true>(W, pf, c, out, &st);
+        decoder_fwd_thread<CD, NOUT, true>(W, pf, c, out, &st, bmax);
         float d_c[CD];
         float dpe[3] = {0.f, 0.f, 0.f};
-        decoder_bwd_thread<CD, NOUT, WANT_PARAMS>(W, gbase, pf, c, st, dout, d_c, dpe, sink);
+        decoder_bwd_thread<CD, NOUT, WANT_PARAMS>(W, gbase, pf, c, st, dout, d_c, dpe, sink, bmax);
         if (valid && any) {
             const bool want_coord = a.dp != nullptr;
             float gn[3] = {0.f, 0.f, 0.f};

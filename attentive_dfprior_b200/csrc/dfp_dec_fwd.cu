@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(NT, 2) k_decoder_fwd(const DecArgs a) {
     load_weights_to_smem(W, a.params + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR)), DecOff<CD>::SIZE);
     __syncthreads();
     const BoxT<PT> box = make_box<PT>(a.bound.b);
+    const float bmax = embed_bmax(W + DecOff<CD>::B);
     for (int64_t base = (int64_t)blockIdx.x * NT; base < a.n; base += (int64_t)gridDim.x * NT) {
         const int64_t s = base + threadIdx.x;
         if (s >= a.n) continue;
@@ -25,7 +26,7 @@ __global__ void __launch_bounds__(NT, 2) k_decoder_fwd(const DecArgs a) {
         if (DEC == 1) gather_features(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), c + CDIM);
         const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};       // p.float()   decoder.py:189
         float out[NOUT];
-        decoder_fwd_thread<CD, NOUT, false>(W, pf, c, out, nullptr);
+        decoder_fwd_thread<CD, NOUT, false>(W, pf, c, out, nullptr, bmax);
         if (NOUT == 1) a.out[s] = out[0];
         else *reinterpret_cast<float4*>(a.out + 4 * s) = make_float4(out[0], out[NOUT > 1 ? 1 : 0], out[NOUT > 2 ? 2 : 0], out[NOUT > 3 ? 3 : 0]);
     }

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
     const BoxT<PT> box = make_box<PT>(a.bound.b);
     const int64_t tiles = (a.n + 127) / 128;
     const bool issuer = (gt == 0);
+    const float bmax = embed_bmax(sm + T::S_B);
 
     for (int64_t tile = (int64_t)blockIdx.x * T::GROUPS + grp; tile < tiles; tile += (int64_t)gridDim.x * T::GROUPS) {
         const int64_t s_raw = tile * 128 + gt;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
         float xn[3];
         normalize(p, box, xn);
         const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
+        const bool fast = embed_fast_ok(pf, bmax);
         {   // trilinear features -> A_C
             float c[32];
             gather_features(a.grid, tri_setup(xn, a.grid.W, a.grid.H, a.grid.D), c);
@@ -122,7 +124,8 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
 #pragma unroll
             for (int kk = 0; kk < 32; ++kk) {
                 const int k = ch * 32 + kk;
-                e[kk] = (k < EMB) ? sinf(embed_arg(sm + T::S_B, pf, k)) : 0.f;
+                const float arg = embed_arg(sm + T::S_B, pf, k);
+                e[kk] = (k < EMB) ? (fast ? sin_cw(arg) : sinf(arg)) : 0.f;
             }
             if (ch > 0) { tc::mbar_wait(bar, parity); parity ^= 1; tc::fence_after_sync(); }   // previous chunk consumed A_X
             tc::tmem_store_split32(tl + T::T_X_HI, tl + T::T_X_LO, e);

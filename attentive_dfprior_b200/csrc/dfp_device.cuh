@@ -95,19 +95,33 @@ __device__ __forceinline__ void gather_features(const DfpGrid& g, const Tri& t, 
     float acc[CDIM];
 #pragma unroll
     for (int j = 0; j < CDIM; ++j) acc[j] = 0.f;
-#pragma unroll 1
-    for (int cn = 0; cn < 8; ++cn) {
-        int x, y, z;
-        if (!tri_corner(t, cn, g.W, g.H, g.D, x, y, z)) continue;      // index == size: skipped (GridSampler.cuh:225)
-        const float wgt = tri_weight(t, cn);
-        const float4* src = reinterpret_cast<const float4*>(g.data + (((int64_t)z * g.H + y) * g.W + x) * CDIM);
+    // two passes of four corners: the four 128-byte corner reads of a pass are independent, so their
+    // loads are all in flight before the first FMA (the serial 8-corner loop was latency-bound)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const float4* src[4];
+        float wgt[4];
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int x, y, z;
+            const int cn = half * 4 + i;
+            ok[i] = tri_corner(t, cn, g.W, g.H, g.D, x, y, z);      // index == size: skipped (GridSampler.cuh:225)
+            wgt[i] = tri_weight(t, cn);
+            src[i] = reinterpret_cast<const float4*>(g.data + (ok[i] ? (((int64_t)z * g.H + y) * g.W + x) * CDIM : 0));
+        }
 #pragma unroll
         for (int q = 0; q < CDIM / 4; ++q) {
-            const float4 v = __ldg(src + q);
-            acc[4 * q + 0] = fmaf(v.x, wgt, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(v.y, wgt, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(v.z, wgt, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(v.w, wgt, acc[4 * q + 3]);
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = ok[i] ? __ldg(src[i] + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[4 * q + 0] = fmaf(v[i].x, wgt[i], acc[4 * q + 0]);
+                acc[4 * q + 1] = fmaf(v[i].y, wgt[i], acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(v[i].z, wgt[i], acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(v[i].w, wgt[i], acc[4 * q + 3]);
+            }
         }
     }
 #pragma unroll

@@ -77,7 +77,7 @@ void decoder_fwd(const DfpScene* sc, const float* packed, const double p[3], flo
     if (DEC == 1) gather(sc->low, tri_setup(xn, sc->low.W, sc->low.H, sc->low.D), c + 32);
     const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
     float o[NOUT];
-    decoder_fwd_thread<CD, NOUT, false>(packed + dec_base(DEC), pf, c, o, nullptr);
+    decoder_fwd_thread<CD, NOUT, false>(packed + dec_base(DEC), pf, c, o, nullptr, embed_bmax(packed + dec_base(DEC) + DecOff<CD>::B));
     for (int k = 0; k < NOUT; ++k) out[k] = o[k];
 }
 
@@ -98,11 +98,12 @@ void decoder_bwd(const DfpScene* sc, const float* packed, const double p[3], con
     float o[NOUT], dout[NOUT];
     for (int k = 0; k < NOUT; ++k) dout[k] = (DEC == 2 && k == 3) ? 0.f : dout_in[k];
     DecState st;
-    decoder_fwd_thread<CD, NOUT, true>(packed + dec_base(DEC), pf, c, o, &st);
+    const float bmax = embed_bmax(packed + dec_base(DEC) + DecOff<CD>::B);
+    decoder_fwd_thread<CD, NOUT, true>(packed + dec_base(DEC), pf, c, o, &st, bmax);
     float d_c[CD], dpe[3] = {0, 0, 0};
     HostSink sink{gparams};
-    if (gparams) decoder_bwd_thread<CD, NOUT, true>(packed + dec_base(DEC), dec_base(DEC), pf, c, st, dout, d_c, dpe, sink);
-    else decoder_bwd_thread<CD, NOUT, false>(packed + dec_base(DEC), dec_base(DEC), pf, c, st, dout, d_c, dpe, sink);
+    if (gparams) decoder_bwd_thread<CD, NOUT, true>(packed + dec_base(DEC), dec_base(DEC), pf, c, st, dout, d_c, dpe, sink, bmax);
+    else decoder_bwd_thread<CD, NOUT, false>(packed + dec_base(DEC), dec_base(DEC), pf, c, st, dout, d_c, dpe, sink, bmax);
     float gn[3] = {0, 0, 0};
     scatter(g, ggrid, tri, d_c, dp != nullptr, gn);
     if (dp)
