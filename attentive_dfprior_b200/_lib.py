@@ -88,6 +88,7 @@ SYMBOLS = {
     "dfp_tsdf_sample": (C.c_int, [C.POINTER(DfpScene), C.POINTER(DfpPoints), C.c_void_p, C.c_void_p]),
     "dfp_launch_count": (C.c_int64, []),
     "dfp_set_tensor_cores": (C.c_int, [C.c_int]),
+    "dfp_probe_tc": (C.c_int, [C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
     "dfp_selftest_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dfp_timing_enable": (C.c_int, [C.c_int]),
     "dfp_timing_collect": (C.c_int, [C.c_char_p, C.c_size_t]),

@@ -527,6 +527,12 @@ int dfp_selftest_tc(const float* A, const float* W, float* D, int32_t K, int32_t
     return launch_tc_selftest(A, W, D, K, N, split, (cudaStream_t)stream);
 }
 
+int dfp_probe_tc(float* D, int32_t N, int32_t b_mn, int32_t lbo, int32_t sbo, int32_t k_hot, int32_t layout_type,
+                 int32_t start_off, void* stream) {
+    if (!D) return fail(DFP_ERR_INVALID, "null argument");
+    return launch_tc_probe(D, N, b_mn, lbo, sbo, k_hot, layout_type, start_off, (cudaStream_t)stream);
+}
+
 int dfp_set_tensor_cores(int on) {
     g_tc.store(on ? 1 : 0);
     return DFP_OK;

@@ -299,5 +299,6 @@ bool use_tensor_cores();
 int launch_attn_fwd(const AttArgs& a, int64_t n, cudaStream_t st);
 template <int MODE> int launch_attn_bwd(const AttArgs& a, int64_t n, cudaStream_t st);
 int launch_tc_selftest(const float* A, const float* W, float* D, int K, int N, int split, cudaStream_t st);
+int launch_tc_probe(float* D, int N, int b_mn, int lbo, int sbo, int k_hot, int layout_type, int start_off, cudaStream_t st);
 
 }  // namespace dfp

@@ -67,9 +67,33 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr, uint32_t lb
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-// instruction descriptor: kind::tf32, f32 accumulate, A and B K-major, M = 128
-__host__ __device__ constexpr uint32_t idesc_tf32_m128(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: kind::tf32, f32 accumulate, M = 128; a_mn / b_mn select the MN-major (transposed) view
+__host__ __device__ constexpr uint32_t idesc_tf32_m128(int n, bool a_mn = false, bool b_mn = false) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// ---- MN-major (transposed) TF32 operands ----------------------------------------------------------------
+// Probed on B200 (dfp_probe_tc): for kind::tf32 the transposed view only exists with layout type 1
+// (SWIZZLE_128B_BASE32B).  An operand X[K rows][MN cols] is then stored as row-major tiles of 32 columns:
+//     word(k, mn) = (mn/32)*LBO/4 + (k/4)*SBO/4 + (k%4)*32 + (((mn%32)/8) ^ (k%4))*8 + mn%8
+// i.e. each K row holds 32 consecutive MN elements (128 B), 4-row groups are SBO apart (512 B when rows are
+// simply consecutive), 32-column blocks are LBO apart, and the four 32-byte groups of a row are XOR-swizzled
+// with address bits 7..8 (the tile base must be 512-byte aligned).
+__host__ __device__ __forceinline__ int mn_tile_index(int row, int col) {              // [rows][32] tile, in floats
+    return row * 32 + ((((col >> 3) ^ row) & 3) << 3) + (col & 7);
+}
+__device__ __forceinline__ uint64_t smem_desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes = 512u) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (1ull << 61);
+}
+// D[tmem] (+)= A[smem] * B[smem], one K=8 step
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
 }
 
 // D[tmem] (+)= A[tmem] * B[smem]^T, one K=8 step
@@ -155,6 +179,39 @@ __device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint3
         mma_tf32_ts(d_tmem, a_lo + ks * 8, dh, idesc, acc);      // small terms first
         mma_tf32_ts(d_tmem, a_hi + ks * 8, dl, idesc, 1u);
         mma_tf32_ts(d_tmem, a_hi + ks * 8, dh, idesc, 1u);
+        acc = 1u;
+    }
+}
+
+// D[128 x N] (+)= A[128 x J] * W[J x N]: A (hi/lo) in TMEM, W as natural row-major [J][N] swizzled tiles (mn_tile_index,
+// one tile per 32 columns, `colblock_bytes` apart), i.e. the MN-major B operand.              (dH = delta * W)
+__device__ __forceinline__ void mma_3xtf32_bT(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, int J,
+                                              int N, uint32_t colblock_bytes, bool accumulate) {
+    const uint32_t idesc = idesc_tf32_m128(N, false, true);
+    uint32_t acc = accumulate ? 1u : 0u;
+    for (int ks = 0; ks < J / 8; ++ks) {                      // 8 rows of W per step = two 4-row groups = 1024 B
+        const uint64_t dh = smem_desc_mnmajor(w_hi + ks * 1024u, colblock_bytes);
+        const uint64_t dl = smem_desc_mnmajor(w_lo + ks * 1024u, colblock_bytes);
+        mma_tf32_ts(d_tmem, a_lo + ks * 8, dh, idesc, acc);
+        mma_tf32_ts(d_tmem, a_hi + ks * 8, dl, idesc, 1u);
+        mma_tf32_ts(d_tmem, a_hi + ks * 8, dh, idesc, 1u);
+        acc = 1u;
+    }
+}
+
+// D[128 (first F rows valid) x N] (+)= H^T * Dl over the 128 samples of a tile.  H: [128][F] row-per-sample swizzled
+// tiles split hi/lo (32-feature blocks `h_block_bytes` apart); Dl: [128][N] likewise, hi part only (the dropped
+// H_hi*Dl_lo term is < 2^-12 of the product).  M is always 128: feature blocks beyond F read whatever lies at the
+// following block addresses and only produce junk in accumulator lanes >= F.                 (dW = H^T * delta)
+__device__ __forceinline__ void mma_outer(uint32_t d_tmem, uint32_t h_hi, uint32_t h_lo, uint32_t h_block_bytes, uint32_t d_hi,
+                                          uint32_t d_block_bytes, int N, bool accumulate) {
+    const uint32_t idesc = idesc_tf32_m128(N, true, true);
+    uint32_t acc = accumulate ? 1u : 0u;
+    for (int ks = 0; ks < 16; ++ks) {                         // 128 samples, 8 per step (1024 B of each tile)
+        const uint64_t ah = smem_desc_mnmajor(h_hi + ks * 1024u, h_block_bytes), al = smem_desc_mnmajor(h_lo + ks * 1024u, h_block_bytes);
+        const uint64_t bh = smem_desc_mnmajor(d_hi + ks * 1024u, d_block_bytes);
+        mma_tf32_ss(d_tmem, al, bh, idesc, acc);
+        mma_tf32_ss(d_tmem, ah, bh, idesc, 1u);
         acc = 1u;
     }
 }

@@ -72,7 +72,188 @@ __global__ void __launch_bounds__(128) k_tc_selftest(const float* __restrict__ A
     if (warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
+// mode 1: D[128 x KIN] = A[128 x J] * Wf[J x KIN] using the transposed view of the canonical Wf buffer (dH pattern)
+__global__ void __launch_bounds__(128) k_tc_selftest_bT(const float* __restrict__ A, const float* __restrict__ Wf,
+                                                        float* __restrict__ D, int J, int KIN) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* Bhi = reinterpret_cast<float*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+    float* Blo = Bhi + J * ((KIN + 31) / 32) * 32;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int idx = tid; idx < J * KIN; idx += 128) {          // natural [j][kin] rows in 32-column swizzled tiles
+        const int j = idx / KIN, k = idx % KIN;
+        const float w = Wf[idx];
+        const float hi = tc::tf32_rna(w);
+        const int o = (k >> 5) * (J * 32) + tc::mn_tile_index(j, k & 31);
+        Bhi[o] = hi;
+        Blo[o] = tc::tf32_rna(w - hi);
+    }
+    if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    const uint32_t col_hi = 0, col_lo = (uint32_t)J, col_d = 2u * (uint32_t)J;
+    for (int c0 = 0; c0 < J; c0 += 8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tc::split_tf32(A[tid * J + c0 + i], hi[i], lo[i]);
+        tc::tmem_st8(lane_base + col_hi + c0, hi);
+        tc::tmem_st8(lane_base + col_lo + c0, lo);
+    }
+    tc::wait_st();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+        tc::fence_after_sync();
+        tc::mma_3xtf32_bT(tbase + col_d, tbase + col_hi, tbase + col_lo, tc::smem_u32(Bhi), tc::smem_u32(Blo), J, KIN, (uint32_t)J * 128u, false);
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    for (int c0 = 0; c0 < KIN; c0 += 8) {
+        uint32_t v[8];
+        tc::tmem_ld8(lane_base + col_d + c0, v);
+        tc::wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) D[tid * KIN + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
+// mode 2: D[128 x N] (rows < F valid) = H[128 x F]^T * Dl[128 x N], both operands sample-major tiles in smem (dW pattern)
+__global__ void __launch_bounds__(128) k_tc_selftest_outer(const float* __restrict__ H, const float* __restrict__ Dl,
+                                                           float* __restrict__ D, int F, int N) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+    // [128][32] row-per-sample swizzled tiles (16 KB each): H hi, H lo, then delta hi (one tile per 32 columns)
+    float* Hhi = sm;
+    float* Hlo = sm + 4096;
+    float* Dhi = sm + 2 * 4096;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int f = 0; f < 32; ++f) {
+        const float v = f < F ? H[tid * F + f] : 0.f;
+        const float hi = tc::tf32_rna(v);
+        Hhi[tc::mn_tile_index(tid, f)] = hi;
+        Hlo[tc::mn_tile_index(tid, f)] = tc::tf32_rna(v - hi);
+    }
+    for (int j = 0; j < N; ++j) Dhi[(j >> 5) * 4096 + tc::mn_tile_index(tid, j & 31)] = tc::tf32_rna(Dl[tid * N + j]);
+    if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    if (tid == 0) {
+        tc::mma_outer(tbase, tc::smem_u32(Hhi), tc::smem_u32(Hlo), 16384u, tc::smem_u32(Dhi), 16384u, N, false);
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[8];
+        tc::tmem_ld8(lane_base + c0, v);
+        tc::wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) D[tid * N + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
+// Layout probe: shared memory word i holds float(i); A (TMEM, 8 K columns) is one-hot at column k_hot for every row,
+// so after ONE tcgen05.mma (M=128, N, K=8) D[s][n] is the index of the shared-memory word the tensor core used as
+// B(n, k_hot) under the descriptor being probed.
+__global__ void __launch_bounds__(128) k_tc_probe(float* __restrict__ D, int N, int b_mn, int lbo, int sbo, int k_hot,
+                                                  int layout_type, int start_off) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // 1024-byte aligned window inside the dynamic allocation: swizzle patterns are functions of absolute address bits
+    float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 16384; i += 128) sm[i] = (float)i;
+    if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    uint32_t a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (i == k_hot) ? __float_as_uint(1.0f) : 0u;
+    tc::tmem_st8(lane_base, a);
+    tc::wait_st();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t idesc = tc::idesc_tf32_m128(N, false, b_mn != 0);
+        uint64_t desc = tc::smem_desc_kmajor(tc::smem_u32(sm) + start_off, lbo, sbo);
+        desc |= ((uint64_t)(layout_type & 7)) << 61;
+        tc::mma_tf32_ts(tbase + 64, tbase, desc, idesc, 0u);
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[8];
+        tc::tmem_ld8(lane_base + 64 + c0, v);
+        tc::wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) D[tid * N + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
+int launch_tc_probe(float* D, int N, int b_mn, int lbo, int sbo, int k_hot, int layout_type, int start_off, cudaStream_t st) {
+    const size_t smem = 16384 * sizeof(float) + 1024;
+    int rc = set_smem(k_tc_probe, smem);
+    if (rc) return rc;
+    DFP_TIMED("k_tc_probe", st, k_tc_probe<<<1, 128, smem, st>>>(D, N, b_mn, lbo, sbo, k_hot, layout_type, start_off));
+    DFP_LAUNCH_CHECK("k_tc_probe");
+    return DFP_OK;
+}
+
+int launch_tc_selftest_mode(const float* A, const float* W, float* D, int K, int N, int mode, cudaStream_t st) {
+    if (mode == 1) {            // K = J, N = KIN
+        if (K < 8 || K % 8 || N < 16 || N % 16 || N > 256 || 2 * K + N > 512) return fail(DFP_ERR_INVALID, "bad selftest shape");
+        const size_t smem = 2 * (size_t)K * ((N + 31) / 32) * 32 * sizeof(float) + 1024;
+        int rc = set_smem(k_tc_selftest_bT, smem);
+        if (rc) return rc;
+        DFP_TIMED("k_tc_selftest_bT", st, k_tc_selftest_bT<<<1, 128, smem, st>>>(A, W, D, K, N));
+        DFP_LAUNCH_CHECK("k_tc_selftest_bT");
+        return DFP_OK;
+    }
+    if (mode == 2) {            // K = F (features of H, <= 32), N = delta columns (<= 64)
+        if (K < 4 || K > 32 || K % 4 || N < 16 || N % 16 || N > 64) return fail(DFP_ERR_INVALID, "bad selftest shape");
+        const size_t smem = 160 * 1024;     // H tiles + delta tiles + room for the M=128 over-read
+        int rc = set_smem(k_tc_selftest_outer, smem);
+        if (rc) return rc;
+        DFP_TIMED("k_tc_selftest_outer", st, k_tc_selftest_outer<<<1, 128, smem, st>>>(A, W, D, K, N));
+        DFP_LAUNCH_CHECK("k_tc_selftest_outer");
+        return DFP_OK;
+    }
+    return fail(DFP_ERR_INVALID, "bad selftest mode");
+}
+
 int launch_tc_selftest(const float* A, const float* W, float* D, int K, int N, int split, cudaStream_t st) {
+    if (split >= 10) return launch_tc_selftest_mode(A, W, D, K, N, split - 10, st);
     if (K < 8 || K % 8 || N < 16 || N % 16 || N > 256 || 2 * K + N > 512)
         return fail(DFP_ERR_INVALID, "selftest needs K%%8==0, N%%16==0, N<=256, 2K+N<=512");
     const size_t smem = 2 * (size_t)N * K * sizeof(float);

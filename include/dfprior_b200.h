@@ -184,6 +184,9 @@ int dfp_tsdf_sample(const DfpScene* scene, const DfpPoints* pts, float* tsdf_out
 int64_t dfp_launch_count(void);
 /* 1 (default): MLP layers on the tcgen05 tensor cores (3xTF32); 0: fp32 SIMT kernels.  Env DFP_TENSOR_CORES=0 too. */
 int dfp_set_tensor_cores(int on);
+/* development probe of tcgen05 shared-memory descriptor semantics (see csrc/dfp_tc_selftest.cu) */
+int dfp_probe_tc(float* D, int32_t N, int32_t b_mn, int32_t lbo, int32_t sbo, int32_t k_hot, int32_t layout_type,
+                 int32_t start_off, void* stream);
 /* tensor-core self test: D[128,N] = A[128,K] * W[N,K]^T through the tcgen05/TMEM path (split=1: 3xTF32) */
 int dfp_selftest_tc(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t split, void* stream);
 int dfp_timing_enable(int on);

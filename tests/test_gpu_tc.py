@@ -50,3 +50,34 @@ def test_tensor_core_and_simt_paths_agree(stage):
     scale = float(raw_sm[:, 3][raw_sm[:, 3] != 100].abs().max())
     assert float((raw_tc - raw_sm).abs().max()) <= 1e-5 * max(scale, 1.0)
     assert float((w_tc - w_sm).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("J,KIN", [(32, 32), (64, 96), (32, 64)])
+def test_tc_transposed_weight_view(J, KIN):
+    """dH pattern: D = A[128,J] @ Wf[J,KIN] through the MN-major view of the canonical (forward) weight buffer."""
+    from attentive_dfprior_b200 import _lib as L
+    lib = L.lib()
+    g = torch.Generator().manual_seed(J * 100 + KIN)
+    A = torch.randn(128, J, generator=g).cuda()
+    Wf = torch.randn(J, KIN, generator=g).cuda()
+    D = torch.full((128, KIN), float("nan"), device="cuda")
+    L.check(lib.dfp_selftest_tc(A.data_ptr(), Wf.data_ptr(), D.data_ptr(), J, KIN, 11, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = A.double() @ Wf.double()
+    assert float((D.double() - ref).abs().max()) / float(ref.abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize("F,N", [(32, 32), (32, 64), (4, 16), (32, 16)])
+def test_tc_outer_product_from_smem(F, N):
+    """dW pattern: D[:F] = H[128,F]^T @ Dl[128,N], both operands sample-major tiles in shared memory, M=128 over-read."""
+    from attentive_dfprior_b200 import _lib as L
+    lib = L.lib()
+    g = torch.Generator().manual_seed(F * 100 + N)
+    H = torch.randn(128, F, generator=g).cuda()
+    Dl = torch.randn(128, N, generator=g).cuda()
+    D = torch.full((128, N), float("nan"), device="cuda")
+    L.check(lib.dfp_selftest_tc(H.data_ptr(), Dl.data_ptr(), D.data_ptr(), F, N, 12, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = H.double().t() @ Dl.double()
+    # the delta operand is used in TF32 (hi part only): ~2^-12 relative per product
+    assert float((D[:F].double() - ref).abs().max()) / float(ref.abs().max()) <= 3e-4
