@@ -13,7 +13,8 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfprior_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+FLAG_SAVE_ACT = 1
 MAX_RAY_SAMPLES = 64
 N_PARAM_TENSORS = 79
 N_PARAMS = 86029
@@ -44,6 +45,7 @@ class DfpRays(C.Structure):
 
 class DfpCfg(C.Structure):
     _fields_ = [("stage", C.c_int32), ("n_samples", C.c_int32), ("n_surface", C.c_int32), ("n_importance", C.c_int32),
+                ("flags", C.c_int32), ("reserved", C.c_int32),
                 ("t_vals", C.c_float * MAX_RAY_SAMPLES), ("one_minus_t", C.c_float * MAX_RAY_SAMPLES),
                 ("t_surf", C.c_double * MAX_RAY_SAMPLES), ("one_minus_t_surf", C.c_double * MAX_RAY_SAMPLES)]
 
@@ -63,7 +65,8 @@ class DfpGrads(C.Structure):
 
 
 class DfpPoints(C.Structure):
-    _fields_ = [("p", C.c_void_p), ("is_f64", C.c_int32), ("apply_bound_mask", C.c_int32), ("n", C.c_int64)]
+    _fields_ = [("p", C.c_void_p), ("is_f64", C.c_int32), ("apply_bound_mask", C.c_int32), ("n", C.c_int64),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/dfprior_b200.h declares: name -> (restype, argtypes)
@@ -75,12 +78,12 @@ SYMBOLS = {
     "dfp_unpack_param_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfp_grid_to_ndhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dfp_grid_to_cdhw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
-    "dfp_render_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int64]),
+    "dfp_render_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int32]),
     "dfp_render_fwd": (C.c_int, [C.POINTER(DfpScene), C.c_void_p, C.POINTER(DfpRays), C.POINTER(DfpCfg),
                                  C.POINTER(DfpRenderOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "dfp_render_bwd": (C.c_int, [C.POINTER(DfpScene), C.c_void_p, C.POINTER(DfpRays), C.POINTER(DfpCfg),
                                  C.POINTER(DfpRenderOutGrad), C.POINTER(DfpGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
-    "dfp_points_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "dfp_points_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "dfp_points_fwd": (C.c_int, [C.POINTER(DfpScene), C.c_void_p, C.POINTER(DfpPoints), C.c_int32, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dfp_points_bwd": (C.c_int, [C.POINTER(DfpScene), C.c_void_p, C.POINTER(DfpPoints), C.c_int32, C.c_void_p,
@@ -88,6 +91,7 @@ SYMBOLS = {
     "dfp_tsdf_sample": (C.c_int, [C.POINTER(DfpScene), C.POINTER(DfpPoints), C.c_void_p, C.c_void_p]),
     "dfp_launch_count": (C.c_int64, []),
     "dfp_set_tensor_cores": (C.c_int, [C.c_int]),
+    "dfp_set_tc_backward": (C.c_int, [C.c_int]),
     "dfp_probe_tc": (C.c_int, [C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
     "dfp_selftest_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dfp_timing_enable": (C.c_int, [C.c_int]),

@@ -23,6 +23,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "dfp_device.cuh"
@@ -88,6 +89,21 @@ bool use_tensor_cores() {
     return v != 0;
 }
 
+// DFP_TC_BACKWARD: 0 = SIMT recompute backward, 1 = tensor-core delta chain + SIMT weight gradients (debug),
+// 2 (default) = tensor-core delta chain and weight gradients
+static std::atomic<int> g_tcb{-1};
+static int tc_backward_level() {
+    int v = g_tcb.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("DFP_TC_BACKWARD");
+        v = e ? atoi(e) : 2;
+        g_tcb.store(v);
+    }
+    return v;
+}
+// the saved-activation path exists only on the tensor-core kernels
+static int train_flags(int flags) { return use_tensor_cores() ? (flags & DFP_FLAG_SAVE_ACT) : 0; }
+
 static int g_num_sms = 0;
 int num_sms() {
     if (g_num_sms == 0) {
@@ -104,7 +120,7 @@ int num_sms() {
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with_z) {
+static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with_z, int stage = DFP_STAGE_COLOR, int flags = 0) {
     size_t off = 0;
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
     w.z = (double*)take(with_z ? ns * sizeof(double) : 0);
@@ -116,6 +132,17 @@ static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with
     w.d_low = (float*)take(ns * 4); w.d_high = (float*)take(ns * 4); w.d_fused = (float*)take(ns * 4);
     w.d_rgb = (float*)take(ns * 16);
     w.dp = (float*)take(ns * 12);
+    const bool act = (flags & DFP_FLAG_SAVE_ACT) != 0;
+    for (int d = 0; d < 3; ++d) {
+        const bool used = act && (d == 0 || (d == 1 && stage >= DFP_STAGE_HIGH) || (d == 2 && stage == DFP_STAGE_COLOR));
+        w.act_h[d] = (float*)take(used ? ns * 160 * 4 : 0);
+        w.act_m[d] = (uint32_t*)take(used ? ns * 5 * 4 : 0);
+        w.act_c[d] = (float*)take(used ? ns * (d == 1 ? 64 : 32) * 4 : 0);
+        if (!used) { w.act_h[d] = nullptr; w.act_m[d] = nullptr; w.act_c[d] = nullptr; }
+    }
+    w.sc_e = (float*)take(act ? ns * 96 * 4 : 0);
+    w.sc_dh = (float*)take(act ? ns * 160 * 4 : 0);
+    w.sc_darg = (float*)take(act ? ns * 96 * 4 : 0);
     return off;
 }
 
@@ -430,7 +457,7 @@ static int check_scene(const DfpScene* sc, int stage) {
 // forward of everything between "points are known" and "low/high/rgb/fused/w/flags are in the workspace"
 template <int MODE>
 static int eval_samples_fwd(const DfpScene* sc, const float* params, const PointSrc& ps, int64_t n, int stage,
-                            int apply_mask, const Ws& w, cudaStream_t st) {
+                            int apply_mask, const Ws& w, int flags, cudaStream_t st) {
     const bool hi = stage >= DFP_STAGE_HIGH;
     if (hi) DFP_CUDA(cudaMemsetAsync(w.band_count, 0, 16, st));
     PrepArgs pa;
@@ -445,14 +472,21 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
     da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params;
     int rc;
     const bool tcp = use_tensor_cores();
+    const bool save = tcp && (flags & DFP_FLAG_SAVE_ACT);
+    auto set_act = [&](int d) {
+        da.act_h = save ? w.act_h[d] : nullptr; da.act_m = save ? w.act_m[d] : nullptr; da.act_c = save ? w.act_c[d] : nullptr;
+    };
     if (hi) {
+        set_act(1);
         da.grid = sc->high; da.grid_low = sc->low; da.out = w.high;
         if ((rc = tcp ? launch_decoder_fwd_tc<1, MODE>(da, st) : launch_decoder_fwd<1, MODE>(da, st))) return rc;
     }
     if (stage == DFP_STAGE_COLOR) {
+        set_act(2);
         da.grid = sc->color; da.out = w.rgb;
         if ((rc = tcp ? launch_decoder_fwd_tc<2, MODE>(da, st) : launch_decoder_fwd<2, MODE>(da, st))) return rc;
     }
+    set_act(0);
     da.grid = sc->low; da.out = w.low;
     if ((rc = tcp ? launch_decoder_fwd_tc<0, MODE>(da, st) : launch_decoder_fwd<0, MODE>(da, st))) return rc;
     if (hi) {
@@ -468,7 +502,7 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
 // backward counterpart: d_low / d_high / d_fused / d_rgb / dp seeded in the workspace
 template <int MODE>
 static int eval_samples_bwd(const DfpScene* sc, const float* params, const PointSrc& ps, int64_t n, int stage,
-                            const float* g_w, const DfpGrads* g, bool want_dp, const Ws& w, cudaStream_t st) {
+                            const float* g_w, const DfpGrads* g, bool want_dp, const Ws& w, int flags, cudaStream_t st) {
     const bool hi = stage >= DFP_STAGE_HIGH;
     int rc;
     if (hi) {
@@ -485,16 +519,30 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
     memset(&da, 0, sizeof(da));
     da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params;
     da.gparams = g->params_packed; da.dp = want_dp ? w.dp : nullptr;
+    // tensor-core backward (needs the activations saved by the tensor-core forward): K1 = delta chain, K2 = weight grads
+    const bool tcb = use_tensor_cores() && (flags & DFP_FLAG_SAVE_ACT) && w.act_h[0] != nullptr && tc_backward_level() > 0;
+    da.sc_e = w.sc_e; da.sc_dh = w.sc_dh; da.sc_darg = w.sc_darg;
+    auto run = [&](auto dec_tag) -> int {
+        constexpr int DEC = decltype(dec_tag)::value;
+        if (!tcb) return launch_decoder_bwd<DEC, MODE>(da, st);
+        da.act_h = w.act_h[DEC]; da.act_m = w.act_m[DEC]; da.act_c = w.act_c[DEC];
+        int r = launch_decoder_dh_tc<DEC, MODE>(da, st);
+        if (r || !da.gparams) return r;
+        if (tc_backward_level() >= 2) return launch_decoder_dw_tc<DEC>(da, st);
+        DecArgs pa = da;                    // level 1 (debug): parameter gradients from the SIMT kernel
+        pa.ggrid = nullptr; pa.dp = nullptr;
+        return launch_decoder_bwd<DEC, MODE>(pa, st);
+    };
     if (hi) {
         da.grid = sc->high; da.grid_low = sc->low; da.dout = w.d_high; da.ggrid = g->grid_high;
-        if ((rc = launch_decoder_bwd<1, MODE>(da, st))) return rc;
+        if ((rc = run(std::integral_constant<int, 1>{}))) return rc;
     }
     if (stage == DFP_STAGE_COLOR) {
         da.grid = sc->color; da.dout = w.d_rgb; da.ggrid = g->grid_color;
-        if ((rc = launch_decoder_bwd<2, MODE>(da, st))) return rc;
+        if ((rc = run(std::integral_constant<int, 2>{}))) return rc;
     }
     da.grid = sc->low; da.dout = w.d_low; da.ggrid = g->grid_low;
-    if ((rc = launch_decoder_bwd<0, MODE>(da, st))) return rc;
+    if ((rc = run(std::integral_constant<int, 0>{}))) return rc;
     return DFP_OK;
 }
 
@@ -535,6 +583,10 @@ int dfp_probe_tc(float* D, int32_t N, int32_t b_mn, int32_t lbo, int32_t sbo, in
 
 int dfp_set_tensor_cores(int on) {
     g_tc.store(on ? 1 : 0);
+    return DFP_OK;
+}
+int dfp_set_tc_backward(int level) {
+    g_tcb.store(level);
     return DFP_OK;
 }
 
@@ -613,16 +665,16 @@ static int transpose_grid(const float* src, float* dst, int32_t C, int32_t D, in
 int dfp_grid_to_ndhwc(const float* s, float* d, int32_t C, int32_t D, int32_t H, int32_t W, void* st) { return transpose_grid(s, d, C, D, H, W, 1, st); }
 int dfp_grid_to_cdhw(const float* s, float* d, int32_t C, int32_t D, int32_t H, int32_t W, void* st) { return transpose_grid(s, d, C, D, H, W, 0, st); }
 
-size_t dfp_render_workspace_bytes(int64_t n_rays, int32_t S, int64_t chunk) {
+size_t dfp_render_workspace_bytes(int64_t n_rays, int32_t S, int64_t chunk, int32_t stage, int32_t flags) {
     if (n_rays < 0 || S < 1) return 0;
     if (chunk <= 0) chunk = n_rays > 0 ? n_rays : 1;
     Ws w;
-    return carve_ws(w, nullptr, n_rays * S, (n_rays + chunk - 1) / chunk, true);
+    return carve_ws(w, nullptr, n_rays * S, (n_rays + chunk - 1) / chunk, true, stage, train_flags(flags));
 }
-size_t dfp_points_workspace_bytes(int64_t n) {
+size_t dfp_points_workspace_bytes(int64_t n, int32_t stage, int32_t flags) {
     if (n < 0) return 0;
     Ws w;
-    return carve_ws(w, nullptr, n, 1, false);
+    return carve_ws(w, nullptr, n, 1, false, stage, train_flags(flags));
 }
 
 int dfp_render_fwd(const DfpScene* sc, const float* params, const DfpRays* rays, const DfpCfg* cfg,
@@ -642,7 +694,8 @@ int dfp_render_fwd(const DfpScene* sc, const float* params, const DfpRays* rays,
     const int64_t chunk = rays->chunk > 0 ? rays->chunk : N;
     const int64_t nchunks = (N + chunk - 1) / chunk;
     Ws w;
-    const size_t need = carve_ws(w, (char*)workspace, NS, nchunks, true);
+    const int flags = train_flags(cfg->flags);
+    const size_t need = carve_ws(w, (char*)workspace, NS, nchunks, true, cfg->stage, flags);
     if (need > ws_bytes) return fail(DFP_ERR_WORKSPACE, "workspace too small: need %zu bytes, have %zu", need, ws_bytes);
     cudaStream_t st = (cudaStream_t)stream;
 
@@ -661,8 +714,8 @@ int dfp_render_fwd(const DfpScene* sc, const float* params, const DfpRays* rays,
     DFP_LAUNCH_CHECK("k_sample_z");
 
     PointSrc ps;
-    ps.rays_o = rays->rays_o; ps.rays_d = rays->rays_d; ps.z = w.z; ps.S = S; ps.pts = nullptr;
-    if ((rc = eval_samples_fwd<0>(sc, params, ps, NS, cfg->stage, 1, w, st))) return rc;
+    ps.rays_o = rays->rays_o; ps.rays_d = rays->rays_d; ps.z = w.z; ps.S = S; ps.pts = nullptr; ps.pts_f64 = 0;
+    if ((rc = eval_samples_fwd<0>(sc, params, ps, NS, cfg->stage, 1, w, flags, st))) return rc;
 
     CompArgs ca;
     memset(&ca, 0, sizeof(ca));
@@ -688,7 +741,8 @@ int dfp_render_bwd(const DfpScene* sc, const float* params, const DfpRays* rays,
     if (N < 1) return fail(DFP_ERR_INVALID, "n_rays must be >= 1");
     const int64_t chunk = rays->chunk > 0 ? rays->chunk : N;
     Ws w;
-    const size_t need = carve_ws(w, (char*)workspace, NS, (N + chunk - 1) / chunk, true);
+    const int flags = train_flags(cfg->flags);
+    const size_t need = carve_ws(w, (char*)workspace, NS, (N + chunk - 1) / chunk, true, cfg->stage, flags);
     if (need > ws_bytes) return fail(DFP_ERR_WORKSPACE, "workspace too small: need %zu bytes, have %zu", need, ws_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     const bool want_dp = g->rays_o || g->rays_d;
@@ -703,8 +757,8 @@ int dfp_render_bwd(const DfpScene* sc, const float* params, const DfpRays* rays,
     DFP_LAUNCH_CHECK("k_composite_bwd");
 
     PointSrc ps;
-    ps.rays_o = rays->rays_o; ps.rays_d = rays->rays_d; ps.z = w.z; ps.S = S; ps.pts = nullptr;
-    if ((rc = eval_samples_bwd<0>(sc, params, ps, NS, cfg->stage, og->weight, g, want_dp, w, st))) return rc;
+    ps.rays_o = rays->rays_o; ps.rays_d = rays->rays_d; ps.z = w.z; ps.S = S; ps.pts = nullptr; ps.pts_f64 = 0;
+    if ((rc = eval_samples_bwd<0>(sc, params, ps, NS, cfg->stage, og->weight, g, want_dp, w, flags, st))) return rc;
     if (want_dp) {
         DFP_TIMED("k_ray_grad", st, k_ray_grad<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(N, S, w.dp, w.z, g->rays_o, g->rays_d));
         DFP_LAUNCH_CHECK("k_ray_grad");
@@ -720,14 +774,15 @@ int dfp_points_fwd(const DfpScene* sc, const float* params, const DfpPoints* pts
     if (pts->n < 1 || !pts->p) return fail(DFP_ERR_INVALID, "no points");
     if (pts->n > 0x7fffffffLL) return fail(DFP_ERR_INVALID, "too many points in one call");
     Ws w;
-    const size_t need = carve_ws(w, (char*)workspace, pts->n, 1, false);
+    const int flags = train_flags(pts->flags);
+    const size_t need = carve_ws(w, (char*)workspace, pts->n, 1, false, stage, flags);
     if (need > ws_bytes) return fail(DFP_ERR_WORKSPACE, "workspace too small: need %zu bytes, have %zu", need, ws_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     PointSrc ps;
     memset(&ps, 0, sizeof(ps));
-    ps.pts = pts->p; ps.S = 1;
-    if (pts->is_f64) rc = eval_samples_fwd<1>(sc, params, ps, pts->n, stage, pts->apply_bound_mask, w, st);
-    else rc = eval_samples_fwd<2>(sc, params, ps, pts->n, stage, pts->apply_bound_mask, w, st);
+    ps.pts = pts->p; ps.S = 1; ps.pts_f64 = pts->is_f64;
+    if (pts->is_f64) rc = eval_samples_fwd<1>(sc, params, ps, pts->n, stage, pts->apply_bound_mask, w, flags, st);
+    else rc = eval_samples_fwd<2>(sc, params, ps, pts->n, stage, pts->apply_bound_mask, w, flags, st);
     if (rc) return rc;
     PtsArgs pa;
     memset(&pa, 0, sizeof(pa));
@@ -745,7 +800,8 @@ int dfp_points_bwd(const DfpScene* sc, const float* params, const DfpPoints* pts
     if (rc) return rc;
     if (pts->n < 1 || !pts->p) return fail(DFP_ERR_INVALID, "no points");
     Ws w;
-    const size_t need = carve_ws(w, (char*)workspace, pts->n, 1, false);
+    const int flags = train_flags(pts->flags);
+    const size_t need = carve_ws(w, (char*)workspace, pts->n, 1, false, stage, flags);
     if (need > ws_bytes) return fail(DFP_ERR_WORKSPACE, "workspace too small: need %zu bytes, have %zu", need, ws_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     const bool want_dp = g->points != nullptr;
@@ -757,9 +813,9 @@ int dfp_points_bwd(const DfpScene* sc, const float* params, const DfpPoints* pts
     DFP_LAUNCH_CHECK("k_points_seed_bwd");
     PointSrc ps;
     memset(&ps, 0, sizeof(ps));
-    ps.pts = pts->p; ps.S = 1;
-    if (pts->is_f64) rc = eval_samples_bwd<1>(sc, params, ps, pts->n, stage, g_w, g, want_dp, w, st);
-    else rc = eval_samples_bwd<2>(sc, params, ps, pts->n, stage, g_w, g, want_dp, w, st);
+    ps.pts = pts->p; ps.S = 1; ps.pts_f64 = pts->is_f64;
+    if (pts->is_f64) rc = eval_samples_bwd<1>(sc, params, ps, pts->n, stage, g_w, g, want_dp, w, flags, st);
+    else rc = eval_samples_bwd<2>(sc, params, ps, pts->n, stage, g_w, g, want_dp, w, flags, st);
     if (rc) return rc;
     if (want_dp) {
         const unsigned blocks = (unsigned)((3 * pts->n + 255) / 256);
@@ -776,7 +832,7 @@ int dfp_tsdf_sample(const DfpScene* sc, const DfpPoints* pts, float* out, void* 
     if (pts->n < 1) return fail(DFP_ERR_INVALID, "no points");
     PointSrc ps;
     memset(&ps, 0, sizeof(ps));
-    ps.pts = pts->p; ps.S = 1;
+    ps.pts = pts->p; ps.S = 1; ps.pts_f64 = pts->is_f64;
     const unsigned blocks = (unsigned)((pts->n + 255) / 256);
     if (pts->is_f64) DFP_TIMED("k_tsdf_sample", (cudaStream_t)stream, k_tsdf_sample<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(ps, pts->n, to_bounds(sc->tsdf_bnds), sc->tsdf, out));
     else DFP_TIMED("k_tsdf_sample", (cudaStream_t)stream, k_tsdf_sample<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(ps, pts->n, to_bounds(sc->tsdf_bnds), sc->tsdf, out));

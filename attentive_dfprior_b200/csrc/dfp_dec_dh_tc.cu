@@ -1,0 +1,287 @@
+// Tensor-core decoder backward, kernel 1 of 2: the delta chain.
+//
+// For tiles of 128 samples (one thread = one sample = one TMEM lane) this back-propagates through the five blocks
+// of one decoder (src/conv_onet/models/decoder.py:192-203 reversed) using the activations the tensor-core forward
+// kept (ReLU masks): per block  d_c += dh_i * Wc_i  and  dh_{i-1} = mask_i(dh_i) * W_i  run as tcgen05.mma with the
+// deltas written into TMEM by their owner threads and the weights resident in shared memory in their natural
+// [out][in] layout (the MN-major / transposed B operand, dfp_tc.cuh).  The embedding gradient
+// d_e = [dacc_0 | dacc_3] * [W_0 ; W_3e] is one K=64, N=96 product.  Outputs: the feature gradient scattered into
+// the dense grid gradient (vector reductions), d(point) for the Tracker, and -- for kernel 2 (dfp_dec_dw_tc.cu) --
+// the per-block deltas, sin(arg) and d(arg) in the feature-major scratch arrays.
+#include "dfp_device.cuh"
+#include "dfp_tc.cuh"
+
+namespace dfp {
+
+struct DhLayout {                                       // shared memory, in floats
+    static constexpr int WH = 0;                        // 4 tiles [32 j][32 kin]: pts_linears.1, .2, .3[:, 93:], .4
+    static constexpr int W03 = WH + 4 * 1024;           // 3 column blocks of [64 j][32 kin]: rows 0..31 pts_linears.0, 32..63 pts_linears.3[:, :93]
+    static constexpr int WC = W03 + 3 * 2048;           // 5 tiles [32 j][32 kin]: fc_c.i restricted to this decoder's own grid features
+    static constexpr int BSIZE = WC + 5 * 1024;         // one split half (hi or lo)
+    static constexpr int S_WO = 2 * BSIZE;              // [4][32] output rows
+    static constexpr int S_B = S_WO + 128;              // [3][96] embedding matrix
+    static constexpr int FLOATS = S_B + 288;
+    // TMEM columns of one 128-sample group
+    static constexpr int T_A = 0;                       // 128 columns of A operands (see kernel)
+    static constexpr int T_DC = 128;                    // d_c accumulator
+    static constexpr int T_DX = 160;                    // dh_{i-1} (32) / d_e (96)
+    static constexpr int T_COLS = 256;
+};
+
+template <int CD>
+__device__ __forceinline__ void stage_weights_dh(float* sm, const float* __restrict__ P) {
+    using L = DecOff<CD>;
+    float* hi = sm;
+    float* lo = sm + DhLayout::BSIZE;
+    const int nt = blockDim.x;
+    for (int i = threadIdx.x; i < 4 * 1024; i += nt) {                 // packed WH: [slot][kin][j]
+        const int slot = i >> 10, kin = (i >> 5) & 31, j = i & 31;
+        const float w = P[L::WH + i];
+        const float h = tc::tf32_rna(w);
+        const int o = DhLayout::WH + slot * 1024 + tc::mn_tile_index(j, kin);
+        hi[o] = h; lo[o] = tc::tf32_rna(w - h);
+    }
+    for (int i = threadIdx.x; i < 96 * 64; i += nt) {                  // packed W03: [kin][64 j]
+        const int kin = i >> 6, j = i & 63;
+        const float w = (kin < EMB) ? P[L::W03 + i] : 0.f;
+        const float h = tc::tf32_rna(w);
+        const int o = DhLayout::W03 + (kin >> 5) * 2048 + tc::mn_tile_index(j, kin & 31);
+        hi[o] = h; lo[o] = tc::tf32_rna(w - h);
+    }
+    for (int i = threadIdx.x; i < 5 * 1024; i += nt) {                 // packed WC: [layer][kin < CD][j], first 32 kin only
+        const int layer = i >> 10, kin = (i >> 5) & 31, j = i & 31;
+        const float w = P[L::WC + layer * CD * 32 + kin * 32 + j];
+        const float h = tc::tf32_rna(w);
+        const int o = DhLayout::WC + layer * 1024 + tc::mn_tile_index(j, kin);
+        hi[o] = h; lo[o] = tc::tf32_rna(w - h);
+    }
+    for (int i = threadIdx.x; i < 128; i += nt) sm[DhLayout::S_WO + i] = P[L::WO + i];
+    for (int i = threadIdx.x; i < 288; i += nt) sm[DhLayout::S_B + i] = P[L::B + i];
+}
+
+// OR-reduction of a predicate over the 128 threads of one group (named barrier `id`)
+__device__ __forceinline__ bool group_any(bool v, int id) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "barrier.cta.red.or.pred p, %2, 128, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"((uint32_t)v), "r"(id)
+        : "memory");
+    return r != 0;
+}
+
+template <int DEC, int MODE>
+__global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
+    constexpr int CD = (DEC == 1) ? 64 : 32;
+    constexpr int NOUT = (DEC == 2) ? 4 : 1;
+    using PT = typename PtT<MODE>::T;
+    using T = DhLayout;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int grp = tid >> 7, gt = tid & 127;
+    stage_weights_dh<CD>(sm, a.params + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR)));
+    if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+    if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_mbar_init(); }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+
+    const uint32_t tb = tmem_base_s + (uint32_t)(grp * T::T_COLS);
+    const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16);
+    uint64_t* bar = &bars[grp];
+    uint32_t parity = 0;
+    const uint32_t whi = tc::smem_u32(sm), wlo = tc::smem_u32(sm + T::BSIZE);
+    const BoxT<PT> box = make_box<PT>(a.bound.b);
+    const int64_t tiles = (a.n + 127) / 128;
+    const bool issuer = (gt == 0);
+    const float bmax = embed_bmax(sm + T::S_B);
+    const int64_t n = a.n;
+
+    for (int64_t tile = (int64_t)blockIdx.x * 2 + grp; tile < tiles; tile += (int64_t)gridDim.x * 2) {
+        const int64_t s_raw = tile * 128 + gt;
+        const bool valid = s_raw < n;
+        const int64_t s = valid ? s_raw : n - 1;
+        float dout[NOUT];
+        if (NOUT == 1) dout[0] = valid ? a.dout[s] : 0.f;
+        else {
+            const float4 v = *reinterpret_cast<const float4*>(a.dout + 4 * s);
+            dout[0] = valid ? v.x : 0.f; dout[NOUT > 1 ? 1 : 0] = valid ? v.y : 0.f; dout[NOUT > 2 ? 2 : 0] = valid ? v.z : 0.f;
+            dout[NOUT > 3 ? 3 : 0] = 0.f;                    // the colour decoder's 4th output is overwritten (decoder.py:352)
+        }
+        bool any = false;
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) any = any || (dout[o] != 0.f);
+        // kernel 2 reads the scratch of every sample of a tile it processes, so a skipped tile is marked by zero deltas:
+        // it decides with the same predicate (all upstream gradients of the tile are zero)
+        if (!group_any(any, 1 + grp)) continue;
+
+        float dh[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) acc = fmaf(sm[T::S_WO + o * 32 + j], dout[o], acc);
+            dh[j] = acc;
+        }
+        float dacc3[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dacc3[j] = 0.f;
+
+#pragma unroll 1
+        for (int i = 4; i >= 1; --i) {
+            const uint32_t m = a.act_m[(int64_t)i * n + s];
+            float dacc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dacc[j] = ((m >> j) & 1u) ? dh[j] : 0.f;
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a.sc_dh[(int64_t)(i * 32 + j) * n + s] = dh[j];
+            }
+            tc::tmem_store_split32(tl + T::T_A, tl + T::T_A + 32, dh);            // for d_c += dh_i * Wc_i
+            tc::tmem_store_split32(tl + T::T_A + 64, tl + T::T_A + 96, dacc);     // for dh_{i-1} = dacc_i * W_i
+            tc::wait_st();
+            tc::fence_before_sync();
+            tc::named_bar_sync(3 + grp, 128);
+            if (issuer) {
+                tc::fence_after_sync();
+                tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + (T::WC + i * 1024) * 4, wlo + (T::WC + i * 1024) * 4,
+                                  32, 32, 4096u, i != 4);
+                tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A + 64, tb + T::T_A + 96, whi + (T::WH + (i - 1) * 1024) * 4,
+                                  wlo + (T::WH + (i - 1) * 1024) * 4, 32, 32, 4096u, false);
+                tc::mma_commit(bar);
+            }
+            if (i == 3) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dacc3[j] = dacc[j];
+            }
+            tc::mbar_wait(bar, parity); parity ^= 1;
+            tc::fence_after_sync();
+            tc::tmem_ld32(tl + T::T_DX, dh);
+            tc::wait_ld();
+        }
+        // block 0: fc_c[0] path, then the embedding
+        {
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a.sc_dh[(int64_t)j * n + s] = dh[j];
+            }
+            tc::tmem_store_split32(tl + T::T_A, tl + T::T_A + 32, dh);
+            tc::wait_st();
+            tc::fence_before_sync();
+            tc::named_bar_sync(3 + grp, 128);
+            if (issuer) {
+                tc::fence_after_sync();
+                tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + T::WC * 4, wlo + T::WC * 4, 32, 32, 4096u, true);
+                tc::mma_commit(bar);
+            }
+            const uint32_t m0 = a.act_m[s];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dh[j] = ((m0 >> j) & 1u) ? dh[j] : 0.f;      // dacc_0
+            tc::mbar_wait(bar, parity); parity ^= 1;
+            tc::fence_after_sync();
+            // A = [dacc_0 | dacc_3]: hi in columns 0..63, lo in 64..127
+            {
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tc::split_tf32(dh[j], hi[j], lo[j]);
+                tc::tmem_st32(tl + T::T_A, hi);
+                tc::tmem_st32(tl + T::T_A + 64, lo);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tc::split_tf32(dacc3[j], hi[j], lo[j]);
+                tc::tmem_st32(tl + T::T_A + 32, hi);
+                tc::tmem_st32(tl + T::T_A + 96, lo);
+            }
+            tc::wait_st();
+            tc::fence_before_sync();
+            tc::named_bar_sync(3 + grp, 128);
+            if (issuer) {
+                tc::fence_after_sync();
+                tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A, tb + T::T_A + 64, whi + T::W03 * 4, wlo + T::W03 * 4, 64, 96, 8192u, false);
+                tc::mma_commit(bar);
+            }
+        }
+        // while the embedding product runs: point, trilinear set-up
+        PT p[3];
+        load_point<MODE>(a.ps, s, p);
+        float xn[3];
+        normalize(p, box, xn);
+        const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
+        const bool fast = embed_fast_ok(pf, bmax);
+        const Tri tri = tri_setup(xn, a.grid.W, a.grid.H, a.grid.D);
+        tc::mbar_wait(bar, parity); parity ^= 1;
+        tc::fence_after_sync();
+        float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < 3; ++ch) {
+            float de[32];
+            tc::tmem_ld32(tl + T::T_DX + ch * 32, de);
+            tc::wait_ld();
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) {
+                const int k = ch * 32 + kk;
+                float sn = (k == EMB) ? 1.f : 0.f, da = 0.f;     // column 93 of the sin array is the constant 1 kernel 2 uses for the bias of block 0
+                if (k < EMB) {
+                    const float arg = embed_arg(sm + T::S_B, pf, k);
+                    float cs;
+                    if (fast) sincos_cw(arg, sn, cs);
+                    else sincosf(arg, &sn, &cs);
+                    da = de[kk] * cs;
+                    gp0 = fmaf(sm[T::S_B + k], da, gp0);
+                    gp1 = fmaf(sm[T::S_B + EMB_PAD + k], da, gp1);
+                    gp2 = fmaf(sm[T::S_B + 2 * EMB_PAD + k], da, gp2);
+                }
+                if (valid && a.gparams) {
+                    a.sc_e[(int64_t)k * n + s] = sn;
+                    a.sc_darg[(int64_t)k * n + s] = da;
+                }
+            }
+        }
+        float d_c[32];
+        tc::tmem_ld32(tl + T::T_DC, d_c);
+        tc::wait_ld();
+        if (valid && any) {
+            const bool want_coord = a.dp != nullptr;
+            float gn[3] = {0.f, 0.f, 0.f};
+            if (a.ggrid || want_coord) scatter_features(a.grid, a.ggrid, tri, d_c, want_coord, gn);
+            if (want_coord) {
+                a.dp[3 * s + 0] += gn[0] * (float)(2.0 / (a.bound.b[0][1] - a.bound.b[0][0])) + gp0;
+                a.dp[3 * s + 1] += gn[1] * (float)(2.0 / (a.bound.b[1][1] - a.bound.b[1][0])) + gp1;
+                a.dp[3 * s + 2] += gn[2] * (float)(2.0 / (a.bound.b[2][1] - a.bound.b[2][0])) + gp2;
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+template <int DEC, int MODE>
+int launch_decoder_dh_tc(const DecArgs& a, cudaStream_t st) {
+    const size_t smem = DhLayout::FLOATS * sizeof(float) + 1024;
+    int rc = set_smem(k_decoder_dh_tc<DEC, MODE>, smem);
+    if (rc) return rc;
+    const int64_t tiles = (a.n + 127) / 128;
+    const int blocks = grid_for(tiles, 2, num_sms());
+    DFP_TIMED("k_decoder_dh_tc", st, k_decoder_dh_tc<DEC, MODE><<<blocks, 256, smem, st>>>(a));
+    DFP_LAUNCH_CHECK("k_decoder_dh_tc");
+    return DFP_OK;
+}
+template int launch_decoder_dh_tc<0, 0>(const DecArgs&, cudaStream_t);
+template int launch_decoder_dh_tc<1, 0>(const DecArgs&, cudaStream_t);
+template int launch_decoder_dh_tc<2, 0>(const DecArgs&, cudaStream_t);
+template int launch_decoder_dh_tc<0, 1>(const DecArgs&, cudaStream_t);
+template int launch_decoder_dh_tc<1, 1>(const DecArgs&, cudaStream_t);
+template int launch_decoder_dh_tc<2, 1>(const DecArgs&, cudaStream_t);
+template int launch_decoder_dh_tc<0, 2>(const DecArgs&, cudaStream_t);
+template int launch_decoder_dh_tc<1, 2>(const DecArgs&, cudaStream_t);
+template int launch_decoder_dh_tc<2, 2>(const DecArgs&, cudaStream_t);
+
+}  // namespace dfp

@@ -112,9 +112,17 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
             float c[32];
             gather_features(a.grid, tri_setup(xn, a.grid.W, a.grid.H, a.grid.D), c);
             tc::tmem_store_split32(tl + T::T_C_HI, tl + T::T_C_LO, c);
+            if (a.act_c && valid) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) a.act_c[(int64_t)k * a.n + s] = c[k];
+            }
             if (DEC == 1) {
                 gather_features(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), c);
                 tc::tmem_store_split32(tl + T::T_C_HI + 32, tl + T::T_C_LO + 32, c);
+                if (a.act_c && valid) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) a.act_c[(int64_t)(32 + k) * a.n + s] = c[k];
+                }
             }
         }
         // Fourier embedding in three 32-wide K chunks, each accumulated into D03 = [z0 | skip part of z3]
@@ -150,8 +158,18 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
             tc::tmem_ld32(tl + T::T_D03, z);
             tc::tmem_ld32(tl + T::T_DC, f);
             tc::wait_ld();
+            uint32_t m = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) h[j] = fmaxf(z[j] + sm[T::S_BP + j], 0.f) + (f[j] + sm[T::S_BC + j]);
+            for (int j = 0; j < 32; ++j) {
+                const float pre = z[j] + sm[T::S_BP + j];
+                m |= (pre > 0.f ? 1u : 0u) << j;
+                h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + j]);
+            }
+            if (a.act_h && valid) {                                   // kept for the backward (DFP_FLAG_SAVE_ACT)
+                a.act_m[s] = m;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a.act_h[(int64_t)j * a.n + s] = h[j];
+            }
         }
 #pragma unroll 1
         for (int i = 1; i < 5; ++i) {
@@ -181,8 +199,18 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
             } else {
                 tc::wait_ld();
             }
+            uint32_t m = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) h[j] = fmaxf(z[j] + sm[T::S_BP + i * 32 + j], 0.f) + (f[j] + sm[T::S_BC + i * 32 + j]);
+            for (int j = 0; j < 32; ++j) {
+                const float pre = z[j] + sm[T::S_BP + i * 32 + j];
+                m |= (pre > 0.f ? 1u : 0u) << j;
+                h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + i * 32 + j]);
+            }
+            if (a.act_h && valid) {
+                a.act_m[(int64_t)i * a.n + s] = m;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a.act_h[(int64_t)(i * 32 + j) * a.n + s] = h[j];
+            }
         }
         float out[NOUT];
 #pragma unroll

@@ -49,6 +49,7 @@ struct PointSrc {                  // where sample s comes from
     const double* z;
     int S;
     const void* pts;               // MODE 1: f64 [n,3]; MODE 2: f32 [n,3]
+    int pts_f64;                   // dtype tag of pts for kernels that are not templated on MODE
 };
 template <int MODE> struct PtT { using T = double; };
 template <> struct PtT<2> { using T = float; };
@@ -85,6 +86,14 @@ struct Ws {                        // per-sample workspace arrays (NS samples)
     float* d_low; float* d_high; float* d_fused;    // [NS]
     float* d_rgb;                  // [NS][4]
     float* dp;                     // [NS][3] gradient w.r.t. the sample point
+    // DFP_FLAG_SAVE_ACT: activations of the three decoders kept by the tensor-core forward, feature-major [f][NS]
+    float* act_h[3];               // [160][NS]: inputs of pts_linears.1..4 and of output_linear
+    uint32_t* act_m[3];            // [5][NS]:   ReLU masks of pts_linears.0..4
+    float* act_c[3];               // [CD][NS]:  gathered grid features
+    // scratch shared by the decoders during the tensor-core backward
+    float* sc_e;                   // [96][NS]  sin(embedding argument)
+    float* sc_dh;                  // [160][NS] gradient of each block's output (before the ReLU mask)
+    float* sc_darg;                // [96][NS]  gradient of the embedding arguments
 };
 
 
@@ -189,6 +198,8 @@ struct DecArgs {
     float* ggrid;            // gradient of `grid` (NDHWC) or null
     float* gparams;          // packed parameter gradient or null
     float* dp;               // [n][3] accumulated, or null
+    // tensor-core training path (DFP_FLAG_SAVE_ACT): saved activations / backward scratch, feature-major with stride n
+    float* act_h; uint32_t* act_m; float* act_c; float* sc_e; float* sc_dh; float* sc_darg;
 };
 
 
@@ -296,6 +307,8 @@ template <int DEC, int MODE> int launch_decoder_fwd(const DecArgs& a, cudaStream
 template <int DEC, int MODE> int launch_decoder_bwd(const DecArgs& a, cudaStream_t st);
 template <int DEC, int MODE> int launch_decoder_fwd_tc(const DecArgs& a, cudaStream_t st);   // tcgen05 path
 bool use_tensor_cores();
+template <int DEC, int MODE> int launch_decoder_dh_tc(const DecArgs& a, cudaStream_t st);      // backward K1: delta chain
+template <int DEC> int launch_decoder_dw_tc(const DecArgs& a, cudaStream_t st);                // backward K2: weight gradients
 int launch_attn_fwd(const AttArgs& a, int64_t n, cudaStream_t st);
 template <int MODE> int launch_attn_bwd(const AttArgs& a, int64_t n, cudaStream_t st);
 int launch_tc_selftest(const float* A, const float* W, float* D, int K, int N, int split, cudaStream_t st);

@@ -41,7 +41,7 @@ _bounds = _BoundsCache()
 _tables = {}
 
 
-def _cfg_struct(stage: str, n_samples: int, n_surface: int, n_importance: int = 0) -> L.DfpCfg:
+def _cfg_struct(stage: str, n_samples: int, n_surface: int, n_importance: int = 0, flags: int = 0) -> L.DfpCfg:
     key = (n_samples, n_surface)
     tab = _tables.get(key)
     if tab is None:
@@ -52,6 +52,7 @@ def _cfg_struct(stage: str, n_samples: int, n_surface: int, n_importance: int = 
     cfg = L.DfpCfg()
     cfg.stage = L.STAGES[stage]
     cfg.n_samples, cfg.n_surface, cfg.n_importance = n_samples, n_surface, n_importance
+    cfg.flags = flags
     for i in range(n_samples):
         cfg.t_vals[i] = tab[0][i]
         cfg.one_minus_t[i] = tab[1][i]
@@ -180,7 +181,8 @@ class _RenderBatchRay(torch.autograd.Function):
         grids_cl = {k: (_grid_ndhwc(given[k]) if k in _needed_grids(aux.stage) else None) for k in GRID_KEYS}
         packed = aux.pack.get(list(params))
         scene = _scene_struct(grids_cl, aux.tsdf_volume, aux.tsdf_bnds, aux.bound)
-        cfg = _cfg_struct(aux.stage, aux.n_samples, aux.n_surface, aux.n_importance)
+        flags = L.FLAG_SAVE_ACT if any(ctx.needs_input_grad) else 0
+        cfg = _cfg_struct(aux.stage, aux.n_samples, aux.n_surface, aux.n_importance, flags)
         rays = L.DfpRays(ro.data_ptr(), rd.data_ptr(), _ptr(gt), N, aux.chunk, _ptr(aux.depth_max))
         depth = torch.empty(N, device=dev, dtype=torch.float64)
         unc = torch.empty(N, device=dev, dtype=torch.float64)
@@ -188,7 +190,7 @@ class _RenderBatchRay(torch.autograd.Function):
         weight = torch.empty(N, S, 1, device=dev, dtype=torch.float32)
         z = torch.empty(N, S, device=dev, dtype=torch.float64) if aux.want_aux else None
         raw = torch.empty(N, S, 4, device=dev, dtype=torch.float32) if aux.want_aux else None
-        ws_bytes = int(lib.dfp_render_workspace_bytes(N, S, aux.chunk))
+        ws_bytes = int(lib.dfp_render_workspace_bytes(N, S, aux.chunk, L.STAGES[aux.stage], flags))
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         out = L.DfpRenderOut(depth.data_ptr(), unc.data_ptr(), color.data_ptr(), weight.data_ptr(), _ptr(z), _ptr(raw))
         L.check(lib.dfp_render_fwd(C.byref(scene), packed.data_ptr(), C.byref(rays), C.byref(cfg), C.byref(out),
@@ -197,7 +199,7 @@ class _RenderBatchRay(torch.autograd.Function):
             aux.z_vals, aux.raw = z, raw
         ctx.aux = aux
         ctx.keep = _Ctx(ro=ro, rd=rd, grids_cl=grids_cl, packed=packed, ws=ws, ws_bytes=ws_bytes, N=N, S=S,
-                        params=params, tsdf=aux.tsdf_volume)
+                        params=params, tsdf=aux.tsdf_volume, flags=flags)
         return depth, unc, color, weight
 
     @staticmethod
@@ -225,7 +227,7 @@ class _RenderBatchRay(torch.autograd.Function):
             og = L.DfpRenderOutGrad(prep(g_depth, torch.float64), prep(g_unc, torch.float64),
                                     prep(g_color, torch.float32), prep(g_weight, torch.float32))
             scene = _scene_struct(k.grids_cl, k.tsdf, aux.tsdf_bnds, aux.bound)
-            cfg = _cfg_struct(aux.stage, aux.n_samples, aux.n_surface, aux.n_importance)
+            cfg = _cfg_struct(aux.stage, aux.n_samples, aux.n_surface, aux.n_importance, k.flags)
             rays = L.DfpRays(k.ro.data_ptr(), k.rd.data_ptr(), _ptr(aux.gt_depth), k.N, aux.chunk, _ptr(aux.depth_max))
             L.check(lib.dfp_render_bwd(C.byref(scene), k.packed.data_ptr(), C.byref(rays), C.byref(cfg), C.byref(og),
                                        C.byref(g), k.ws.data_ptr(), k.ws_bytes, _stream()))
@@ -290,16 +292,17 @@ class _EvalPoints(torch.autograd.Function):
         grids_cl = {k: (_grid_ndhwc(given[k]) if k in _needed_grids(aux.stage) else None) for k in GRID_KEYS}
         packed = aux.pack.get(list(params))
         scene = _scene_struct(grids_cl, aux.tsdf_volume, aux.tsdf_bnds, aux.bound)
-        P = L.DfpPoints(p.data_ptr(), 1 if p.dtype == torch.float64 else 0, 1 if aux.apply_bound_mask else 0, n)
+        flags = L.FLAG_SAVE_ACT if any(ctx.needs_input_grad) else 0
+        P = L.DfpPoints(p.data_ptr(), 1 if p.dtype == torch.float64 else 0, 1 if aux.apply_bound_mask else 0, n, flags, 0)
         raw = torch.empty(n, 4, device=dev, dtype=torch.float32)
         w = torch.empty(n, device=dev, dtype=torch.float32)
-        ws_bytes = int(lib.dfp_points_workspace_bytes(n))
+        ws_bytes = int(lib.dfp_points_workspace_bytes(n, L.STAGES[aux.stage], flags))
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         L.check(lib.dfp_points_fwd(C.byref(scene), packed.data_ptr(), C.byref(P), L.STAGES[aux.stage],
                                    raw.data_ptr(), w.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
         ctx.aux = aux
         ctx.keep = _Ctx(p=p, grids_cl=grids_cl, packed=packed, ws=ws, ws_bytes=ws_bytes, n=n, params=params,
-                        tsdf=aux.tsdf_volume)
+                        tsdf=aux.tsdf_volume, flags=flags)
         return raw, w
 
     @staticmethod
@@ -317,7 +320,8 @@ class _EvalPoints(torch.autograd.Function):
             gr = g_raw.detach().float().contiguous() if g_raw is not None else None
             gw = g_w.detach().float().contiguous() if g_w is not None else None
             scene = _scene_struct(k.grids_cl, k.tsdf, aux.tsdf_bnds, aux.bound)
-            P = L.DfpPoints(k.p.data_ptr(), 1 if k.p.dtype == torch.float64 else 0, 1 if aux.apply_bound_mask else 0, k.n)
+            P = L.DfpPoints(k.p.data_ptr(), 1 if k.p.dtype == torch.float64 else 0, 1 if aux.apply_bound_mask else 0, k.n,
+                            k.flags, 0)
             L.check(lib.dfp_points_bwd(C.byref(scene), k.packed.data_ptr(), C.byref(P), L.STAGES[aux.stage],
                                        _ptr(gr), _ptr(gw), C.byref(g), k.ws.data_ptr(), k.ws_bytes, _stream()))
             pgrads = _param_grads(gp, k.params, need[5:])
@@ -356,7 +360,7 @@ def sample_tsdf(p, tsdf_volume, tsdf_bnds):
     if n == 0:
         return out
     scene = _scene_struct({}, tsdf_volume.detach(), tsdf_bnds, tsdf_bnds)
-    P = L.DfpPoints(pp.data_ptr(), 1 if pp.dtype == torch.float64 else 0, 0, n)
+    P = L.DfpPoints(pp.data_ptr(), 1 if pp.dtype == torch.float64 else 0, 0, n, 0, 0)
     with torch.cuda.device(pp.device):
         L.check(L.lib().dfp_tsdf_sample(C.byref(scene), C.byref(P), out.data_ptr(), _stream()))
     return out

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DFP_ABI_VERSION 1
+#define DFP_ABI_VERSION 2
 
 #define DFP_C_DIM 32            /* configs/df_prior.yaml:102 (model.c_dim) */
 #define DFP_HIDDEN 32           /* src/conv_onet/models/decoder.py:278 */
@@ -47,6 +47,10 @@ typedef enum DfpStatus {
 } DfpStatus;
 
 typedef enum DfpStage { DFP_STAGE_LOW = 0, DFP_STAGE_HIGH = 1, DFP_STAGE_COLOR = 2 } DfpStage;
+
+/* forward-call flags */
+#define DFP_FLAG_SAVE_ACT 1    /* a backward call will follow: the tensor-core forward keeps the decoders' layer
+                                  activations in the (larger) workspace so that the backward need not recompute them */
 
 /* One feature grid.  Logical shape is the reference's [1, C, D, H, W]
  * (src/DF_Prior.py:243-266) but memory is channels-last: element (z, y, x, c)
@@ -94,6 +98,8 @@ typedef struct DfpCfg {
     int32_t n_samples;         /* N_samples (32) */
     int32_t n_surface;         /* N_surface (16); ignored when gt_depth == NULL */
     int32_t n_importance;      /* must be 0 */
+    int32_t flags;             /* DFP_FLAG_* (pass the same value to the forward, the backward and the workspace size) */
+    int32_t reserved;
     float t_vals[DFP_MAX_RAY_SAMPLES];              /* linspace(0,1,N_samples) f32 */
     float one_minus_t[DFP_MAX_RAY_SAMPLES];         /* 1 - t_vals, f32 */
     double t_surf[DFP_MAX_RAY_SAMPLES];             /* linspace(0,1,N_surface) f32 -> f64 */
@@ -136,6 +142,8 @@ typedef struct DfpPoints {
     int32_t apply_bound_mask;  /* 1: eval_points semantics (occ=100 outside bound, Renderer.py:51-64);
                                   0: bare DF.forward (decoder.py:307-353) */
     int64_t n;
+    int32_t flags;             /* DFP_FLAG_* */
+    int32_t reserved;
 } DfpPoints;
 
 int dfp_abi_version(void);
@@ -157,7 +165,7 @@ int dfp_grid_to_cdhw(const float* src_dhwc, float* dst_cdhw, int32_t C, int32_t 
 /* ---- Renderer.render_batch_ray / render_img  (src/utils/Renderer.py:110-255, 258-327) ----
  * The workspace written by the forward call is what the backward call reads; keep it
  * alive (and unmodified) between the two. */
-size_t dfp_render_workspace_bytes(int64_t n_rays, int32_t samples_per_ray, int64_t chunk);
+size_t dfp_render_workspace_bytes(int64_t n_rays, int32_t samples_per_ray, int64_t chunk, int32_t stage, int32_t flags);
 int dfp_render_fwd(const DfpScene* scene, const float* params_packed, const DfpRays* rays, const DfpCfg* cfg,
                    const DfpRenderOut* out, void* workspace, size_t workspace_bytes, void* stream);
 int dfp_render_bwd(const DfpScene* scene, const float* params_packed, const DfpRays* rays, const DfpCfg* cfg,
@@ -167,7 +175,7 @@ int dfp_render_bwd(const DfpScene* scene, const float* params_packed, const DfpR
 /* ---- Renderer.eval_points / Mesher.eval_points / DF.forward --------------------------
  * (src/utils/Renderer.py:27-71, src/utils/Mesher.py:286-326, decoder.py:307-353)
  * raw [n,4] f32, w [n] f32. */
-size_t dfp_points_workspace_bytes(int64_t n_points);
+size_t dfp_points_workspace_bytes(int64_t n_points, int32_t stage, int32_t flags);
 int dfp_points_fwd(const DfpScene* scene, const float* params_packed, const DfpPoints* pts, int32_t stage,
                    float* raw, float* w, void* workspace, size_t workspace_bytes, void* stream);
 int dfp_points_bwd(const DfpScene* scene, const float* params_packed, const DfpPoints* pts, int32_t stage,
@@ -184,6 +192,8 @@ int dfp_tsdf_sample(const DfpScene* scene, const DfpPoints* pts, float* tsdf_out
 int64_t dfp_launch_count(void);
 /* 1 (default): MLP layers on the tcgen05 tensor cores (3xTF32); 0: fp32 SIMT kernels.  Env DFP_TENSOR_CORES=0 too. */
 int dfp_set_tensor_cores(int on);
+/* 2 (default): tensor-core backward; 1: tensor-core delta chain + SIMT weight gradients; 0: SIMT recompute backward */
+int dfp_set_tc_backward(int level);
 /* development probe of tcgen05 shared-memory descriptor semantics (see csrc/dfp_tc_selftest.cu) */
 int dfp_probe_tc(float* D, int32_t N, int32_t b_mn, int32_t lbo, int32_t sbo, int32_t k_hot, int32_t layout_type,
                  int32_t start_off, void* stream);

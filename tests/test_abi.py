@@ -38,8 +38,9 @@ def test_library_exports_every_declared_symbol(lib):
 def test_version_and_sizes(lib):
     assert lib.dfp_abi_version() == L.ABI_VERSION
     assert lib.dfp_packed_param_floats() >= L.N_PARAMS
-    assert lib.dfp_render_workspace_bytes(1000, 48, 0) > 1000 * 48 * 8
-    assert lib.dfp_points_workspace_bytes(500000) > 0
+    assert lib.dfp_render_workspace_bytes(1000, 48, 0, 2, 0) > 1000 * 48 * 8
+    assert lib.dfp_render_workspace_bytes(1000, 48, 0, 2, 1) > lib.dfp_render_workspace_bytes(1000, 48, 0, 2, 0)
+    assert lib.dfp_points_workspace_bytes(500000, 1, 0) > 0
     assert lib.dfp_launch_count() == 0
 
 
@@ -60,5 +61,5 @@ def test_invalid_arguments_return_error_codes_not_crashes(lib):
 def test_struct_sizes_match_header_layout():
     assert C.sizeof(L.DfpGrid) == 24 and C.sizeof(L.DfpTsdf) == 48
     assert C.sizeof(L.DfpScene) == 3 * 24 + 48 + 2 * 48
-    assert C.sizeof(L.DfpCfg) == 16 + 64 * 4 * 2 + 64 * 8 * 2
-    assert C.sizeof(L.DfpRays) == 48 and C.sizeof(L.DfpPoints) == 24
+    assert C.sizeof(L.DfpCfg) == 24 + 64 * 4 * 2 + 64 * 8 * 2
+    assert C.sizeof(L.DfpRays) == 48 and C.sizeof(L.DfpPoints) == 32
