@@ -133,16 +133,17 @@ static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with
     w.d_rgb = (float*)take(ns * 16);
     w.dp = (float*)take(ns * 12);
     const bool act = (flags & DFP_FLAG_SAVE_ACT) != 0;
+    const int64_t nsp = (ns + 127) / 128 * 128;          // tile-major arrays cover whole 128-sample tiles
     for (int d = 0; d < 3; ++d) {
         const bool used = act && (d == 0 || (d == 1 && stage >= DFP_STAGE_HIGH) || (d == 2 && stage == DFP_STAGE_COLOR));
-        w.act_h[d] = (float*)take(used ? ns * 160 * 4 : 0);
-        w.act_m[d] = (uint32_t*)take(used ? ns * 5 * 4 : 0);
-        w.act_c[d] = (float*)take(used ? ns * (d == 1 ? 64 : 32) * 4 : 0);
+        w.act_h[d] = (float*)take(used ? nsp * 160 * 4 : 0);
+        w.act_m[d] = (uint32_t*)take(used ? nsp * 5 * 4 : 0);
+        w.act_c[d] = (float*)take(used ? nsp * (d == 1 ? 64 : 32) * 4 : 0);
         if (!used) { w.act_h[d] = nullptr; w.act_m[d] = nullptr; w.act_c[d] = nullptr; }
     }
-    w.sc_e = (float*)take(act ? ns * 96 * 4 : 0);
-    w.sc_dh = (float*)take(act ? ns * 160 * 4 : 0);
-    w.sc_darg = (float*)take(act ? ns * 96 * 4 : 0);
+    w.sc_e = (float*)take(act ? nsp * 96 * 4 : 0);
+    w.sc_dh = (float*)take(act ? nsp * 160 * 4 : 0);
+    w.sc_darg = (float*)take(act ? nsp * 96 * 4 : 0);
     return off;
 }
 

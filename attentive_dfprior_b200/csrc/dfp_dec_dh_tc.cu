@@ -137,13 +137,13 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
 
 #pragma unroll 1
         for (int i = 4; i >= 1; --i) {
-            const uint32_t m = a.act_m[(int64_t)i * n + s];
+            const uint32_t m = a.act_m[tm_index(s, i, 5)];
             float dacc[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) dacc[j] = ((m >> j) & 1u) ? dh[j] : 0.f;
             if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a.sc_dh[(int64_t)(i * 32 + j) * n + s] = dh[j];
+                for (int j = 0; j < 32; ++j) a.sc_dh[tm_index(s, i * 32 + j, 160)] = dh[j];
             }
             tc::tmem_store_split32(tl + T::T_A, tl + T::T_A + 32, dh);            // for d_c += dh_i * Wc_i
             tc::tmem_store_split32(tl + T::T_A + 64, tl + T::T_A + 96, dacc);     // for dh_{i-1} = dacc_i * W_i
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
         {
             if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a.sc_dh[(int64_t)j * n + s] = dh[j];
+                for (int j = 0; j < 32; ++j) a.sc_dh[tm_index(s, j, 160)] = dh[j];
             }
             tc::tmem_store_split32(tl + T::T_A, tl + T::T_A + 32, dh);
             tc::wait_st();
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
                 tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + T::WC * 4, wlo + T::WC * 4, 32, 32, 4096u, true);
                 tc::mma_commit(bar);
             }
-            const uint32_t m0 = a.act_m[s];
+            const uint32_t m0 = a.act_m[tm_index(s, 0, 5)];
 #pragma unroll
             for (int j = 0; j < 32; ++j) dh[j] = ((m0 >> j) & 1u) ? dh[j] : 0.f;      // dacc_0
             tc::mbar_wait(bar, parity); parity ^= 1;
@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
                     gp2 = fmaf(sm[T::S_B + 2 * EMB_PAD + k], da, gp2);
                 }
                 if (valid && a.gparams) {
-                    a.sc_e[(int64_t)k * n + s] = sn;
-                    a.sc_darg[(int64_t)k * n + s] = da;
+                    a.sc_e[tm_index(s, k, 96)] = sn;
+                    a.sc_darg[tm_index(s, k, 96)] = da;
                 }
             }
         }

@@ -114,14 +114,14 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
             tc::tmem_store_split32(tl + T::T_C_HI, tl + T::T_C_LO, c);
             if (a.act_c && valid) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) a.act_c[(int64_t)k * a.n + s] = c[k];
+                for (int k = 0; k < 32; ++k) a.act_c[tm_index(s, k, CD)] = c[k];
             }
             if (DEC == 1) {
                 gather_features(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), c);
                 tc::tmem_store_split32(tl + T::T_C_HI + 32, tl + T::T_C_LO + 32, c);
                 if (a.act_c && valid) {
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) a.act_c[(int64_t)(32 + k) * a.n + s] = c[k];
+                    for (int k = 0; k < 32; ++k) a.act_c[tm_index(s, 32 + k, CD)] = c[k];
                 }
             }
         }
@@ -166,9 +166,9 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
                 h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + j]);
             }
             if (a.act_h && valid) {                                   // kept for the backward (DFP_FLAG_SAVE_ACT)
-                a.act_m[s] = m;
+                a.act_m[tm_index(s, 0, 5)] = m;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a.act_h[(int64_t)j * a.n + s] = h[j];
+                for (int j = 0; j < 32; ++j) a.act_h[tm_index(s, j, 160)] = h[j];
             }
         }
 #pragma unroll 1
@@ -207,9 +207,9 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
                 h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + i * 32 + j]);
             }
             if (a.act_h && valid) {
-                a.act_m[(int64_t)i * a.n + s] = m;
+                a.act_m[tm_index(s, i, 5)] = m;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a.act_h[(int64_t)(i * 32 + j) * a.n + s] = h[j];
+                for (int j = 0; j < 32; ++j) a.act_h[tm_index(s, i * 32 + j, 160)] = h[j];
             }
         }
         float out[NOUT];

@@ -74,6 +74,11 @@ __device__ __forceinline__ void load_point(const PointSrc& ps, int64_t s, typena
 
 struct Bounds { double b[3][2]; };
 
+// Saved activations and backward scratch are tile-major: element (feature f, sample s) of an F-feature array lives at
+// ((s/128)*F + f)*128 + s%128, so the 32-feature operand block of one 128-sample tile is 16 KB contiguous in HBM
+// (feature-major [f][n] put consecutive features ~12 MB apart and thrashed DRAM pages).
+__host__ __device__ __forceinline__ int64_t tm_index(int64_t s, int f, int F) { return ((s >> 7) * F + f) * 128 + (s & 127); }
+
 struct Ws {                        // per-sample workspace arrays (NS samples)
     double* z;                     // [NS] sorted sample depths (render only)
     float* depthmax;               // [nchunks][2]: max(gt_depth*1.2), max(gt_depth)
@@ -86,7 +91,7 @@ struct Ws {                        // per-sample workspace arrays (NS samples)
     float* d_low; float* d_high; float* d_fused;    // [NS]
     float* d_rgb;                  // [NS][4]
     float* dp;                     // [NS][3] gradient w.r.t. the sample point
-    // DFP_FLAG_SAVE_ACT: activations of the three decoders kept by the tensor-core forward, feature-major [f][NS]
+    // DFP_FLAG_SAVE_ACT: activations of the three decoders kept by the tensor-core forward, tile-major (tm_index)
     float* act_h[3];               // [160][NS]: inputs of pts_linears.1..4 and of output_linear
     uint32_t* act_m[3];            // [5][NS]:   ReLU masks of pts_linears.0..4
     float* act_c[3];               // [CD][NS]:  gathered grid features

@@ -67,10 +67,13 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr, uint32_t lb
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-// instruction descriptor: kind::tf32, f32 accumulate, M = 128; a_mn / b_mn select the MN-major (transposed) view
-__host__ __device__ constexpr uint32_t idesc_tf32_m128(int n, bool a_mn = false, bool b_mn = false) {
+// instruction descriptor: kind::tf32, f32 accumulate, M = 128 (or 64); a_mn / b_mn select the MN-major (transposed) view
+__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n, bool a_mn = false, bool b_mn = false) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc_tf32_m128(int n, bool a_mn = false, bool b_mn = false) {
+    return idesc_tf32(128, n, a_mn, b_mn);
 }
 // ---- MN-major (transposed) TF32 operands ----------------------------------------------------------------
 // Probed on B200 (dfp_probe_tc): for kind::tf32 the transposed view only exists with layout type 1
@@ -212,6 +215,22 @@ __device__ __forceinline__ void mma_outer(uint32_t d_tmem, uint32_t h_hi, uint32
         const uint64_t bh = smem_desc_mnmajor(d_hi + ks * 1024u, d_block_bytes);
         mma_tf32_ss(d_tmem, al, bh, idesc, acc);
         mma_tf32_ss(d_tmem, ah, bh, idesc, 1u);
+        acc = 1u;
+    }
+}
+
+// M = 64 variant of mma_outer: D[64 x N] (+)= [H | X]^T * Dl, where the A operand's second 32-feature block X lives
+// `h*_lbo_bytes` after the first (any shared block: the callers point the hi part at a constant-one block, giving the
+// column sums of Dl in accumulator row 32, and the lo part at a zero block).  Accumulator row m sits in TMEM lane
+// (m/16)*32 + m%16 (probed: dfp_probe_tc, M = 64).  Half the shared-memory operand traffic of the M = 128 form.
+__device__ __forceinline__ void mma_outer64(uint32_t d_tmem, uint32_t h_hi, uint32_t h_hi_lbo_bytes, uint32_t h_lo,
+                                            uint32_t h_lo_lbo_bytes, uint32_t d_hi, int N, bool accumulate) {
+    const uint32_t idesc = idesc_tf32(64, N, true, true);
+    uint32_t acc = accumulate ? 1u : 0u;
+    for (int ks = 0; ks < 16; ++ks) {
+        const uint64_t bh = smem_desc_mnmajor(d_hi + ks * 1024u, 16384u);
+        mma_tf32_ss(d_tmem, smem_desc_mnmajor(h_lo + ks * 1024u, h_lo_lbo_bytes), bh, idesc, acc);
+        mma_tf32_ss(d_tmem, smem_desc_mnmajor(h_hi + ks * 1024u, h_hi_lbo_bytes), bh, idesc, 1u);
         acc = 1u;
     }
 }

@@ -221,7 +221,67 @@ __global__ void __launch_bounds__(128) k_tc_probe(float* __restrict__ D, int N, 
     if (warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
+// Probe of the accumulator layout for M = 64: SS-mode MMA with A[m][0] = m + 1 (K-major canonical), B[n][0] = 1, so that
+// D[m][n] = m + 1; all 128 lanes x 16 columns are dumped to see which TMEM lane holds row m.
+__global__ void __launch_bounds__(128) k_tc_probe_m64(float* __restrict__ D, int M) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    float* A = sm;            // [M][8] canonical K-major: chunk ck at ck*(M*4 floats) + m*4
+    float* B = sm + 2048;     // [16][8]
+    for (int i = tid; i < 4096; i += 128) sm[i] = 0.f;
+    __syncthreads();
+    if (tid < M) A[tc::b_index(tid, 0, M)] = (float)(tid + 1);
+    if (tid < 16) B[tc::b_index(tid, 0, 16)] = 1.0f;
+    if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 32); tc::tmem_relinquish(); }
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    {   // clear the accumulator columns first so untouched lanes read back as 0
+        uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        tc::tmem_st8(lane_base, z);
+        tc::tmem_st8(lane_base + 8, z);
+        tc::wait_st();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | (((uint32_t)M >> 4) << 24);
+        const uint64_t da = tc::smem_desc_kmajor(tc::smem_u32(A), (uint32_t)M * 16u, 128u);
+        const uint64_t db = tc::smem_desc_kmajor(tc::smem_u32(B), 16u * 16u, 128u);
+        tc::mma_tf32_ss(tbase, da, db, idesc, 0u);
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    for (int c0 = 0; c0 < 16; c0 += 8) {
+        uint32_t v[8];
+        tc::tmem_ld8(lane_base + c0, v);
+        tc::wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) D[tid * 16 + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 32);
+}
+
 int launch_tc_probe(float* D, int N, int b_mn, int lbo, int sbo, int k_hot, int layout_type, int start_off, cudaStream_t st) {
+    if (layout_type >= 100) {          // M = 64 / 128 accumulator-layout probe: N is reused as M
+        const size_t smem2 = 4096 * sizeof(float) + 1024;
+        int rc2 = set_smem(k_tc_probe_m64, smem2);
+        if (rc2) return rc2;
+        DFP_TIMED("k_tc_probe_m64", st, k_tc_probe_m64<<<1, 128, smem2, st>>>(D, N));
+        DFP_LAUNCH_CHECK("k_tc_probe_m64");
+        return DFP_OK;
+    }
     const size_t smem = 16384 * sizeof(float) + 1024;
     int rc = set_smem(k_tc_probe, smem);
     if (rc) return rc;
