@@ -25,7 +25,8 @@ constexpr int ONES = NSTAGE * STAGE;          // constant-one A block (column 0 
 constexpr int ZERO = ONES + BLK;              // zero block: second MN block of every lo operand
 constexpr int FLOATS = ZERO + BLK;
 constexpr int MAX_TILES = 1024;               // active tiles of one CTA
-constexpr int PRODUCERS = 256;
+constexpr int PRODUCERS = 256;               // threads staging one item (128 A rows + 128 B rows)
+constexpr int GROUPS = 2;                     // producer groups working on alternating items
 }  // namespace dw
 
 struct DwProduct {
@@ -65,7 +66,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <int DEC>
-__global__ void __launch_bounds__(dw::PRODUCERS + 32, 1) k_decoder_dw_tc(const DecArgs a) {
+__global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_dw_tc(const DecArgs a) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
     constexpr int NOUT = (DEC == 2) ? 4 : 1;
     constexpr int NPROD = dw_num_products<CD>();
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(dw::PRODUCERS + 32, 1) k_decoder_dw_tc(const D
     const uint32_t sm_base = tc::smem_u32(sm);
 
     if (n_active > 0) {
-        if (warp == dw::PRODUCERS / 32) {
+        if (warp == dw::GROUPS * dw::PRODUCERS / 32) {
             // ===================== MMA issuer (one lane) =====================
             if (lane == 0) {
                 uint32_t q = 0;
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(dw::PRODUCERS + 32, 1) k_decoder_dw_tc(const D
             }
         } else {
             // ===================== producers (256 threads) + flush (warp 0) =====================
-            const bool roleA = tid < 128;
+            const int pgrp = tid / dw::PRODUCERS;                  // this thread's producer group
+            const bool roleA = (tid % dw::PRODUCERS) < 128;
             const int row = tid & 127;
             float* g = a.gparams + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR));
             // this thread's 32 operand values of item (product p, active tile t)
@@ -195,19 +197,22 @@ __global__ void __launch_bounds__(dw::PRODUCERS + 32, 1) k_decoder_dw_tc(const D
                     }
                 }
             };
-            uint32_t q = 0;
+            // items are numbered q = p * n_active + t; this group stages the items with q % GROUPS == pgrp
+            const uint32_t total = (uint32_t)NPROD * (uint32_t)n_active;
             float vnext[32];
-            load_item(0, 0, vnext);
+            uint32_t q = (uint32_t)pgrp;
+            if (q < total) load_item((int)(q / n_active), (int)(q % n_active), vnext);
             for (int p = 0; p < NPROD; ++p) {
                 const DwProduct pr = dw_product<CD>(p);
-                for (int t = 0; t < n_active; ++t, ++q) {
+                const uint32_t q_end = (uint32_t)(p + 1) * (uint32_t)n_active;
+                for (; q < q_end; q += dw::GROUPS) {
                     const int st = q % dw::NSTAGE;
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = vnext[j];
-                    // software pipeline: the next item's loads are in flight while this one is split and stored
-                    if (t + 1 < n_active) load_item(p, t + 1, vnext);
-                    else if (p + 1 < NPROD) load_item(p + 1, 0, vnext);
+                    // software pipeline: this group's next item is in flight while the current one is split and stored
+                    const uint32_t qn = q + dw::GROUPS;
+                    if (qn < total) load_item((int)(qn / n_active), (int)(qn % n_active), vnext);
                     if (q >= dw::NSTAGE) tc::mbar_wait(&empty_bar[st], ((q / dw::NSTAGE) - 1) & 1);      // MMAs of the previous use are done
                     float* stage = sm + st * dw::STAGE;
                     if (roleA) {
@@ -281,7 +286,7 @@ int launch_decoder_dw_tc(const DecArgs& a, cudaStream_t st) {
     int blocks = grid_for(tiles, 1, num_sms());
     const int64_t min_blocks = (tiles + dw::MAX_TILES - 1) / dw::MAX_TILES;      // a CTA lists at most MAX_TILES tiles
     if (blocks < min_blocks) blocks = (int)min_blocks;
-    DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC><<<blocks, dw::PRODUCERS + 32, smem, st>>>(a));
+    DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC><<<blocks, dw::GROUPS * dw::PRODUCERS + 32, smem, st>>>(a));
     DFP_LAUNCH_CHECK("k_decoder_dw_tc");
     return DFP_OK;
 }
