@@ -224,23 +224,40 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
             float de[32];
             tc::tmem_ld32(tl + T::T_DX + ch * 32, de);
             tc::wait_ld();
+            float sn[32], da[32];
+            if (fast) {                                   // branch hoisted out of the unrolled loop (code size / I-cache)
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) {
+                    const int k = ch * 32 + kk;
+                    float s1 = (k == EMB) ? 1.f : 0.f, c1 = 0.f;    // column 93 of the sin array: constant 1 (bias of block 0 in kernel 2)
+                    if (k < EMB) sincos_cw(embed_arg(sm + T::S_B, pf, k), s1, c1);
+                    sn[kk] = s1;
+                    da[kk] = de[kk] * c1;
+                }
+            } else {
+#pragma unroll 1
+                for (int kk = 0; kk < 32; ++kk) {
+                    const int k = ch * 32 + kk;
+                    float s1 = (k == EMB) ? 1.f : 0.f, c1 = 0.f;
+                    if (k < EMB) sincosf(embed_arg(sm + T::S_B, pf, k), &s1, &c1);
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) if (u == kk) { sn[u] = s1; da[u] = de[u] * c1; }
+                }
+            }
 #pragma unroll
             for (int kk = 0; kk < 32; ++kk) {
                 const int k = ch * 32 + kk;
-                float sn = (k == EMB) ? 1.f : 0.f, da = 0.f;     // column 93 of the sin array is the constant 1 kernel 2 uses for the bias of block 0
                 if (k < EMB) {
-                    const float arg = embed_arg(sm + T::S_B, pf, k);
-                    float cs;
-                    if (fast) sincos_cw(arg, sn, cs);
-                    else sincosf(arg, &sn, &cs);
-                    da = de[kk] * cs;
-                    gp0 = fmaf(sm[T::S_B + k], da, gp0);
-                    gp1 = fmaf(sm[T::S_B + EMB_PAD + k], da, gp1);
-                    gp2 = fmaf(sm[T::S_B + 2 * EMB_PAD + k], da, gp2);
+                    gp0 = fmaf(sm[T::S_B + k], da[kk], gp0);
+                    gp1 = fmaf(sm[T::S_B + EMB_PAD + k], da[kk], gp1);
+                    gp2 = fmaf(sm[T::S_B + 2 * EMB_PAD + k], da[kk], gp2);
                 }
-                if (valid && a.gparams) {
-                    a.sc_e[tm_index(s, k, 96)] = sn;
-                    a.sc_darg[tm_index(s, k, 96)] = da;
+            }
+            if (valid && a.gparams) {
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) {
+                    a.sc_e[tm_index(s, ch * 32 + kk, 96)] = sn[kk];
+                    a.sc_darg[tm_index(s, ch * 32 + kk, 96)] = da[kk];
                 }
             }
         }

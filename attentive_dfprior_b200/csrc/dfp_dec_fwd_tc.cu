@@ -129,11 +129,20 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
 #pragma unroll 1
         for (int ch = 0; ch < 3; ++ch) {
             float e[32];
+            if (fast) {                                   // branch hoisted: one copy of each path keeps the kernel inside the I-cache
 #pragma unroll
-            for (int kk = 0; kk < 32; ++kk) {
-                const int k = ch * 32 + kk;
-                const float arg = embed_arg(sm + T::S_B, pf, k);
-                e[kk] = (k < EMB) ? (fast ? sin_cw(arg) : sinf(arg)) : 0.f;
+                for (int kk = 0; kk < 32; ++kk) {
+                    const int k = ch * 32 + kk;
+                    e[kk] = (k < EMB) ? sin_cw(embed_arg(sm + T::S_B, pf, k)) : 0.f;
+                }
+            } else {
+#pragma unroll 1
+                for (int kk = 0; kk < 32; ++kk) {
+                    const int k = ch * 32 + kk;
+                    const float v = (k < EMB) ? sinf(embed_arg(sm + T::S_B, pf, k)) : 0.f;
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) if (u == kk) e[u] = v;
+                }
             }
             if (ch > 0) { tc::mbar_wait(bar, parity); parity ^= 1; tc::fence_after_sync(); }   // previous chunk consumed A_X
             tc::tmem_store_split32(tl + T::T_X_HI, tl + T::T_X_LO, e);
