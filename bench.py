@@ -42,6 +42,12 @@ KERNEL_BYTES_PER_SAMPLE = {
     "k_decoder_fwd": {"low": 1024, "high": 2048, "color": 1024},
     "k_decoder_bwd": {"low": 2048, "high": 3072, "color": 2048},
     "k_prep": 32 + 24, "k_attn_fwd": 20, "k_attn_bwd": 28 + 32,
+    # tensor-core path: forward gathers as above; K1 (delta chain) scatters the feature gradient (1024 B) and re-gathers
+    # nothing; K2 (weight gradients) touches no grid data: its algorithmic bytes are the 32 B/sample of deltas in and
+    # the parameter gradient out (negligible) -- its real traffic is the saved-activation stream
+    "k_decoder_fwd_tc": {"low": 1024, "high": 2048, "color": 1024},
+    "k_decoder_dh_tc": {"low": 1024, "high": 1024, "color": 1024},
+    "k_decoder_dw_tc": {"low": 32, "high": 32, "color": 32},
 }
 
 
@@ -275,29 +281,53 @@ def run_ours(args):
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
     e2e = rays_total / (ms_e2e / 1e3)
 
+    # live per-kernel durations (CUDA events on the launching stream) over a few more steps; every rank runs them
+    # because the steps contain collectives, rank 0 reports
+    prof_steps = 3
+    kt = L.kernel_times(lambda: [step_dev() for _ in range(prof_steps)])
+    # the reference's own batch size (1000 mapping pixels per step over all ranks) as a latency figure
+    small = None
+    if not args.no_small:
+        n_small = max(1, 1000 // world)
+        ro, rd, g, gc = synth.make_rays(scene, n_small, seed=7 + rank, device=dev)
+        small_step = lambda: step(ro, rd, g, gc)
+        for _ in range(5):
+            small_step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            small_step()
+        b.record()
+        torch.cuda.synchronize()
+        small = {"rays_per_step": n_small * world, "ms_per_step": a.elapsed_time(b) / 20,
+                 "rays_per_s": n_small * world * 20 / (a.elapsed_time(b) / 1e3)}
+
     out = None
     if rank == 0:
         peak, peak_src = load_peaks()
-        # live per-kernel durations (CUDA events on the launching stream) over a few more steps
-        prof_steps = 3
-        kt = L.kernel_times(lambda: [step_dev() for _ in range(prof_steps)])
         ns = n * S
-        # decoder kernels are launched in a fixed order: fwd high, colour, low / bwd high, colour, low
         total_kernel_ms = sum(v[1] for v in kt.values())
-        top = max(kt.items(), key=lambda kv: kv[1][1])
-        kb = KERNEL_BYTES_PER_SAMPLE.get(top[0])
-        per_launch_ms = top[1][1] / top[1][0]
-        if isinstance(kb, dict):
-            bytes_per_launch = sum(kb[s] for s in ("low", "high", "color")) / 3.0 * ns
-        elif kb is not None:
-            bytes_per_launch = kb * ns
-        else:
-            bytes_per_launch = 0.0
-        achieved = bytes_per_launch / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
+        # The roofline object describes the dominant OPERATION of the step.  The decoder backward is one logical op that
+        # this library runs as two kernels per decoder on the tensor-core path (k_decoder_dh_tc: delta chain + grid
+        # scatter, k_decoder_dw_tc: weight gradients) or as one (k_decoder_bwd) on the SIMT path; its algorithmic bytes
+        # are SURVEY 8d's backward figure (re-gather + gradient scatter).
+        ops = {
+            "decoder_bwd": (["k_decoder_bwd", "k_decoder_dh_tc", "k_decoder_dw_tc"], {"low": 2048, "high": 3072, "color": 2048}),
+            "decoder_fwd": (["k_decoder_fwd", "k_decoder_fwd_tc"], {"low": 1024, "high": 2048, "color": 1024}),
+            "attention": (["k_attn_fwd", "k_attn_bwd"], {"low": 0, "high": 0, "color": 48 + 60}),
+        }
+        op_ms = {o: sum(kt[k][1] for k in ks if k in kt) / prof_steps for o, (ks, _) in ops.items()}
+        top_op = max(op_ms, key=op_ms.get)
+        kernels, kb = ops[top_op]
+        bytes_per_step = sum(kb.values()) * ns                       # the three decoders of stage `color`
+        achieved = bytes_per_step / (op_ms[top_op] / 1e3) / 1e9 if op_ms[top_op] > 0 else 0.0
         step_gbs = value / world * BYTES_PER_RAY[STAGE] / 1e9
-        roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "kernel_share_of_step": top[1][1] / total_kernel_ms if total_kernel_ms else None,
+        roofline = {"bound": "hbm", "kernel": top_op + " (" + " + ".join(k for k in kernels if k in kt) + ")",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "kernel_share_of_step": op_ms[top_op] * prof_steps / total_kernel_ms if total_kernel_ms else None,
+                    "algorithmic_bytes_per_step": bytes_per_step, "op_ms_per_step": op_ms[top_op],
                     "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak,
                                    "bytes_per_ray": BYTES_PER_RAY[STAGE]},
                     "kernels_ms_per_step": {k: round(v[1] / prof_steps, 4) for k, v in sorted(kt.items())}}
@@ -310,32 +340,18 @@ def run_ours(args):
                        ("channels_last_3d" if not args.channels_first else "channels_first (transposed per call)"),
                        "tsdf": list(scene.tsdf_volume.shape[2:]), "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": f"ray-sharded dp{world}" + (" + NCCL all-reduce of grid/decoder grads" if world > 1 else ""),
+                       "mlp": "tcgen05 3xTF32 tensor-core path" if os.environ.get("DFP_TENSOR_CORES", "1") != "0" else "fp32 SIMT",
                        "loss": "Mapper depth L1 + 0.2 colour L1"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         }
+        if small is not None:
+            out["mapping_1000_rays"] = small
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         del flush
         out["cpu_baseline"] = cpu_baseline(lambda: synth.make_scene("room0", seed=0, high_std=1e-2))
     if rank == 0:
-        # the reference's own batch size (1000 mapping pixels) as a latency figure
-        if not args.no_small:
-            n_small = 1000
-            ro, rd, g, gc = synth.make_rays(scene, n_small, seed=7, device=dev)
-            small = lambda: step(ro, rd, g, gc)
-            for _ in range(5):
-                small()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(20):
-                small()
-            b.record()
-            torch.cuda.synchronize()
-            if world == 1:
-                out["mapping_1000_rays"] = {"ms_per_step": a.elapsed_time(b) / 20,
-                                            "rays_per_s": n_small * 20 / (a.elapsed_time(b) / 1e3)}
         print(json.dumps(out))
     if group is not None:
         torch.distributed.barrier()

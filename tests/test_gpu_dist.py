@@ -1,0 +1,65 @@
+"""GPU, world_size 2 (NCCL): the ray-sharded mapping step gives the same outputs and the same (all-reduced)
+gradients as the single-GPU step on the whole batch.  Skipped when fewer than 2 GPUs are visible."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import attentive_dfprior_b200 as A
+        from attentive_dfprior_b200 import dist as D
+        from attentive_dfprior_b200 import synth
+        from attentive_dfprior_b200.config import default_cfg, slam_namespace
+        torch.manual_seed(0)
+        scene = synth.make_scene("small", seed=3, device=dev, high_std=1e-2, channels_last=True)
+        model = A.DF().to(dev)
+        with torch.no_grad():
+            for dec in (model.low_decoder, model.high_decoder):
+                dec.output_linear.weight.mul_(0.05)
+        renderer = A.Renderer(default_cfg(), None, slam_namespace(scene.bound, scene.tsdf_bnds))
+        n = 512
+        rays_o, rays_d, gt, gc = synth.make_rays(scene, n, seed=5, device=dev)      # identical on every rank
+
+        def run(lo, hi, group):
+            grids = {k: v.clone().requires_grad_(True) for k, v in scene.grids.items()}
+            for p in model.parameters():
+                p.grad = None
+            d, u, c, w = D.render_batch_ray_sharded(renderer, grids, model, rays_d[lo:hi], rays_o[lo:hi], scene.tsdf_volume,
+                                                    scene.tsdf_bnds, "color", gt[lo:hi], group=group)
+            g = gt[lo:hi]
+            m = g > 0
+            (torch.abs(g[m] - d[m]).sum() + 0.2 * torch.abs(gc[lo:hi] - c).sum()).backward()
+            return d.detach(), {k: v.grad.clone() for k, v in grids.items()}, [p.grad.clone() for p in model.parameters()]
+
+        lo, hi = D.shard_range(n, rank, world)
+        d_sh, gg_sh, gp_sh = run(lo, hi, dist.group.WORLD)
+        d_full, gg_full, gp_full = run(0, n, None)
+        ok = bool(torch.equal(d_sh, d_full[lo:hi]))            # per-ray outputs do not depend on the sharding (global depth max)
+        def rel(a, b):
+            return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+        worst = max([rel(gg_sh[k], gg_full[k]) for k in gg_full] + [rel(a, b) for a, b in zip(gp_sh, gp_full) if float(b.abs().max()) > 0])
+        ret[rank] = (ok, worst)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_step_matches_single_gpu():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, 29611, ret), nprocs=2, join=True)
+    for r in range(2):
+        ok, worst = ret[r]
+        assert ok, "sharded outputs differ from the single-GPU outputs"
+        assert worst <= 1e-4, worst
