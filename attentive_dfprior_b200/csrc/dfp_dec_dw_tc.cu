@@ -3,11 +3,15 @@
 //
 // The decoder's parameter tensors are cut into "products" of one 32-feature A block times one 32-column delta block
 // (pts_linears.1..4, output_linear, fc_c.i per 32 features, the three 32-wide chunks of the embedding against the
-// deltas of blocks 0 and 3, embedder._B).  A CTA walks  product (outer) x its 128-sample tiles (inner):  eight
+// deltas of blocks 0 and 3, embedder._B).  The kernel runs in two passes (pass 0: pts_linears.1..4, output_linear,
+// fc_c; pass 1: the embedding-side products) so that the accumulators of ALL products of a pass fit the 512 TMEM
+// columns and stay resident for the CTA's lifetime; a CTA then walks  tile (outer) x product (inner): every operand
+// block comes from HBM once per tile and its re-stagings for other products hit L2.  Sixteen
 // producer warps load the saved activations / deltas (feature-major arrays written by the forward and by kernel 1),
 // split them to TF32 hi/lo and store them as row-per-sample swizzled tiles (the MN-major operand layout of
 // dfp_tc.cuh) into a 3-stage shared-memory ring; a ninth warp issues the SS-mode tcgen05.mma chains (K = 128 samples
-// per stage) and hands the stage back through tcgen05.commit.  The MMAs are M = 64: rows 0..31 are the product, row 32 (from a
+// per stage) and hands the stage back through tcgen05.commit.  (An earlier product-outer variant re-read every operand
+// from HBM for each product: 13.9 GB per decoder at 65 536 rays, ncu profiles/r01.)  The MMAs are M = 64: rows 0..31 are the product, row 32 (from a
 // constant-one feature block addressed as the A operand's second MN block) the bias sums.  The accumulator (32 TMEM
 // columns) lives in one of two TMEM sets, so flushing product p (one atomic pass per CTA
 // and product) overlaps the MMAs of product p+1.  No per-sample or per-tile atomics.
@@ -65,15 +69,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
-template <int DEC>
+template <int DEC, int PASS>
 __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_dw_tc(const DecArgs a) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
     constexpr int NOUT = (DEC == 2) ? 4 : 1;
-    constexpr int NPROD = dw_num_products<CD>();
+    constexpr int NPROD_ALL = dw_num_products<CD>();
+    constexpr int P0 = (PASS == 0) ? 0 : 5 + 5 * (CD / 32);          // first product of this pass
+    constexpr int NP = (PASS == 0) ? 5 + 5 * (CD / 32) : NPROD_ALL - P0;   // 10 / 15 products (pass 0), 9 (pass 1): <= 16 x 32 TMEM columns
     using L = DecOff<CD>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
-    __shared__ __align__(8) uint64_t full_bar[dw::NSTAGE], empty_bar[dw::NSTAGE], done_bar[2], free_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[dw::NSTAGE], empty_bar[dw::NSTAGE], done_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ int tile_list[dw::MAX_TILES];
     __shared__ int n_active_s;
@@ -101,10 +107,10 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
         }
         if (lane == 0) n_active_s = cnt;
     }
-    if (warp == 3) { tc::tmem_alloc(&tmem_base_s, 64); tc::tmem_relinquish(); }
+    if (warp == 3) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
     if (tid == 0) {
         for (int i = 0; i < dw::NSTAGE; ++i) { tc::mbar_init(&full_bar[i], dw::PRODUCERS); tc::mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&done_bar[i], 1); tc::mbar_init(&free_bar[i], 96); }
+        tc::mbar_init(&done_bar, 1);
         tc::fence_mbar_init();
     }
     tc::fence_proxy_async();
@@ -119,23 +125,19 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
         if (warp == dw::GROUPS * dw::PRODUCERS / 32) {
             // ===================== MMA issuer (one lane) =====================
             if (lane == 0) {
-                uint32_t q = 0;
-                for (int p = 0; p < NPROD; ++p) {
-                    const int set = p & 1;
-                    if (p >= 2) { tc::mbar_wait(&free_bar[set], ((p >> 1) - 1) & 1); tc::fence_after_sync(); }   // flushed by warp 0
-                    const uint32_t dW = tb + set * 32;
-                    for (int t = 0; t < n_active; ++t, ++q) {
-                        const int st = q % dw::NSTAGE;
-                        tc::mbar_wait(&full_bar[st], (q / dw::NSTAGE) & 1);
-                        tc::fence_after_sync();
-                        const uint32_t sa = sm_base + st * dw::STAGE * 4;
-                        const uint32_t a_hi = sa, a_lo = sa + dw::BLK_BYTES, b = sa + 2 * dw::BLK_BYTES;
-                        // M = 64: rows 0..31 = the product, row 32 = column sums of the delta tile (constant-one block)
-                        tc::mma_outer64(dW, a_hi, sm_base + dw::ONES * 4 - a_hi, a_lo, sm_base + dw::ZERO * 4 - a_lo, b, 32, t > 0);
-                        tc::mma_commit(&empty_bar[st]);                 // stage reusable once these MMAs have read it
-                    }
-                    tc::mma_commit(&done_bar[set]);                     // product complete
+                const uint32_t total = (uint32_t)NP * (uint32_t)n_active;
+                for (uint32_t q = 0; q < total; ++q) {                   // item q = (tile q / NP, product P0 + q % NP)
+                    const int st = q % dw::NSTAGE;
+                    tc::mbar_wait(&full_bar[st], (q / dw::NSTAGE) & 1);
+                    tc::fence_after_sync();
+                    const uint32_t sa = sm_base + st * dw::STAGE * 4;
+                    const uint32_t a_hi = sa, a_lo = sa + dw::BLK_BYTES, b = sa + 2 * dw::BLK_BYTES;
+                    // M = 64: rows 0..31 = the product, row 32 = column sums of the delta tile (constant-one block)
+                    tc::mma_outer64(tb + (q % NP) * 32, a_hi, sm_base + dw::ONES * 4 - a_hi, a_lo, sm_base + dw::ZERO * 4 - a_lo, b, 32,
+                                    q >= (uint32_t)NP);
+                    tc::mma_commit(&empty_bar[st]);                      // stage reusable once these MMAs have read it
                 }
+                tc::mma_commit(&done_bar);                               // everything accumulated
             }
         } else {
             // ===================== producers (256 threads) + flush (warp 0) =====================
@@ -197,48 +199,45 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
                     }
                 }
             };
-            // items are numbered q = p * n_active + t; this group stages the items with q % GROUPS == pgrp
-            const uint32_t total = (uint32_t)NPROD * (uint32_t)n_active;
+            // items are numbered q = t * NP + (p - P0) (tile-outer); this group stages the items with q % GROUPS == pgrp
+            const uint32_t total = (uint32_t)NP * (uint32_t)n_active;
             float vnext[32];
             uint32_t q = (uint32_t)pgrp;
-            if (q < total) load_item((int)(q / n_active), (int)(q % n_active), vnext);
-            for (int p = 0; p < NPROD; ++p) {
-                const DwProduct pr = dw_product<CD>(p);
-                const uint32_t q_end = (uint32_t)(p + 1) * (uint32_t)n_active;
-                for (; q < q_end; q += dw::GROUPS) {
-                    const int st = q % dw::NSTAGE;
-                    float v[32];
+            if (q < total) load_item(P0 + (int)(q % NP), (int)(q / NP), vnext);
+            for (; q < total; q += dw::GROUPS) {
+                const int st = q % dw::NSTAGE;
+                float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = vnext[j];
-                    // software pipeline: this group's next item is in flight while the current one is split and stored
-                    const uint32_t qn = q + dw::GROUPS;
-                    if (qn < total) load_item((int)(qn / n_active), (int)(qn % n_active), vnext);
-                    if (q >= dw::NSTAGE) tc::mbar_wait(&empty_bar[st], ((q / dw::NSTAGE) - 1) & 1);      // MMAs of the previous use are done
-                    float* stage = sm + st * dw::STAGE;
-                    if (roleA) {
-                        float hi[32], lo[32];
+                for (int j = 0; j < 32; ++j) v[j] = vnext[j];
+                // software pipeline: this group's next item is in flight while the current one is split and stored
+                const uint32_t qn = q + dw::GROUPS;
+                if (qn < total) load_item(P0 + (int)(qn % NP), (int)(qn / NP), vnext);
+                if (q >= dw::NSTAGE) tc::mbar_wait(&empty_bar[st], ((q / dw::NSTAGE) - 1) & 1);      // MMAs of the previous use are done
+                float* stage = sm + st * dw::STAGE;
+                if (roleA) {
+                    float hi[32], lo[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) { hi[j] = tc::tf32_rna(v[j]); lo[j] = tc::tf32_rna(v[j] - hi[j]); }
-                        tile_store_row(stage, row, hi);
-                        tile_store_row(stage + dw::BLK, row, lo);
-                    } else {
+                    for (int j = 0; j < 32; ++j) { hi[j] = tc::tf32_rna(v[j]); lo[j] = tc::tf32_rna(v[j] - hi[j]); }
+                    tile_store_row(stage, row, hi);
+                    tile_store_row(stage + dw::BLK, row, lo);
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = tc::tf32_rna(v[j]);
-                        tile_store_row(stage + 2 * dw::BLK, row, v);
-                    }
-                    tc::fence_proxy_async();
-                    mbar_arrive(&full_bar[st]);
+                    for (int j = 0; j < 32; ++j) v[j] = tc::tf32_rna(v[j]);
+                    tile_store_row(stage + 2 * dw::BLK, row, v);
                 }
-                // ---- flush product p (warps 0..2): accumulator row m is TMEM lane (m/16)*32 + m%16; row 32 holds the bias sums
-                if (warp < 3) {
-                    const int set = p & 1;
-                    tc::mbar_wait(&done_bar[set], (p >> 1) & 1);
-                    tc::fence_after_sync();
+                tc::fence_proxy_async();
+                mbar_arrive(&full_bar[st]);
+            }
+            // ---- flush (warps 0..2), once per CTA: accumulator row m is TMEM lane (m/16)*32 + m%16; row 32 holds the bias sums
+            if (warp < 3) {
+                tc::mbar_wait(&done_bar, 0);
+                tc::fence_after_sync();
+#pragma unroll 1
+                for (int pp = 0; pp < NP; ++pp) {
+                    const DwProduct pr = dw_product<CD>(P0 + pp);
                     float d[32];
-                    tc::tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + set * 32, d);
+                    tc::tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + pp * 32, d);
                     tc::wait_ld();
-                    tc::fence_before_sync();
-                    mbar_arrive(&free_bar[set]);
                     if (lane < 16) {
                         const int k = warp * 16 + lane;                 // accumulator row
                         if (k == 32) {                                   // bias sums
@@ -274,19 +273,22 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 3) tc::tmem_dealloc(tb, 64);
+    if (warp == 3) tc::tmem_dealloc(tb, 512);
 }
 
 template <int DEC>
 int launch_decoder_dw_tc(const DecArgs& a, cudaStream_t st) {
     const size_t smem = dw::FLOATS * sizeof(float) + 1024;
-    int rc = set_smem(k_decoder_dw_tc<DEC>, smem);
+    int rc = set_smem(k_decoder_dw_tc<DEC, 0>, smem);
     if (rc) return rc;
+    if ((rc = set_smem(k_decoder_dw_tc<DEC, 1>, smem))) return rc;
     const int64_t tiles = (a.n + 127) / 128;
     int blocks = grid_for(tiles, 1, num_sms());
     const int64_t min_blocks = (tiles + dw::MAX_TILES - 1) / dw::MAX_TILES;      // a CTA lists at most MAX_TILES tiles
     if (blocks < min_blocks) blocks = (int)min_blocks;
-    DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC><<<blocks, dw::GROUPS * dw::PRODUCERS + 32, smem, st>>>(a));
+    DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC, 0><<<blocks, dw::GROUPS * dw::PRODUCERS + 32, smem, st>>>(a));
+    DFP_LAUNCH_CHECK("k_decoder_dw_tc");
+    DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC, 1><<<blocks, dw::GROUPS * dw::PRODUCERS + 32, smem, st>>>(a));
     DFP_LAUNCH_CHECK("k_decoder_dw_tc");
     return DFP_OK;
 }
