@@ -23,8 +23,8 @@ namespace dfp {
 namespace dw {
 constexpr int BLK = 4096;                     // one [128][32] f32 tile (16 KB)
 constexpr uint32_t BLK_BYTES = BLK * 4;
-constexpr int NSTAGE = 3;
-constexpr int STAGE = 3 * BLK;                // A_hi | A_lo | B
+constexpr int NSTAGE = 2;
+constexpr int STAGE = 5 * BLK;                // A_hi | A_lo | B0 | B1 | B2  (an item = one A block against up to 3 delta blocks)
 constexpr int ONES = NSTAGE * STAGE;          // constant-one A block (column 0 == 1): second MN block of every hi operand
 constexpr int ZERO = ONES + BLK;              // zero block: second MN block of every lo operand
 constexpr int FLOATS = ZERO + BLK;
@@ -51,6 +51,28 @@ __device__ __forceinline__ DwProduct dw_product(int p) {
 }
 template <int CD> __host__ __device__ constexpr int dw_num_products() { return 5 + 5 * (CD / 32) + 6 + 3; }
 
+// An item = up to three products that share their A block; its MMAs are N = 32 * nprod wide (the transposed SS-mode
+// TF32 MMA has a high fixed cost, ~27 ns measured, so fewer and wider MMAs win).  slot = first 32-column TMEM slot.
+struct DwItem { int nprod; int prod[3]; int slot; };
+template <int CD, int PASS> __host__ __device__ constexpr int dw_num_items() { return PASS == 0 ? 5 + 2 * (CD / 32) : 4; }
+template <int CD, int PASS>
+__device__ __forceinline__ DwItem dw_item(int it) {
+    DwItem d = {1, {0, 0, 0}, 0};
+    if (PASS == 0) {
+        if (it < 5) { d.prod[0] = it; d.slot = it; return d; }                 // pts_linears.1..4, output_linear
+        const int hf = (it - 5) >> 1, second = (it - 5) & 1;                   // fc_c: (c half, [dh_0 dh_1 dh_2]) and (c half, [dh_3 dh_4])
+        const int base = 5 + hf * 5 + (second ? 3 : 0);
+        d.nprod = second ? 2 : 3;
+        d.prod[0] = base; d.prod[1] = base + 1; d.prod[2] = base + 2;
+        d.slot = base;
+        return d;
+    }
+    constexpr int B0 = 5 + 5 * (CD / 32);
+    if (it < 3) { d.nprod = 2; d.prod[0] = B0 + it; d.prod[1] = B0 + 3 + it; d.slot = 2 * it; return d; }   // sin chunk x [dacc_0 | dacc_3]
+    d.nprod = 3; d.prod[0] = B0 + 6; d.prod[1] = B0 + 7; d.prod[2] = B0 + 8; d.slot = 6;                        // point x [darg chunks]
+    return d;
+}
+
 // write 32 values of sample-row `row` into a swizzled [128][32] tile, as eight 16-byte stores
 __device__ __forceinline__ void tile_store_row(float* tile, int row, const float (&v)[32]) {
 #pragma unroll
@@ -73,9 +95,7 @@ template <int DEC, int PASS>
 __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_dw_tc(const DecArgs a) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
     constexpr int NOUT = (DEC == 2) ? 4 : 1;
-    constexpr int NPROD_ALL = dw_num_products<CD>();
-    constexpr int P0 = (PASS == 0) ? 0 : 5 + 5 * (CD / 32);          // first product of this pass
-    constexpr int NP = (PASS == 0) ? 5 + 5 * (CD / 32) : NPROD_ALL - P0;   // 10 / 15 products (pass 0), 9 (pass 1): <= 16 x 32 TMEM columns
+    constexpr int NI = dw_num_items<CD, PASS>();                     // items per tile: 7 / 9 (pass 0), 4 (pass 1)
     using L = DecOff<CD>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -125,16 +145,17 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
         if (warp == dw::GROUPS * dw::PRODUCERS / 32) {
             // ===================== MMA issuer (one lane) =====================
             if (lane == 0) {
-                const uint32_t total = (uint32_t)NP * (uint32_t)n_active;
-                for (uint32_t q = 0; q < total; ++q) {                   // item q = (tile q / NP, product P0 + q % NP)
+                const uint32_t total = (uint32_t)NI * (uint32_t)n_active;
+                for (uint32_t q = 0; q < total; ++q) {                   // q = tile * NI + item (tile-outer)
                     const int st = q % dw::NSTAGE;
+                    const DwItem it = dw_item<CD, PASS>((int)(q % NI));
                     tc::mbar_wait(&full_bar[st], (q / dw::NSTAGE) & 1);
                     tc::fence_after_sync();
                     const uint32_t sa = sm_base + st * dw::STAGE * 4;
                     const uint32_t a_hi = sa, a_lo = sa + dw::BLK_BYTES, b = sa + 2 * dw::BLK_BYTES;
-                    // M = 64: rows 0..31 = the product, row 32 = column sums of the delta tile (constant-one block)
-                    tc::mma_outer64(tb + (q % NP) * 32, a_hi, sm_base + dw::ONES * 4 - a_hi, a_lo, sm_base + dw::ZERO * 4 - a_lo, b, 32,
-                                    q >= (uint32_t)NP);
+                    // M = 64: rows 0..31 = the products, row 32 = column sums of the delta tiles (constant-one block)
+                    tc::mma_outer64(tb + it.slot * 32, a_hi, sm_base + dw::ONES * 4 - a_hi, a_lo, sm_base + dw::ZERO * 4 - a_lo, b,
+                                    32 * it.nprod, q >= (uint32_t)NI);
                     tc::mma_commit(&empty_bar[st]);                      // stage reusable once these MMAs have read it
                 }
                 tc::mma_commit(&done_bar);                               // everything accumulated
@@ -142,88 +163,99 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
         } else {
             // ===================== producers (256 threads) + flush (warp 0) =====================
             const int pgrp = tid / dw::PRODUCERS;                  // this thread's producer group
-            const bool roleA = (tid % dw::PRODUCERS) < 128;
+            const int half = (tid % dw::PRODUCERS) >> 7;           // 0: stages A (and delta block 2), 1: stages delta blocks 0 and 1
             const int row = tid & 127;
             float* g = a.gparams + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR));
-            // this thread's 32 operand values of item (product p, active tile t)
-            auto load_item = [&](int p, int t, float (&v)[32]) {
-                const DwProduct pr = dw_product<CD>(p);
-                const int64_t s_raw = (int64_t)tile_list[t] * 128 + row;
-                const bool valid = s_raw < n;
-                const int64_t s = valid ? s_raw : n - 1;
-                if (roleA) {
-                    if (pr.kind == 0) load_features(a.act_h, 160, s, (pr.i - 1) * 32, valid, v);
-                    else if (pr.kind == 1) load_features(a.act_h, 160, s, 4 * 32, valid, v);
-                    else if (pr.kind == 2) load_features(a.act_c, CD, s, pr.hf * 32, valid, v);
-                    else if (pr.kind == 3) load_features(a.sc_e, 96, s, pr.cb * 32, valid, v);
-                    else {
-                        float pw[3] = {0.f, 0.f, 0.f};
-                        if (valid) {
-                            if (a.ps.pts == nullptr) {
-                                const int64_t r = s / a.ps.S;
-                                double pq[3];
-                                const float o[3] = {a.ps.rays_o[3 * r], a.ps.rays_o[3 * r + 1], a.ps.rays_o[3 * r + 2]};
-                                const float d[3] = {a.ps.rays_d[3 * r], a.ps.rays_d[3 * r + 1], a.ps.rays_d[3 * r + 2]};
-                                ray_point(o, d, a.ps.z[s], pq);
-                                pw[0] = (float)pq[0]; pw[1] = (float)pq[1]; pw[2] = (float)pq[2];
-                            } else if (a.ps.pts_f64) {
-                                const double* pq = reinterpret_cast<const double*>(a.ps.pts) + 3 * s;
-                                pw[0] = (float)pq[0]; pw[1] = (float)pq[1]; pw[2] = (float)pq[2];
-                            } else {
-                                const float* pq = reinterpret_cast<const float*>(a.ps.pts) + 3 * s;
-                                pw[0] = pq[0]; pw[1] = pq[1]; pw[2] = pq[2];
-                            }
+            // the A block (32 features) of product p for sample s
+            auto load_A = [&](const DwProduct& pr, int64_t s, bool valid, float (&v)[32]) {
+                if (pr.kind == 0) load_features(a.act_h, 160, s, (pr.i - 1) * 32, valid, v);
+                else if (pr.kind == 1) load_features(a.act_h, 160, s, 4 * 32, valid, v);
+                else if (pr.kind == 2) load_features(a.act_c, CD, s, pr.hf * 32, valid, v);
+                else if (pr.kind == 3) load_features(a.sc_e, 96, s, pr.cb * 32, valid, v);
+                else {
+                    float pw[3] = {0.f, 0.f, 0.f};
+                    if (valid) {
+                        if (a.ps.pts == nullptr) {
+                            const int64_t r = s / a.ps.S;
+                            double pq[3];
+                            const float o[3] = {a.ps.rays_o[3 * r], a.ps.rays_o[3 * r + 1], a.ps.rays_o[3 * r + 2]};
+                            const float d[3] = {a.ps.rays_d[3 * r], a.ps.rays_d[3 * r + 1], a.ps.rays_d[3 * r + 2]};
+                            ray_point(o, d, a.ps.z[s], pq);
+                            pw[0] = (float)pq[0]; pw[1] = (float)pq[1]; pw[2] = (float)pq[2];
+                        } else if (a.ps.pts_f64) {
+                            const double* pq = reinterpret_cast<const double*>(a.ps.pts) + 3 * s;
+                            pw[0] = (float)pq[0]; pw[1] = (float)pq[1]; pw[2] = (float)pq[2];
+                        } else {
+                            const float* pq = reinterpret_cast<const float*>(a.ps.pts) + 3 * s;
+                            pw[0] = pq[0]; pw[1] = pq[1]; pw[2] = pq[2];
                         }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = j < 3 ? pw[j] : 0.f;
                     }
-                } else {
-                    if (pr.kind == 0 || pr.kind == 3) {
-                        const int blk = pr.kind == 0 ? pr.i : pr.which;
-                        load_features(a.sc_dh, 160, s, blk * 32, valid, v);
-                        const uint32_t m = a.act_m[tm_index(s, blk, 5)];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
-                    } else if (pr.kind == 1) {
-                        float d4[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (valid) {
-                            if (NOUT == 1) d4[0] = a.dout[s];
-                            else { const float4 x = *reinterpret_cast<const float4*>(a.dout + 4 * s); d4[0] = x.x; d4[1] = x.y; d4[2] = x.z; }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = j < 4 ? d4[j] : 0.f;     // colour: the 4th output carries no gradient
-                    } else if (pr.kind == 2) {
-                        load_features(a.sc_dh, 160, s, pr.i * 32, valid, v);
-                    } else {
-                        load_features(a.sc_darg, 96, s, pr.cb * 32, valid, v);
-                    }
+                    for (int j = 0; j < 32; ++j) v[j] = j < 3 ? pw[j] : 0.f;
                 }
             };
-            // items are numbered q = t * NP + (p - P0) (tile-outer); this group stages the items with q % GROUPS == pgrp
-            const uint32_t total = (uint32_t)NP * (uint32_t)n_active;
-            float vnext[32];
-            uint32_t q = (uint32_t)pgrp;
-            if (q < total) load_item(P0 + (int)(q % NP), (int)(q / NP), vnext);
-            for (; q < total; q += dw::GROUPS) {
-                const int st = q % dw::NSTAGE;
-                float v[32];
+            // the delta block (32 columns) of product p for sample s
+            auto load_B = [&](const DwProduct& pr, int64_t s, bool valid, float (&v)[32]) {
+                if (pr.kind == 0 || pr.kind == 3) {
+                    const int blk = pr.kind == 0 ? pr.i : pr.which;
+                    load_features(a.sc_dh, 160, s, blk * 32, valid, v);
+                    const uint32_t m = a.act_m[tm_index(s, blk, 5)];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = vnext[j];
-                // software pipeline: this group's next item is in flight while the current one is split and stored
-                const uint32_t qn = q + dw::GROUPS;
-                if (qn < total) load_item(P0 + (int)(qn % NP), (int)(qn / NP), vnext);
+                    for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
+                } else if (pr.kind == 1) {
+                    float d4[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
+                        if (NOUT == 1) d4[0] = a.dout[s];
+                        else { const float4 x = *reinterpret_cast<const float4*>(a.dout + 4 * s); d4[0] = x.x; d4[1] = x.y; d4[2] = x.z; }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = j < 4 ? d4[j] : 0.f;     // colour: the 4th output carries no gradient
+                } else if (pr.kind == 2) {
+                    load_features(a.sc_dh, 160, s, pr.i * 32, valid, v);
+                } else {
+                    load_features(a.sc_darg, 96, s, pr.cb * 32, valid, v);
+                }
+            };
+            // items are numbered q = tile * NI + item (tile-outer); this group stages the items with q % GROUPS == pgrp
+            const uint32_t total = (uint32_t)NI * (uint32_t)n_active;
+            for (uint32_t q = (uint32_t)pgrp; q < total; q += dw::GROUPS) {
+                const int st = q % dw::NSTAGE;
+                const DwItem it = dw_item<CD, PASS>((int)(q % NI));
+                const int64_t s_raw = (int64_t)tile_list[q / NI] * 128 + row;
+                const bool valid = s_raw < n;
+                const int64_t s = valid ? s_raw : n - 1;
+                float v0[32], v1[32];
+                // half 0: the A block and (if present) delta block 2;  half 1: delta blocks 0 and (if present) 1
+                const bool second = half == 0 ? it.nprod > 2 : it.nprod > 1;
+                if (half == 0) {
+                    load_A(dw_product<CD>(it.prod[0]), s, valid, v0);
+                    if (second) load_B(dw_product<CD>(it.prod[2]), s, valid, v1);
+                } else {
+                    load_B(dw_product<CD>(it.prod[0]), s, valid, v0);
+                    if (second) load_B(dw_product<CD>(it.prod[1]), s, valid, v1);
+                }
                 if (q >= dw::NSTAGE) tc::mbar_wait(&empty_bar[st], ((q / dw::NSTAGE) - 1) & 1);      // MMAs of the previous use are done
                 float* stage = sm + st * dw::STAGE;
-                if (roleA) {
-                    float hi[32], lo[32];
+                if (half == 0) {
+                    float hi[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { hi[j] = tc::tf32_rna(v[j]); lo[j] = tc::tf32_rna(v[j] - hi[j]); }
+                    for (int j = 0; j < 32; ++j) { hi[j] = tc::tf32_rna(v0[j]); v0[j] = tc::tf32_rna(v0[j] - hi[j]); }
                     tile_store_row(stage, row, hi);
-                    tile_store_row(stage + dw::BLK, row, lo);
+                    tile_store_row(stage + dw::BLK, row, v0);
+                    if (second) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v1[j] = tc::tf32_rna(v1[j]);
+                        tile_store_row(stage + 4 * dw::BLK, row, v1);
+                    }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = tc::tf32_rna(v[j]);
-                    tile_store_row(stage + 2 * dw::BLK, row, v);
+                    for (int j = 0; j < 32; ++j) v0[j] = tc::tf32_rna(v0[j]);
+                    tile_store_row(stage + 2 * dw::BLK, row, v0);
+                    if (second) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v1[j] = tc::tf32_rna(v1[j]);
+                        tile_store_row(stage + 3 * dw::BLK, row, v1);
+                    }
                 }
                 tc::fence_proxy_async();
                 mbar_arrive(&full_bar[st]);
@@ -233,10 +265,13 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
                 tc::mbar_wait(&done_bar, 0);
                 tc::fence_after_sync();
 #pragma unroll 1
-                for (int pp = 0; pp < NP; ++pp) {
-                    const DwProduct pr = dw_product<CD>(P0 + pp);
+                for (int pp = 0; pp < NI * 3; ++pp) {
+                    const DwItem it = dw_item<CD, PASS>(pp / 3);
+                    const int blk = pp % 3;
+                    if (blk >= it.nprod) continue;
+                    const DwProduct pr = dw_product<CD>(it.prod[blk]);
                     float d[32];
-                    tc::tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + pp * 32, d);
+                    tc::tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + (it.slot + blk) * 32, d);
                     tc::wait_ld();
                     if (lane < 16) {
                         const int k = warp * 16 + lane;                 // accumulator row
