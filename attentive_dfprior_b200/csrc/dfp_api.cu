@@ -480,7 +480,9 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
     if (hi) {
         set_act(1);
         da.grid = sc->high; da.grid_low = sc->low; da.out = w.high;
+        if (tcp) { da.list = w.band_list; da.count = w.band_count; }      // high occupancy is only read on band samples
         if ((rc = tcp ? launch_decoder_fwd_tc<1, MODE>(da, st) : launch_decoder_fwd<1, MODE>(da, st))) return rc;
+        da.list = nullptr; da.count = nullptr;
     }
     if (stage == DFP_STAGE_COLOR) {
         set_act(2);
@@ -527,6 +529,7 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
         constexpr int DEC = decltype(dec_tag)::value;
         if (!tcb) return launch_decoder_bwd<DEC, MODE>(da, st);
         da.act_h = w.act_h[DEC]; da.act_m = w.act_m[DEC]; da.act_c = w.act_c[DEC];
+        da.list = (DEC == 1) ? w.band_list : nullptr; da.count = (DEC == 1) ? w.band_count : nullptr;   // as in the forward
         int r = launch_decoder_dh_tc<DEC, MODE>(da, st);
         if (r || !da.gparams) return r;
         if (tc_backward_level() >= 2) return launch_decoder_dw_tc<DEC>(da, st);

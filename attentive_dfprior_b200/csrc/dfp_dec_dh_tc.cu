@@ -100,15 +100,16 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
     uint32_t parity = 0;
     const uint32_t whi = tc::smem_u32(sm), wlo = tc::smem_u32(sm + T::BSIZE);
     const BoxT<PT> box = make_box<PT>(a.bound.b);
-    const int64_t tiles = (a.n + 127) / 128;
+    const int64_t n = dec_items(a);
+    const int64_t tiles = (n + 127) / 128;
     const bool issuer = (gt == 0);
     const float bmax = embed_bmax(sm + T::S_B);
-    const int64_t n = a.n;
 
     for (int64_t tile = (int64_t)blockIdx.x * 2 + grp; tile < tiles; tile += (int64_t)gridDim.x * 2) {
-        const int64_t s_raw = tile * 128 + gt;
-        const bool valid = s_raw < n;
-        const int64_t s = valid ? s_raw : n - 1;
+        const int64_t i_raw = tile * 128 + gt;
+        const bool valid = i_raw < n;
+        const int64_t ia = valid ? i_raw : n - 1;                    // list position: index of saved activations and scratch
+        const int64_t s = dec_sample(a, ia);                         // sample id: index of points, dout, dp
         float dout[NOUT];
         if (NOUT == 1) dout[0] = valid ? a.dout[s] : 0.f;
         else {
@@ -137,13 +138,13 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
 
 #pragma unroll 1
         for (int i = 4; i >= 1; --i) {
-            const uint32_t m = a.act_m[tm_index(s, i, 5)];
+            const uint32_t m = a.act_m[tm_index(ia, i, 5)];
             float dacc[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) dacc[j] = ((m >> j) & 1u) ? dh[j] : 0.f;
             if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a.sc_dh[tm_index(s, i * 32 + j, 160)] = dh[j];
+                for (int j = 0; j < 32; ++j) a.sc_dh[tm_index(ia, i * 32 + j, 160)] = dh[j];
             }
             tc::tmem_store_split32(tl + T::T_A, tl + T::T_A + 32, dh);            // for d_c += dh_i * Wc_i
             tc::tmem_store_split32(tl + T::T_A + 64, tl + T::T_A + 96, dacc);     // for dh_{i-1} = dacc_i * W_i
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
         {
             if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a.sc_dh[tm_index(s, j, 160)] = dh[j];
+                for (int j = 0; j < 32; ++j) a.sc_dh[tm_index(ia, j, 160)] = dh[j];
             }
             tc::tmem_store_split32(tl + T::T_A, tl + T::T_A + 32, dh);
             tc::wait_st();
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
                 tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + T::WC * 4, wlo + T::WC * 4, 32, 32, 4096u, true);
                 tc::mma_commit(bar);
             }
-            const uint32_t m0 = a.act_m[tm_index(s, 0, 5)];
+            const uint32_t m0 = a.act_m[tm_index(ia, 0, 5)];
 #pragma unroll
             for (int j = 0; j < 32; ++j) dh[j] = ((m0 >> j) & 1u) ? dh[j] : 0.f;      // dacc_0
             tc::mbar_wait(bar, parity); parity ^= 1;
@@ -256,8 +257,8 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
             if (valid && a.gparams) {
 #pragma unroll
                 for (int kk = 0; kk < 32; ++kk) {
-                    a.sc_e[tm_index(s, ch * 32 + kk, 96)] = sn[kk];
-                    a.sc_darg[tm_index(s, ch * 32 + kk, 96)] = da[kk];
+                    a.sc_e[tm_index(ia, ch * 32 + kk, 96)] = sn[kk];
+                    a.sc_darg[tm_index(ia, ch * 32 + kk, 96)] = da[kk];
                 }
             }
         }

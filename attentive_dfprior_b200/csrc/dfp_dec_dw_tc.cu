@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
     __shared__ int tile_list[dw::MAX_TILES];
     __shared__ int n_active_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t n = a.n;
+    const int64_t n = dec_items(a);
     const int64_t tiles = (n + 127) / 128;
 
     for (int i = tid; i < dw::FLOATS; i += blockDim.x) sm[i] = 0.f;
@@ -117,8 +117,9 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
         for (int64_t tile = blockIdx.x; tile < tiles && cnt < dw::MAX_TILES; tile += gridDim.x) {
             bool any = false;
             for (int r = lane; r < 128; r += 32) {
-                const int64_t s = tile * 128 + r;
-                if (s < n) {
+                const int64_t ii = tile * 128 + r;
+                if (ii < n) {
+                    const int64_t s = dec_sample(a, ii);
                     if (NOUT == 1) any = any || a.dout[s] != 0.f;
                     else { const float4 v = *reinterpret_cast<const float4*>(a.dout + 4 * s); any = any || v.x != 0.f || v.y != 0.f || v.z != 0.f; }
                 }
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
             const int row = tid & 127;
             float* g = a.gparams + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR));
             // the A block (32 features) of product p for sample s
-            auto load_A = [&](const DwProduct& pr, int64_t s, bool valid, float (&v)[32]) {
+            auto load_A = [&](const DwProduct& pr, int64_t s, int64_t sid, bool valid, float (&v)[32]) {
                 if (pr.kind == 0) load_features(a.act_h, 160, s, (pr.i - 1) * 32, valid, v);
                 else if (pr.kind == 1) load_features(a.act_h, 160, s, 4 * 32, valid, v);
                 else if (pr.kind == 2) load_features(a.act_c, CD, s, pr.hf * 32, valid, v);
@@ -176,17 +177,17 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
                     float pw[3] = {0.f, 0.f, 0.f};
                     if (valid) {
                         if (a.ps.pts == nullptr) {
-                            const int64_t r = s / a.ps.S;
+                            const int64_t r = sid / a.ps.S;
                             double pq[3];
                             const float o[3] = {a.ps.rays_o[3 * r], a.ps.rays_o[3 * r + 1], a.ps.rays_o[3 * r + 2]};
                             const float d[3] = {a.ps.rays_d[3 * r], a.ps.rays_d[3 * r + 1], a.ps.rays_d[3 * r + 2]};
-                            ray_point(o, d, a.ps.z[s], pq);
+                            ray_point(o, d, a.ps.z[sid], pq);
                             pw[0] = (float)pq[0]; pw[1] = (float)pq[1]; pw[2] = (float)pq[2];
                         } else if (a.ps.pts_f64) {
-                            const double* pq = reinterpret_cast<const double*>(a.ps.pts) + 3 * s;
+                            const double* pq = reinterpret_cast<const double*>(a.ps.pts) + 3 * sid;
                             pw[0] = (float)pq[0]; pw[1] = (float)pq[1]; pw[2] = (float)pq[2];
                         } else {
-                            const float* pq = reinterpret_cast<const float*>(a.ps.pts) + 3 * s;
+                            const float* pq = reinterpret_cast<const float*>(a.ps.pts) + 3 * sid;
                             pw[0] = pq[0]; pw[1] = pq[1]; pw[2] = pq[2];
                         }
                     }
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
                 }
             };
             // the delta block (32 columns) of product p for sample s
-            auto load_B = [&](const DwProduct& pr, int64_t s, bool valid, float (&v)[32]) {
+            auto load_B = [&](const DwProduct& pr, int64_t s, int64_t sid, bool valid, float (&v)[32]) {
                 if (pr.kind == 0 || pr.kind == 3) {
                     const int blk = pr.kind == 0 ? pr.i : pr.which;
                     load_features(a.sc_dh, 160, s, blk * 32, valid, v);
@@ -205,8 +206,8 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
                 } else if (pr.kind == 1) {
                     float d4[4] = {0.f, 0.f, 0.f, 0.f};
                     if (valid) {
-                        if (NOUT == 1) d4[0] = a.dout[s];
-                        else { const float4 x = *reinterpret_cast<const float4*>(a.dout + 4 * s); d4[0] = x.x; d4[1] = x.y; d4[2] = x.z; }
+                        if (NOUT == 1) d4[0] = a.dout[sid];
+                        else { const float4 x = *reinterpret_cast<const float4*>(a.dout + 4 * sid); d4[0] = x.x; d4[1] = x.y; d4[2] = x.z; }
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = j < 4 ? d4[j] : 0.f;     // colour: the 4th output carries no gradient
@@ -221,18 +222,19 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
             for (uint32_t q = (uint32_t)pgrp; q < total; q += dw::GROUPS) {
                 const int st = q % dw::NSTAGE;
                 const DwItem it = dw_item<CD, PASS>((int)(q % NI));
-                const int64_t s_raw = (int64_t)tile_list[q / NI] * 128 + row;
-                const bool valid = s_raw < n;
-                const int64_t s = valid ? s_raw : n - 1;
+                const int64_t i_raw = (int64_t)tile_list[q / NI] * 128 + row;
+                const bool valid = i_raw < n;
+                const int64_t s = valid ? i_raw : n - 1;             // list position (saved activations / scratch index)
+                const int64_t sid = dec_sample(a, s);                // sample id (points, dout)
                 float v0[32], v1[32];
                 // half 0: the A block and (if present) delta block 2;  half 1: delta blocks 0 and (if present) 1
                 const bool second = half == 0 ? it.nprod > 2 : it.nprod > 1;
                 if (half == 0) {
-                    load_A(dw_product<CD>(it.prod[0]), s, valid, v0);
-                    if (second) load_B(dw_product<CD>(it.prod[2]), s, valid, v1);
+                    load_A(dw_product<CD>(it.prod[0]), s, sid, valid, v0);
+                    if (second) load_B(dw_product<CD>(it.prod[2]), s, sid, valid, v1);
                 } else {
-                    load_B(dw_product<CD>(it.prod[0]), s, valid, v0);
-                    if (second) load_B(dw_product<CD>(it.prod[1]), s, valid, v1);
+                    load_B(dw_product<CD>(it.prod[0]), s, sid, valid, v0);
+                    if (second) load_B(dw_product<CD>(it.prod[1]), s, sid, valid, v1);
                 }
                 if (q >= dw::NSTAGE) tc::mbar_wait(&empty_bar[st], ((q / dw::NSTAGE) - 1) & 1);      // MMAs of the previous use are done
                 float* stage = sm + st * dw::STAGE;

@@ -94,14 +94,16 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
     uint32_t parity = 0;
     const uint32_t bhi = tc::smem_u32(sm), blo = tc::smem_u32(sm + T::BSIZE);
     const BoxT<PT> box = make_box<PT>(a.bound.b);
-    const int64_t tiles = (a.n + 127) / 128;
+    const int64_t nitems = dec_items(a);
+    const int64_t tiles = (nitems + 127) / 128;
     const bool issuer = (gt == 0);
     const float bmax = embed_bmax(sm + T::S_B);
 
     for (int64_t tile = (int64_t)blockIdx.x * T::GROUPS + grp; tile < tiles; tile += (int64_t)gridDim.x * T::GROUPS) {
-        const int64_t s_raw = tile * 128 + gt;
-        const bool valid = s_raw < a.n;
-        const int64_t s = valid ? s_raw : a.n - 1;
+        const int64_t i_raw = tile * 128 + gt;
+        const bool valid = i_raw < nitems;
+        const int64_t ia = valid ? i_raw : nitems - 1;               // position in the (optional) list: index of saved activations
+        const int64_t s = dec_sample(a, ia);                         // sample id: index of points and outputs
         PT p[3];
         load_point<MODE>(a.ps, s, p);
         float xn[3];
@@ -114,14 +116,14 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
             tc::tmem_store_split32(tl + T::T_C_HI, tl + T::T_C_LO, c);
             if (a.act_c && valid) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) a.act_c[tm_index(s, k, CD)] = c[k];
+                for (int k = 0; k < 32; ++k) a.act_c[tm_index(ia, k, CD)] = c[k];
             }
             if (DEC == 1) {
                 gather_features(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), c);
                 tc::tmem_store_split32(tl + T::T_C_HI + 32, tl + T::T_C_LO + 32, c);
                 if (a.act_c && valid) {
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) a.act_c[tm_index(s, 32 + k, CD)] = c[k];
+                    for (int k = 0; k < 32; ++k) a.act_c[tm_index(ia, 32 + k, CD)] = c[k];
                 }
             }
         }
@@ -175,9 +177,9 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
                 h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + j]);
             }
             if (a.act_h && valid) {                                   // kept for the backward (DFP_FLAG_SAVE_ACT)
-                a.act_m[tm_index(s, 0, 5)] = m;
+                a.act_m[tm_index(ia, 0, 5)] = m;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a.act_h[tm_index(s, j, 160)] = h[j];
+                for (int j = 0; j < 32; ++j) a.act_h[tm_index(ia, j, 160)] = h[j];
             }
         }
 #pragma unroll 1
@@ -216,9 +218,9 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
                 h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + i * 32 + j]);
             }
             if (a.act_h && valid) {
-                a.act_m[tm_index(s, i, 5)] = m;
+                a.act_m[tm_index(ia, i, 5)] = m;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a.act_h[tm_index(s, i * 32 + j, 160)] = h[j];
+                for (int j = 0; j < 32; ++j) a.act_h[tm_index(ia, i * 32 + j, 160)] = h[j];
             }
         }
         float out[NOUT];

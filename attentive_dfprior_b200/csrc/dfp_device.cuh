@@ -205,7 +205,14 @@ struct DecArgs {
     float* dp;               // [n][3] accumulated, or null
     // tensor-core training path (DFP_FLAG_SAVE_ACT): saved activations / backward scratch, feature-major with stride n
     float* act_h; uint32_t* act_m; float* act_c; float* sc_e; float* sc_dh; float* sc_darg;
+    // optional compacted sample list (device): the kernel then processes samples list[0..*count) only and indexes the
+    // saved activations / scratch by list position.  Used for the high decoder, whose output and gradient only matter
+    // on TSDF-band samples (decoder.py:326-333: f_add_m_occ is read under the band mask only).
+    const int* list; const int* count;
 };
+// number of work items and the sample id of item idx
+__device__ __forceinline__ int64_t dec_items(const DecArgs& a) { return a.list ? (int64_t)*a.count : a.n; }
+__device__ __forceinline__ int64_t dec_sample(const DecArgs& a, int64_t idx) { return a.list ? (int64_t)a.list[idx] : idx; }
 
 
 // ------------------------------------------------------------------------------------------
