@@ -1,6 +1,6 @@
 // Tensor-core decoder backward, kernel 1 of 2: the delta chain.
 //
-// For tiles of 128 samples (one thread = one sample = one TMEM lane) this back-propagates through the five blocks
+// For tiles of 128 samples (one sample = one TMEM lane, served by two threads that own 16 columns each) this back-propagates through the five blocks
 // of one decoder (src/conv_onet/models/decoder.py:192-203 reversed) using the activations the tensor-core forward
 // kept (ReLU masks): per block  d_c += dh_i * Wc_i  and  dh_{i-1} = mask_i(dh_i) * W_i  run as tcgen05.mma with the
 // deltas written into TMEM by their owner threads and the weights resident in shared memory in their natural
@@ -59,13 +59,13 @@ __device__ __forceinline__ void stage_weights_dh(float* sm, const float* __restr
     for (int i = threadIdx.x; i < 288; i += nt) sm[DhLayout::S_B + i] = P[L::B + i];
 }
 
-// OR-reduction of a predicate over the 128 threads of one group (named barrier `id`)
+// OR-reduction of a predicate over the 256 threads of one group (named barrier `id`)
 __device__ __forceinline__ bool group_any(bool v, int id) {
     uint32_t r;
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.u32 q, %1, 0;\n\t"
-        "barrier.cta.red.or.pred p, %2, 128, q;\n\t"
+        "barrier.cta.red.or.pred p, %2, 256, q;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(r)
         : "r"((uint32_t)v), "r"(id)
@@ -73,8 +73,10 @@ __device__ __forceinline__ bool group_any(bool v, int id) {
     return r != 0;
 }
 
+// Two threads per sample (as in the forward, dfp_dec_fwd_tc.cu): thread (row r, half hf) owns columns 16*hf..16*hf+15
+// of every 32-wide delta block of sample r.
 template <int DEC, int MODE>
-__global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
+__global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
     constexpr int NOUT = (DEC == 2) ? 4 : 1;
     using PT = typename PtT<MODE>::T;
@@ -83,9 +85,11 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
     float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float part[2][6][128];                                  // d(point) partial sums of the upper halves
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int grp = tid >> 7, gt = tid & 127;
+    const int grp = tid >> 8, gt = tid & 255;
+    const int r = gt & 127, hf = gt >> 7;
     stage_weights_dh<CD>(sm, a.params + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR)));
     if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
     if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_mbar_init(); }
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
     tc::fence_after_sync();
 
     const uint32_t tb = tmem_base_s + (uint32_t)(grp * T::T_COLS);
-    const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16) + 16u * hf;      // this warp's lanes, this half's columns
     uint64_t* bar = &bars[grp];
     uint32_t parity = 0;
     const uint32_t whi = tc::smem_u32(sm), wlo = tc::smem_u32(sm + T::BSIZE);
@@ -104,9 +108,10 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
     const int64_t tiles = (n + 127) / 128;
     const bool issuer = (gt == 0);
     const float bmax = embed_bmax(sm + T::S_B);
+    const int c0 = 16 * hf;
 
     for (int64_t tile = (int64_t)blockIdx.x * 2 + grp; tile < tiles; tile += (int64_t)gridDim.x * 2) {
-        const int64_t i_raw = tile * 128 + gt;
+        const int64_t i_raw = tile * 128 + r;
         const bool valid = i_raw < n;
         const int64_t ia = valid ? i_raw : n - 1;                    // list position: index of saved activations and scratch
         const int64_t s = dec_sample(a, ia);                         // sample id: index of points, dout, dp
@@ -124,33 +129,35 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
         // it decides with the same predicate (all upstream gradients of the tile are zero)
         if (!group_any(any, 1 + grp)) continue;
 
-        float dh[32];
+        float dh[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
             float acc = 0.f;
 #pragma unroll
-            for (int o = 0; o < NOUT; ++o) acc = fmaf(sm[T::S_WO + o * 32 + j], dout[o], acc);
+            for (int o = 0; o < NOUT; ++o) acc = fmaf(sm[T::S_WO + o * 32 + c0 + j], dout[o], acc);
             dh[j] = acc;
         }
-        float dacc3[32];
+        float dacc3[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dacc3[j] = 0.f;
+        for (int j = 0; j < 16; ++j) dacc3[j] = 0.f;
 
+        uint32_t m_next = a.act_m[tm_index(ia, 4, 5)];             // ReLU masks are fetched one block ahead of their use
 #pragma unroll 1
         for (int i = 4; i >= 1; --i) {
-            const uint32_t m = a.act_m[tm_index(ia, i, 5)];
-            float dacc[32];
+            const uint32_t m = m_next >> c0;
+            m_next = a.act_m[tm_index(ia, i - 1, 5)];
+            float dacc[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dacc[j] = ((m >> j) & 1u) ? dh[j] : 0.f;
+            for (int j = 0; j < 16; ++j) dacc[j] = ((m >> j) & 1u) ? dh[j] : 0.f;
             if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a.sc_dh[tm_index(ia, i * 32 + j, 160)] = dh[j];
+                for (int j = 0; j < 16; ++j) a.sc_dh[tm_index(ia, i * 32 + c0 + j, 160)] = dh[j];
             }
-            tc::tmem_store_split32(tl + T::T_A, tl + T::T_A + 32, dh);            // for d_c += dh_i * Wc_i
-            tc::tmem_store_split32(tl + T::T_A + 64, tl + T::T_A + 96, dacc);     // for dh_{i-1} = dacc_i * W_i
+            tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 32, dh);            // for d_c += dh_i * Wc_i
+            tc::tmem_store_split16(tl + T::T_A + 64, tl + T::T_A + 96, dacc);     // for dh_{i-1} = dacc_i * W_i
             tc::wait_st();
             tc::fence_before_sync();
-            tc::named_bar_sync(3 + grp, 128);
+            tc::named_bar_sync(3 + grp, 256);
             if (issuer) {
                 tc::fence_after_sync();
                 tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + (T::WC + i * 1024) * 4, wlo + (T::WC + i * 1024) * 4,
@@ -161,48 +168,39 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
             }
             if (i == 3) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) dacc3[j] = dacc[j];
+                for (int j = 0; j < 16; ++j) dacc3[j] = dacc[j];
             }
             tc::mbar_wait(bar, parity); parity ^= 1;
             tc::fence_after_sync();
-            tc::tmem_ld32(tl + T::T_DX, dh);
+            tc::tmem_ld16(tl + T::T_DX, dh);
             tc::wait_ld();
         }
         // block 0: fc_c[0] path, then the embedding
         {
             if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a.sc_dh[tm_index(ia, j, 160)] = dh[j];
+                for (int j = 0; j < 16; ++j) a.sc_dh[tm_index(ia, c0 + j, 160)] = dh[j];
             }
-            tc::tmem_store_split32(tl + T::T_A, tl + T::T_A + 32, dh);
+            tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 32, dh);
             tc::wait_st();
             tc::fence_before_sync();
-            tc::named_bar_sync(3 + grp, 128);
+            tc::named_bar_sync(3 + grp, 256);
             if (issuer) {
                 tc::fence_after_sync();
                 tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + T::WC * 4, wlo + T::WC * 4, 32, 32, 4096u, true);
                 tc::mma_commit(bar);
             }
-            const uint32_t m0 = a.act_m[tm_index(ia, 0, 5)];
+            const uint32_t m0 = m_next >> c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dh[j] = ((m0 >> j) & 1u) ? dh[j] : 0.f;      // dacc_0
+            for (int j = 0; j < 16; ++j) dh[j] = ((m0 >> j) & 1u) ? dh[j] : 0.f;      // dacc_0
             tc::mbar_wait(bar, parity); parity ^= 1;
             tc::fence_after_sync();
             // A = [dacc_0 | dacc_3]: hi in columns 0..63, lo in 64..127
-            {
-                uint32_t hi[32], lo[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) tc::split_tf32(dh[j], hi[j], lo[j]);
-                tc::tmem_st32(tl + T::T_A, hi);
-                tc::tmem_st32(tl + T::T_A + 64, lo);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) tc::split_tf32(dacc3[j], hi[j], lo[j]);
-                tc::tmem_st32(tl + T::T_A + 32, hi);
-                tc::tmem_st32(tl + T::T_A + 96, lo);
-            }
+            tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 64, dh);
+            tc::tmem_store_split16(tl + T::T_A + 32, tl + T::T_A + 96, dacc3);
             tc::wait_st();
             tc::fence_before_sync();
-            tc::named_bar_sync(3 + grp, 128);
+            tc::named_bar_sync(3 + grp, 256);
             if (issuer) {
                 tc::fence_after_sync();
                 tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A, tb + T::T_A + 64, whi + T::W03 * 4, wlo + T::W03 * 4, 64, 96, 8192u, false);
@@ -222,14 +220,14 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
         float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
 #pragma unroll 1
         for (int ch = 0; ch < 3; ++ch) {
-            float de[32];
-            tc::tmem_ld32(tl + T::T_DX + ch * 32, de);
+            float de[16];
+            tc::tmem_ld16(tl + T::T_DX + ch * 32, de);
             tc::wait_ld();
-            float sn[32], da[32];
+            float sn[16], da[16];
             if (fast) {                                   // branch hoisted out of the unrolled loop (code size / I-cache)
 #pragma unroll
-                for (int kk = 0; kk < 32; ++kk) {
-                    const int k = ch * 32 + kk;
+                for (int kk = 0; kk < 16; ++kk) {
+                    const int k = ch * 32 + c0 + kk;
                     float s1 = (k == EMB) ? 1.f : 0.f, c1 = 0.f;    // column 93 of the sin array: constant 1 (bias of block 0 in kernel 2)
                     if (k < EMB) sincos_cw(embed_arg(sm + T::S_B, pf, k), s1, c1);
                     sn[kk] = s1;
@@ -237,17 +235,17 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
                 }
             } else {
 #pragma unroll 1
-                for (int kk = 0; kk < 32; ++kk) {
-                    const int k = ch * 32 + kk;
+                for (int kk = 0; kk < 16; ++kk) {
+                    const int k = ch * 32 + c0 + kk;
                     float s1 = (k == EMB) ? 1.f : 0.f, c1 = 0.f;
                     if (k < EMB) sincosf(embed_arg(sm + T::S_B, pf, k), &s1, &c1);
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) if (u == kk) { sn[u] = s1; da[u] = de[u] * c1; }
+                    for (int u = 0; u < 16; ++u) if (u == kk) { sn[u] = s1; da[u] = de[u] * c1; }
                 }
             }
 #pragma unroll
-            for (int kk = 0; kk < 32; ++kk) {
-                const int k = ch * 32 + kk;
+            for (int kk = 0; kk < 16; ++kk) {
+                const int k = ch * 32 + c0 + kk;
                 if (k < EMB) {
                     gp0 = fmaf(sm[T::S_B + k], da[kk], gp0);
                     gp1 = fmaf(sm[T::S_B + EMB_PAD + k], da[kk], gp1);
@@ -256,20 +254,28 @@ __global__ void __launch_bounds__(256, 1) k_decoder_dh_tc(const DecArgs a) {
             }
             if (valid && a.gparams) {
 #pragma unroll
-                for (int kk = 0; kk < 32; ++kk) {
-                    a.sc_e[tm_index(ia, ch * 32 + kk, 96)] = sn[kk];
-                    a.sc_darg[tm_index(ia, ch * 32 + kk, 96)] = da[kk];
+                for (int kk = 0; kk < 16; ++kk) {
+                    a.sc_e[tm_index(ia, ch * 32 + c0 + kk, 96)] = sn[kk];
+                    a.sc_darg[tm_index(ia, ch * 32 + c0 + kk, 96)] = da[kk];
                 }
             }
         }
-        float d_c[32];
-        tc::tmem_ld32(tl + T::T_DC, d_c);
+        float d_c[16];
+        tc::tmem_ld16(tl + T::T_DC, d_c);
         tc::wait_ld();
-        if (valid && any) {
-            const bool want_coord = a.dp != nullptr;
-            float gn[3] = {0.f, 0.f, 0.f};
-            if (a.ggrid || want_coord) scatter_features(a.grid, a.ggrid, tri, d_c, want_coord, gn);
-            if (want_coord) {
+        const bool want_coord = a.dp != nullptr;
+        float gn[3] = {0.f, 0.f, 0.f};
+        if (a.ggrid && !want_coord) scatter_features16_agg(a.grid, a.ggrid, tri, hf, d_c, valid && any);     // whole warp
+        else if (valid && any && (a.ggrid || want_coord)) scatter_features16(a.grid, a.ggrid, tri, hf, d_c, want_coord, gn);
+        if (want_coord) {                                            // uniform: the two halves of a sample add up in the lower one
+            if (hf == 1) {
+                part[grp][0][r] = gn[0]; part[grp][1][r] = gn[1]; part[grp][2][r] = gn[2];
+                part[grp][3][r] = gp0; part[grp][4][r] = gp1; part[grp][5][r] = gp2;
+            }
+            tc::named_bar_sync(3 + grp, 256);
+            if (hf == 0 && valid && any) {
+                gn[0] += part[grp][0][r]; gn[1] += part[grp][1][r]; gn[2] += part[grp][2][r];
+                gp0 += part[grp][3][r]; gp1 += part[grp][4][r]; gp2 += part[grp][5][r];
                 a.dp[3 * s + 0] += gn[0] * (float)(2.0 / (a.bound.b[0][1] - a.bound.b[0][0])) + gp0;
                 a.dp[3 * s + 1] += gn[1] * (float)(2.0 / (a.bound.b[1][1] - a.bound.b[1][0])) + gp1;
                 a.dp[3 * s + 2] += gn[2] * (float)(2.0 / (a.bound.b[2][1] - a.bound.b[2][0])) + gp2;
@@ -288,7 +294,7 @@ int launch_decoder_dh_tc(const DecArgs& a, cudaStream_t st) {
     if (rc) return rc;
     const int64_t tiles = (a.n + 127) / 128;
     const int blocks = grid_for(tiles, 2, num_sms());
-    DFP_TIMED("k_decoder_dh_tc", st, k_decoder_dh_tc<DEC, MODE><<<blocks, 256, smem, st>>>(a));
+    DFP_TIMED("k_decoder_dh_tc", st, k_decoder_dh_tc<DEC, MODE><<<blocks, 512, smem, st>>>(a));
     DFP_LAUNCH_CHECK("k_decoder_dh_tc");
     return DFP_OK;
 }

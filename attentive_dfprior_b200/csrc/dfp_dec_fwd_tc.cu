@@ -67,8 +67,11 @@ __device__ __forceinline__ void stage_weights_tc(float* sm, const float* __restr
     if (threadIdx.x < 4) sm[T::S_BO + threadIdx.x] = P[L::BO + threadIdx.x];
 }
 
+// Two threads per sample: thread (row r, half hf) owns columns 16*hf..16*hf+15 of every 32-wide block of sample r
+// (both halves sit in warps with the same warp%4, i.e. the same TMEM lane quarter).  That doubles the warps per SM at
+// the same TMEM budget; the single-thread-per-sample version of this kernel ran at ~30 % issue utilisation with 8 warps.
 template <int DEC, int MODE>
-__global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 1) k_decoder_fwd_tc(const DecArgs a) {
+__global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 1) k_decoder_fwd_tc(const DecArgs a) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
     constexpr int NOUT = (DEC == 2) ? 4 : 1;
     using PT = typename PtT<MODE>::T;
@@ -77,9 +80,11 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
     float* sm = reinterpret_cast<float*>(smem_raw);
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float part[2][4][128];                                  // output-layer partial sums of the upper halves
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int grp = tid >> 7, gt = tid & 127;                        // group and row within the group's tile
+    const int grp = tid >> 8, gt = tid & 255;                         // group, thread within the group
+    const int r = gt & 127, hf = gt >> 7;                             // sample row of the tile, column half
     stage_weights_tc<CD>(sm, a.params + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR)));
     if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
     if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_mbar_init(); }
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
     tc::fence_after_sync();
 
     const uint32_t tb = tmem_base_s + (uint32_t)(grp * T::T_COLS);                 // this group's columns, lane 0
-    const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16);                  // ... at this warp's lanes
+    const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16) + 16u * hf;       // ... this warp's lanes, this half's columns
     uint64_t* bar = &bars[grp];
     uint32_t parity = 0;
     const uint32_t bhi = tc::smem_u32(sm), blo = tc::smem_u32(sm + T::BSIZE);
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
     const float bmax = embed_bmax(sm + T::S_B);
 
     for (int64_t tile = (int64_t)blockIdx.x * T::GROUPS + grp; tile < tiles; tile += (int64_t)gridDim.x * T::GROUPS) {
-        const int64_t i_raw = tile * 128 + gt;
+        const int64_t i_raw = tile * 128 + r;
         const bool valid = i_raw < nitems;
         const int64_t ia = valid ? i_raw : nitems - 1;               // position in the (optional) list: index of saved activations
         const int64_t s = dec_sample(a, ia);                         // sample id: index of points and outputs
@@ -110,47 +115,47 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
         normalize(p, box, xn);
         const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
         const bool fast = embed_fast_ok(pf, bmax);
-        {   // trilinear features -> A_C
-            float c[32];
-            gather_features(a.grid, tri_setup(xn, a.grid.W, a.grid.H, a.grid.D), c);
-            tc::tmem_store_split32(tl + T::T_C_HI, tl + T::T_C_LO, c);
+        {   // trilinear features (this half's 16 channels) -> A_C
+            float c[16];
+            gather_features16(a.grid, tri_setup(xn, a.grid.W, a.grid.H, a.grid.D), hf, c);
+            tc::tmem_store_split16(tl + T::T_C_HI, tl + T::T_C_LO, c);
             if (a.act_c && valid) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) a.act_c[tm_index(ia, k, CD)] = c[k];
+                for (int k = 0; k < 16; ++k) a.act_c[tm_index(ia, 16 * hf + k, CD)] = c[k];
             }
             if (DEC == 1) {
-                gather_features(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), c);
-                tc::tmem_store_split32(tl + T::T_C_HI + 32, tl + T::T_C_LO + 32, c);
+                gather_features16(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), hf, c);
+                tc::tmem_store_split16(tl + T::T_C_HI + 32, tl + T::T_C_LO + 32, c);
                 if (a.act_c && valid) {
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) a.act_c[tm_index(ia, 32 + k, CD)] = c[k];
+                    for (int k = 0; k < 16; ++k) a.act_c[tm_index(ia, 32 + 16 * hf + k, CD)] = c[k];
                 }
             }
         }
-        // Fourier embedding in three 32-wide K chunks, each accumulated into D03 = [z0 | skip part of z3]
+        // Fourier embedding in three 32-wide K chunks (16 per thread), each accumulated into D03 = [z0 | skip part of z3]
 #pragma unroll 1
         for (int ch = 0; ch < 3; ++ch) {
-            float e[32];
+            float e[16];
             if (fast) {                                   // branch hoisted: one copy of each path keeps the kernel inside the I-cache
 #pragma unroll
-                for (int kk = 0; kk < 32; ++kk) {
-                    const int k = ch * 32 + kk;
+                for (int kk = 0; kk < 16; ++kk) {
+                    const int k = ch * 32 + 16 * hf + kk;
                     e[kk] = (k < EMB) ? sin_cw(embed_arg(sm + T::S_B, pf, k)) : 0.f;
                 }
             } else {
 #pragma unroll 1
-                for (int kk = 0; kk < 32; ++kk) {
-                    const int k = ch * 32 + kk;
+                for (int kk = 0; kk < 16; ++kk) {
+                    const int k = ch * 32 + 16 * hf + kk;
                     const float v = (k < EMB) ? sinf(embed_arg(sm + T::S_B, pf, k)) : 0.f;
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) if (u == kk) e[u] = v;
+                    for (int u = 0; u < 16; ++u) if (u == kk) e[u] = v;
                 }
             }
             if (ch > 0) { tc::mbar_wait(bar, parity); parity ^= 1; tc::fence_after_sync(); }   // previous chunk consumed A_X
-            tc::tmem_store_split32(tl + T::T_X_HI, tl + T::T_X_LO, e);
+            tc::tmem_store_split16(tl + T::T_X_HI, tl + T::T_X_LO, e);
             tc::wait_st();
             tc::fence_before_sync();
-            tc::named_bar_sync(1 + grp, 128);
+            tc::named_bar_sync(1 + grp, 256);
             if (issuer) {
                 tc::fence_after_sync();
                 const uint32_t koff = (uint32_t)ch * 8u * (64u * 16u);             // 8 K-chunks of 16 B per 32 k, LBO = N*16
@@ -163,31 +168,31 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
         }
         tc::mbar_wait(bar, parity); parity ^= 1;
         tc::fence_after_sync();
-        float h[32];
+        float h[16];
         {
-            float z[32], f[32];
-            tc::tmem_ld32(tl + T::T_D03, z);
-            tc::tmem_ld32(tl + T::T_DC, f);
+            float z[16], f[16];
+            tc::tmem_ld16(tl + T::T_D03, z);
+            tc::tmem_ld16(tl + T::T_DC, f);
             tc::wait_ld();
             uint32_t m = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float pre = z[j] + sm[T::S_BP + j];
+            for (int j = 0; j < 16; ++j) {
+                const float pre = z[j] + sm[T::S_BP + 16 * hf + j];
                 m |= (pre > 0.f ? 1u : 0u) << j;
-                h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + j]);
+                h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + 16 * hf + j]);
             }
             if (a.act_h && valid) {                                   // kept for the backward (DFP_FLAG_SAVE_ACT)
-                a.act_m[tm_index(ia, 0, 5)] = m;
+                reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, 0, 5))[hf] = (uint16_t)m;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a.act_h[tm_index(ia, j, 160)] = h[j];
+                for (int j = 0; j < 16; ++j) a.act_h[tm_index(ia, 16 * hf + j, 160)] = h[j];
             }
         }
 #pragma unroll 1
         for (int i = 1; i < 5; ++i) {
-            tc::tmem_store_split32(tl + T::T_X_HI, tl + T::T_X_LO, h);
+            tc::tmem_store_split16(tl + T::T_X_HI, tl + T::T_X_LO, h);
             tc::wait_st();
             tc::fence_before_sync();
-            tc::named_bar_sync(1 + grp, 128);
+            tc::named_bar_sync(1 + grp, 256);
             if (issuer) {
                 tc::fence_after_sync();
                 tc::mma_3xtf32(tb + T::T_DH, tb + T::T_X_HI, tb + T::T_X_LO, bhi + (T::WH + (i - 1) * 1024) * 4,
@@ -198,40 +203,48 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 128, 
             }
             tc::mbar_wait(bar, parity); parity ^= 1;
             tc::fence_after_sync();
-            float z[32], f[32];
-            tc::tmem_ld32(tl + T::T_DH, z);
-            tc::tmem_ld32(tl + T::T_DC, f);
+            float z[16], f[16];
+            tc::tmem_ld16(tl + T::T_DH, z);
+            tc::tmem_ld16(tl + T::T_DC, f);
             if (i == 3) {
-                float z3[32];
-                tc::tmem_ld32(tl + T::T_D03 + 32, z3);
+                float z3[16];
+                tc::tmem_ld16(tl + T::T_D03 + 32, z3);
                 tc::wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) z[j] += z3[j];
+                for (int j = 0; j < 16; ++j) z[j] += z3[j];
             } else {
                 tc::wait_ld();
             }
             uint32_t m = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float pre = z[j] + sm[T::S_BP + i * 32 + j];
+            for (int j = 0; j < 16; ++j) {
+                const float pre = z[j] + sm[T::S_BP + i * 32 + 16 * hf + j];
                 m |= (pre > 0.f ? 1u : 0u) << j;
-                h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + i * 32 + j]);
+                h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + i * 32 + 16 * hf + j]);
             }
             if (a.act_h && valid) {
-                a.act_m[tm_index(ia, i, 5)] = m;
+                reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, i, 5))[hf] = (uint16_t)m;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a.act_h[tm_index(ia, i * 32 + j, 160)] = h[j];
+                for (int j = 0; j < 16; ++j) a.act_h[tm_index(ia, i * 32 + 16 * hf + j, 160)] = h[j];
             }
         }
+        // output layer: each half sums its 16 inputs, the lower half adds the upper half's partial and the bias
         float out[NOUT];
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) {
-            float acc = sm[T::S_BO + o];
+            float acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc = fmaf(sm[T::S_WO + o * 32 + j], h[j], acc);
+            for (int j = 0; j < 16; ++j) acc = fmaf(sm[T::S_WO + o * 32 + 16 * hf + j], h[j], acc);
             out[o] = acc;
         }
-        if (valid) {
+        if (hf == 1) {
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) part[grp][o][r] = out[o];
+        }
+        tc::named_bar_sync(1 + grp, 256);
+        if (hf == 0 && valid) {
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) out[o] += part[grp][o][r] + sm[T::S_BO + o];
             if (NOUT == 1) a.out[s] = out[0];
             else *reinterpret_cast<float4*>(a.out + 4 * s) = make_float4(out[0], out[NOUT > 1 ? 1 : 0], out[NOUT > 2 ? 2 : 0], out[NOUT > 3 ? 3 : 0]);
         }
@@ -250,7 +263,7 @@ int launch_decoder_fwd_tc(const DecArgs& a, cudaStream_t st) {
     if (rc) return rc;
     const int64_t tiles = (a.n + 127) / 128;
     const int blocks = grid_for(tiles, T::GROUPS, num_sms());
-    DFP_TIMED("k_decoder_fwd_tc", st, k_decoder_fwd_tc<DEC, MODE><<<blocks, T::GROUPS * 128, smem, st>>>(a));
+    DFP_TIMED("k_decoder_fwd_tc", st, k_decoder_fwd_tc<DEC, MODE><<<blocks, T::GROUPS * 256, smem, st>>>(a));
     DFP_LAUNCH_CHECK("k_decoder_fwd_tc");
     return DFP_OK;
 }

@@ -142,6 +142,39 @@ __device__ __forceinline__ void gather_features(const DfpGrid& g, const Tri& t, 
     for (int j = 0; j < CDIM; ++j) c[j] = acc[j];
 }
 
+// 16-channel half (channels 16*hf .. 16*hf+15) of gather_features, for kernels with two threads per sample
+__device__ __forceinline__ void gather_features16(const DfpGrid& g, const Tri& t, int hf, float (&c)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) c[j] = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const float4* src[4];
+        float wgt[4];
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int x, y, z;
+            const int cn = half * 4 + i;
+            ok[i] = tri_corner(t, cn, g.W, g.H, g.D, x, y, z);
+            wgt[i] = tri_weight(t, cn);
+            src[i] = reinterpret_cast<const float4*>(g.data + (ok[i] ? (((int64_t)z * g.H + y) * g.W + x) * CDIM : 0)) + 4 * hf;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = ok[i] ? __ldg(src[i] + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                c[4 * q + 0] = fmaf(v[i].x, wgt[i], c[4 * q + 0]);
+                c[4 * q + 1] = fmaf(v[i].y, wgt[i], c[4 * q + 1]);
+                c[4 * q + 2] = fmaf(v[i].z, wgt[i], c[4 * q + 2]);
+                c[4 * q + 3] = fmaf(v[i].w, wgt[i], c[4 * q + 3]);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -180,6 +213,78 @@ __device__ __forceinline__ void scatter_features(const DfpGrid& g, float* ggrid,
         }
     }
     gn[0] = gx * t.gx; gn[1] = gy * t.gy; gn[2] = gz * t.gz;
+}
+
+// 16-channel half of scatter_features: gn receives this half's partial coordinate gradient
+__device__ __forceinline__ void scatter_features16(const DfpGrid& g, float* ggrid, const Tri& t, int hf, const float (&dc)[16],
+                                                   bool want_coord, float gn[3]) {
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll 1
+    for (int cn = 0; cn < 8; ++cn) {
+        int x, y, z;
+        if (!tri_corner(t, cn, g.W, g.H, g.D, x, y, z)) continue;
+        const int64_t off = (((int64_t)z * g.H + y) * g.W + x) * CDIM + 16 * hf;
+        if (ggrid) {
+            const float wgt = tri_weight(t, cn);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                red_add_v4(ggrid + off + 4 * q, dc[4 * q] * wgt, dc[4 * q + 1] * wgt, dc[4 * q + 2] * wgt, dc[4 * q + 3] * wgt);
+        }
+        if (want_coord) {
+            const float4* src = reinterpret_cast<const float4*>(g.data + off);
+            float dot = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = __ldg(src + q);
+                dot = fmaf(v.x, dc[4 * q], dot); dot = fmaf(v.y, dc[4 * q + 1], dot);
+                dot = fmaf(v.z, dc[4 * q + 2], dot); dot = fmaf(v.w, dc[4 * q + 3], dot);
+            }
+            float dx, dy, dz;
+            tri_weight_grad(t, cn, dx, dy, dz);
+            gx = fmaf(dot, dx, gx); gy = fmaf(dot, dy, gy); gz = fmaf(dot, dz, gz);
+        }
+    }
+    gn[0] = gx * t.gx; gn[1] = gy * t.gy; gn[2] = gz * t.gz;
+}
+
+// Warp-aggregated variant of scatter_features16 (grid gradient only).  The lanes of a warp hold consecutive samples of a
+// ray, which often fall into the same grid cell (always for the 16 near-surface samples, and for most neighbours in the
+// coarse low grid); all rays also start in the camera's cell.  Runs of adjacent lanes in one cell are summed with a
+// segmented shuffle reduction and only the head lane of a run issues the vector reductions, which cuts the number of
+// atomics that serialise on hot voxels in L2.  Must be called by all 32 lanes; `active` masks lanes without a gradient.
+__device__ __forceinline__ void scatter_features16_agg(const DfpGrid& g, float* ggrid, const Tri& t, int hf, const float (&dc)[16],
+                                                       bool active) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int cell = active ? (t.z0 * g.H + t.y0) * g.W + t.x0 : -1 - lane;       // inactive lanes never merge
+    const int nxt = __shfl_down_sync(full, cell, 1);
+    const unsigned same = __ballot_sync(full, lane < 31 && nxt == cell);          // bit i: lanes i and i+1 share a cell
+    const int run = __ffs(~(same >> lane)) - 1;                                   // lanes after this one that continue its run
+    const bool head = active && (lane == 0 || !((same >> (lane - 1)) & 1u));
+    const int maxrun = __reduce_max_sync(full, run);
+#pragma unroll 1
+    for (int cn = 0; cn < 8; ++cn) {
+        int x, y, z;
+        const bool ok = tri_corner(t, cn, g.W, g.H, g.D, x, y, z);                 // a property of the cell: uniform over a run
+        const float wgt = (ok && active) ? tri_weight(t, cn) : 0.f;
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = dc[k] * wgt;
+#pragma unroll 1
+        for (int d = 1; d <= maxrun; d <<= 1) {                                    // segmented suffix sums within each run
+            const bool take = run >= d;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float o = __shfl_down_sync(full, v[k], d);
+                v[k] += take ? o : 0.f;
+            }
+        }
+        if (head && ok) {
+            float* dst = ggrid + (((int64_t)z * g.H + y) * g.W + x) * CDIM + 16 * hf;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+    }
 }
 
 __device__ __forceinline__ void load_weights_to_smem(float* dst, const float* __restrict__ src, int nfloats) {
