@@ -7,6 +7,8 @@ Public surface mirrors the reference's seam for this path:
 * ``Mesher``                    -- the dense point query of src/utils/Mesher.py (eval_points, get_grid_uniform, query loop)
 * ``functional``                -- the same operations as plain functions
 * ``dist``                      -- ray / voxel-block sharding across GPUs
+* ``mapper_ops``                -- the Mapper-side rows next to the path: masked-grid Adam, frustum mask, ray batch
+                                   assembly, loss (src/Mapper.py:90-158, 351-388, 408-482)
 
 All arithmetic runs in libdfprior_b200.so (hand-written CUDA behind a C ABI, include/dfprior_b200.h).
 There is no CPU fallback: importing is cheap, but any call raises if the library is not built.
@@ -16,6 +18,8 @@ from .decoder import DF, MLP, DenseLayer, GaussianFourierFeatureTransform, get_m
 from .mesher import Mesher  # noqa: F401
 from .renderer import Renderer  # noqa: F401
 from . import dist  # noqa: F401
+from . import mapper_ops  # noqa: F401
+from .mapper_ops import MaskedGridAdam  # noqa: F401
 
-__all__ = ["Renderer", "Mesher", "dist", "DF", "MLP", "mlp_tsdf", "DenseLayer", "GaussianFourierFeatureTransform", "get_model",
+__all__ = ["Renderer", "Mesher", "dist", "mapper_ops", "MaskedGridAdam", "DF", "MLP", "mlp_tsdf", "DenseLayer", "GaussianFourierFeatureTransform", "get_model",
            "functional", "common"]

@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfprior_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FLAG_SAVE_ACT = 1
 MAX_RAY_SAMPLES = 64
 N_PARAM_TENSORS = 79
@@ -69,6 +69,43 @@ class DfpPoints(C.Structure):
                 ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
+class DfpAdam(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("voxel_mask", C.c_void_p), ("n_vox", C.c_int64), ("C", C.c_int32), ("step", C.c_int32),
+                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double)]
+
+
+class DfpFrustum(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("w2c", C.c_float * 16), ("cam_o", C.c_float * 3),
+                ("xs", C.c_void_p), ("ys", C.c_void_p), ("zs", C.c_void_p),
+                ("Dg", C.c_int32), ("Hg", C.c_int32), ("Wg", C.c_int32)]
+
+
+class DfpFrame(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("color", C.c_void_p), ("c2w", C.c_float * 12)]
+
+
+class DfpRayBatch(C.Structure):
+    _fields_ = [("frames", C.POINTER(DfpFrame)), ("n_frames", C.c_int32), ("indices", C.c_void_p), ("n_per_frame", C.c_int32),
+                ("H0", C.c_int32), ("H1", C.c_int32), ("W0", C.c_int32), ("W1", C.c_int32), ("W", C.c_int32),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("bound", (C.c_double * 2) * 3), ("filter", C.c_int32)]
+
+
+class DfpRayBatchOut(C.Structure):
+    _fields_ = [("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("gt_depth", C.c_void_p), ("gt_color", C.c_void_p),
+                ("n_kept", C.c_void_p)]
+
+
+class DfpMapLoss(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("color", C.c_void_p), ("weight", C.c_void_p), ("gt_depth", C.c_void_p),
+                ("gt_color", C.c_void_p), ("n", C.c_int64), ("S", C.c_int32), ("w_color", C.c_double),
+                ("use_weight", C.c_int32), ("g_depth", C.c_void_p), ("g_color", C.c_void_p), ("g_weight", C.c_void_p),
+                ("loss", C.c_void_p)]
+
+
 # every symbol include/dfprior_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "dfp_abi_version": (C.c_int, []),
@@ -89,6 +126,12 @@ SYMBOLS = {
     "dfp_points_bwd": (C.c_int, [C.POINTER(DfpScene), C.c_void_p, C.POINTER(DfpPoints), C.c_int32, C.c_void_p,
                                  C.c_void_p, C.POINTER(DfpGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
     "dfp_tsdf_sample": (C.c_int, [C.POINTER(DfpScene), C.POINTER(DfpPoints), C.c_void_p, C.c_void_p]),
+    "dfp_masked_adam_step": (C.c_int, [C.POINTER(DfpAdam), C.c_void_p]),
+    "dfp_frustum_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "dfp_frustum_mask": (C.c_int, [C.POINTER(DfpFrustum), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dfp_assemble_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "dfp_assemble_rays": (C.c_int, [C.POINTER(DfpRayBatch), C.POINTER(DfpRayBatchOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dfp_mapper_loss": (C.c_int, [C.POINTER(DfpMapLoss), C.c_void_p]),
     "dfp_launch_count": (C.c_int64, []),
     "dfp_set_tensor_cores": (C.c_int, [C.c_int]),
     "dfp_set_tc_backward": (C.c_int, [C.c_int]),

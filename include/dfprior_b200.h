@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DFP_ABI_VERSION 2
+#define DFP_ABI_VERSION 3
 
 #define DFP_C_DIM 32            /* configs/df_prior.yaml:102 (model.c_dim) */
 #define DFP_HIDDEN 32           /* src/conv_onet/models/decoder.py:278 */
@@ -184,6 +184,96 @@ int dfp_points_bwd(const DfpScene* scene, const float* params_packed, const DfpP
 
 /* ---- Renderer.eval_points_tsdf / sample_grid_tsdf (Renderer.py:73-107) ---------------- */
 int dfp_tsdf_sample(const DfpScene* scene, const DfpPoints* pts, float* tsdf_out, void* stream);
+
+/* ---- Mapper-side rows --------------------------------------------
+ *
+ * (f1) Masked-grid optimiser step, src/Mapper.py:351-361 (val_grad = val[mask]), :374-378 (one Adam,
+ * per-group lr set per stage :392-398), :383-388 (val[mask] = val_grad), :472-482 (step, zero_grad,
+ * write-back).  One kernel updates the dense channels-last grid in place for the voxels of the mask:
+ * torch.optim.Adam's arithmetic (betas, eps, bias correction by `step`, no weight decay / amsgrad) on
+ * dense moment buffers; voxels outside the mask, their moments and their gradients are not touched.
+ * lr = 0 still advances the moments, as torch does.  voxel_mask NULL = every voxel (the
+ * frustum_feature_selection = False branch, Mapper.py:333-342). */
+typedef struct {
+    float* param;              /* [n_vox, C] grid values (NDHWC), updated in place */
+    const float* grad;         /* [n_vox, C] dense gradient from dfp_render_bwd */
+    float* exp_avg;            /* [n_vox, C] first moment  (zero-initialised by the caller) */
+    float* exp_avg_sq;         /* [n_vox, C] second moment */
+    const uint8_t* voxel_mask; /* [n_vox] 0/1, or NULL */
+    int64_t n_vox;
+    int32_t C;                 /* multiple of 4 */
+    int32_t step;              /* 1-based Adam step of this parameter */
+    double lr, beta1, beta2, eps;
+} DfpAdam;
+int dfp_masked_adam_step(const DfpAdam* a, void* stream);
+
+/* (f3) Frustum feature selection, Mapper.get_mask_from_c2w (src/Mapper.py:90-158): project every grid
+ * vertex into the camera (w2c in f32 as numpy computes it, K in f64), bilinear depth look-up with
+ * cv2.remap's INTER_LINEAR arithmetic (1/32-pixel fixed-point coordinates, constant-0 border), fill
+ * zero depths with the maximum, depth test (-z <= depth + 0.5), or within 0.5 m of the camera centre.
+ * mask is written in the grid's voxel order [D,H,W] (what Mapper.py:347-348 permutes to). */
+typedef struct {
+    const float* depth;        /* [H, W] f32 depth image (device) */
+    int32_t H, W;
+    double fx, fy, cx, cy;
+    float w2c[16];             /* row-major inverse pose, f32 (np.linalg.inv of the f32 c2w, computed by the caller) */
+    float cam_o[3];            /* c2w[:3, 3] */
+    const float* xs;           /* [Wg] torch.linspace(bound[0][0], bound[0][1], Wg) (device, f32) */
+    const float* ys;           /* [Hg] */
+    const float* zs;           /* [Dg] */
+    int32_t Dg, Hg, Wg;        /* grid shape val.shape[2:] = (D, H, W) */
+} DfpFrustum;
+/* scratch: n_vox f32 (sampled depths) + n_vox f64 (-z) + n_vox u8 (in-image flag) + 4 bytes (max): use
+ * dfp_frustum_scratch_bytes */
+size_t dfp_frustum_scratch_bytes(int32_t Dg, int32_t Hg, int32_t Wg);
+int dfp_frustum_mask(const DfpFrustum* f, uint8_t* mask, void* scratch, size_t scratch_bytes, void* stream);
+
+/* (f2) Ray batch assembly + loss, src/Mapper.py:414-449 (get_samples per frame, bbox pre-filter) and
+ * :457-469 (loss); src/common.py:76-136.  The random pixel pick stays torch.randint on the caller's side
+ * (same generator stream as the reference); everything downstream of the indices is fused:
+ * dfp_assemble_rays gathers depth/colour, builds rays (get_rays_from_uv, common.py:76-91), applies the
+ * bounding-box filter and compacts the survivors in order (what the boolean indexing of Mapper.py:446-449
+ * yields); n_kept is written to device memory. */
+typedef struct {
+    const float* depth;        /* [H, W] */
+    const float* color;        /* [H, W, 3] */
+    float c2w[12];             /* rows 0..2 of the pose, f32 */
+} DfpFrame;
+typedef struct {
+    const DfpFrame* frames;    /* HOST array [n_frames] (copied into the launch arguments; at most 16 per call) */
+    int32_t n_frames;
+    const int64_t* indices;    /* [n_frames, n_per_frame] flat pixel indices into the H0..H1 x W0..W1 window (device) */
+    int32_t n_per_frame;
+    int32_t H0, H1, W0, W1;    /* sampling window (Mapper: whole image; Tracker: edge-cropped) */
+    int32_t W;                 /* image width (row stride of depth / colour) */
+    double fx, fy, cx, cy;
+    double bound[3][2];
+    int32_t filter;            /* 1: drop rays whose depth lies beyond the scene box (Mapper.py:439-449) */
+} DfpRayBatch;
+typedef struct {
+    float* rays_o;             /* [n, 3] capacity n_frames * n_per_frame */
+    float* rays_d;             /* [n, 3] */
+    float* gt_depth;           /* [n] */
+    float* gt_color;           /* [n, 3] */
+    int32_t* n_kept;           /* [1] device */
+} DfpRayBatchOut;
+size_t dfp_assemble_scratch_bytes(int64_t n_total);
+int dfp_assemble_rays(const DfpRayBatch* b, const DfpRayBatchOut* out, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Mapper loss (Mapper.py:457-469) and its gradient in one pass: loss = sum_{gt>0} |gt - depth|
+ * (+ sum |weight - 1| when w_weight != 0) (+ w_color * sum |gt_color - color| when color != NULL);
+ * writes d(loss)/d(depth) f64 [n], d/d(color) f32 [n,3], d/d(weight) f32 [n*S] (each optional) and
+ * accumulates the loss (f64) into *loss, which the caller zeroes. */
+typedef struct {
+    const double* depth; const float* color; const float* weight;      /* renderer outputs */
+    const float* gt_depth; const float* gt_color;
+    int64_t n; int32_t S;
+    double w_color;            /* 0 = no colour term */
+    int32_t use_weight;        /* 1 = add sum |weight - 1| */
+    double* g_depth; float* g_color; float* g_weight;
+    double* loss;
+} DfpMapLoss;
+int dfp_mapper_loss(const DfpMapLoss* l, void* stream);
 
 /* ---- diagnostics (used by bench.py; not part of the reference seam) ---------------------
  * dfp_launch_count: kernels launched by this library since load.  dfp_timing_enable(1) makes

@@ -33,4 +33,6 @@ def load_golden(name):
     return fx
 
 
-GOLDEN_CASES = sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith(".pt")) if os.path.isdir(GOLDEN_DIR) else []
+# render fixtures (map_*/track_*); mapper_rows.pt belongs to the Mapper-side rows (tests/test_mapper_oracle.py)
+GOLDEN_CASES = sorted(f[:-3] for f in os.listdir(GOLDEN_DIR)
+                      if f.endswith(".pt") and f.startswith(("map_", "track_"))) if os.path.isdir(GOLDEN_DIR) else []
