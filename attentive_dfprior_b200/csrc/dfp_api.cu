@@ -584,6 +584,11 @@ int dfp_probe_tc(float* D, int32_t N, int32_t b_mn, int32_t lbo, int32_t sbo, in
     if (!D) return fail(DFP_ERR_INVALID, "null argument");
     return launch_tc_probe(D, N, b_mn, lbo, sbo, k_hot, layout_type, start_off, (cudaStream_t)stream);
 }
+int dfp_probe_bf16(const float* A, const float* B, float* D, int32_t N, int32_t fmt, int32_t layout_type, int32_t lbo_a, int32_t lbo_b,
+                   int32_t sbo, int32_t kstep_a, int32_t kstep_b, void* stream) {
+    if (!A || !B || !D) return fail(DFP_ERR_INVALID, "null argument");
+    return launch_tc_probe_bf16(A, B, D, N, fmt, layout_type, lbo_a, lbo_b, sbo, kstep_a, kstep_b, (cudaStream_t)stream);
+}
 
 int dfp_set_tensor_cores(int on) {
     g_tc.store(on ? 1 : 0);

@@ -9,7 +9,11 @@ __global__ void __launch_bounds__(NT) k_attn_fwd(const AttArgs a) {
     load_weights_to_smem(A, a.params + OFF_ATT, AttOff::SIZE);
     __syncthreads();
     const int count = *a.band_count;
-    for (int i = blockIdx.x * NT + threadIdx.x; i < count; i += gridDim.x * NT) {
+    // 32-sample chunks are dealt round-robin over the CTAs first and their warps second, so that a short band list
+    // (the Mapper's 1000-ray batches) runs one warp on every SM instead of eight warps on a few
+    for (int chunk = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; chunk * 32 < count; chunk += WARPS * gridDim.x) {
+        const int i = chunk * 32 + (threadIdx.x & 31);
+        if (i >= count) continue;
         const int s = a.band_list[i];
         const float x0 = a.high[s] + a.low[s];                         // decoder.py:326,343
         const float x1 = tsdf_logit(a.tsdf[s]).inv;
@@ -35,8 +39,8 @@ __global__ void __launch_bounds__(NT) k_attn_bwd(const AttArgs a) {
     __syncthreads();
     const int count = *a.band_count;
     const BoxT<PT> tbox = make_box<PT>(a.tsdf_bnds.b);
-    for (int base = blockIdx.x * NT; base < count; base += gridDim.x * NT) {
-        const int i = base + threadIdx.x;
+    for (int chunk = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; chunk * 32 < count; chunk += WARPS * gridDim.x) {     // as in k_attn_fwd
+        const int i = chunk * 32 + (threadIdx.x & 31);
         const bool valid = i < count;
         const int s = a.band_list[valid ? i : count - 1];
         const float g_out = valid ? a.d_fused[s] : 0.f;

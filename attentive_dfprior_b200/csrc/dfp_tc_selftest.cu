@@ -3,6 +3,7 @@
 // back from TMEM.  tests/test_gpu_tc.py compares it with an f64 matmul.
 #include "dfp_device.cuh"
 #include "dfp_tc.cuh"
+#include <cuda_bf16.h>
 
 namespace dfp {
 
@@ -271,6 +272,81 @@ __global__ void __launch_bounds__(128) k_tc_probe_m64(float* __restrict__ D, int
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tbase, 32);
+}
+
+// bf16 MN-major operand probe: D[64 x N] = A^T * B over 128 samples with both operands row-per-sample (MN contiguous) in
+// shared memory under a candidate layout `fmt` (0: no-swizzle interleaved core matrices, 1: 64-byte rows + SWIZZLE_64B,
+// 2: 128-byte rows + SWIZZLE_128B); descriptor fields are passed in so one build can try several readings of LBO/SBO.
+__device__ __forceinline__ uint32_t bf16_off(int fmt, int k, int mn, int MN) {
+    if (fmt == 0) return (uint32_t)((k >> 3) * ((MN >> 3) * 128) + (mn >> 3) * 128 + (k & 7) * 16 + (mn & 7) * 2);
+    if (fmt == 1) return (uint32_t)((mn >> 5) * 8192 + k * 64 + ((((mn & 31) >> 3) ^ ((k >> 1) & 3)) << 4) + (mn & 7) * 2);
+    return (uint32_t)((mn >> 6) * 16384 + k * 128 + ((((mn & 63) >> 3) ^ (k & 7)) << 4) + (mn & 7) * 2);
+}
+__global__ void __launch_bounds__(128) k_tc_probe_bf16(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D,
+                                                       int N, int fmt, int layout_type, int lbo_a, int lbo_b, int sbo, int kstep_a, int kstep_b) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* sa = sm;                 // A: 128 samples x 64 features bf16 (16 KB)
+    unsigned char* sb = sm + 32768;         // B: 128 x N (<= 128) bf16
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+    __syncthreads();
+    for (int f = 0; f < 64; ++f) *reinterpret_cast<__nv_bfloat16*>(sa + bf16_off(fmt, tid, f, 64)) = __float2bfloat16_rn(A[tid * 64 + f]);
+    for (int j = 0; j < N; ++j) *reinterpret_cast<__nv_bfloat16*>(sb + bf16_off(fmt, tid, j, N)) = __float2bfloat16_rn(B[tid * N + j]);
+    if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 128); tc::tmem_relinquish(); }
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < 128; c0 += 8) { uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; tc::tmem_st8(lane_base + c0, z); }
+    tc::wait_st();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((64u >> 4) << 24);
+        for (int ks = 0; ks < 8; ++ks) {
+            auto desc = [&](uint32_t addr, uint32_t lbo) {
+                return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(((uint32_t)sbo >> 4) & 0x3FFF) << 32) |
+                       (1ull << 46) | ((uint64_t)(layout_type & 7) << 61);
+            };
+            const uint64_t da = desc(tc::smem_u32(sa) + ks * kstep_a, (uint32_t)lbo_a), db = desc(tc::smem_u32(sb) + ks * kstep_b, (uint32_t)lbo_b);
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+                ::"r"(tbase), "l"(da), "l"(db), "r"(idesc), "r"(ks > 0 ? 1u : 0u), "r"(0), "r"(0), "r"(0), "r"(0)
+                : "memory");
+        }
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[8];
+        tc::tmem_ld8(lane_base + c0, v);
+        tc::wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) D[tid * N + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 128);
+}
+int launch_tc_probe_bf16(const float* A, const float* B, float* D, int N, int fmt, int layout_type, int lbo_a, int lbo_b, int sbo,
+                         int kstep_a, int kstep_b, cudaStream_t st) {
+    if (N < 16 || N > 128 || N % 16) return fail(DFP_ERR_INVALID, "bad probe shape");
+    const size_t smem = 65536 + 1024;
+    int rc = set_smem(k_tc_probe_bf16, smem);
+    if (rc) return rc;
+    DFP_TIMED("k_tc_probe_bf16", st, k_tc_probe_bf16<<<1, 128, smem, st>>>(A, B, D, N, fmt, layout_type, lbo_a, lbo_b, sbo, kstep_a, kstep_b));
+    DFP_LAUNCH_CHECK("k_tc_probe_bf16");
+    return DFP_OK;
 }
 
 int launch_tc_probe(float* D, int N, int b_mn, int lbo, int sbo, int k_hot, int layout_type, int start_off, cudaStream_t st) {

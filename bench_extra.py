@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Secondary workloads of BASELINE.json (configs 3-5) on one GPU (or sharded with torchrun): tracker step,
-full-frame render_img, Mesher dense occupancy query.  One JSON line per workload (rank 0).
+"""Secondary workloads of BASELINE.json (configs 2-5) on one GPU (or sharded with torchrun): tracker step, the Mapper
+iteration with its surrounding rows, full-frame render_img, Mesher dense occupancy query.  One JSON line per workload (rank 0).
 Not the driver's contract bench (that is bench.py); results are kept under profiles/."""
 from __future__ import annotations
 
@@ -78,6 +78,87 @@ def main():
             loss.backward()
         ms = timeit(tracker_step, 3, 9)
         out.append({"workload": "tracker_step", "rays": n, "stage": "color", "ms_per_step": ms, "rays_per_s": n / ms * 1e3})
+
+    # ---- config 2 as the Mapper runs it (rank 0): frustum masks, then per iteration ray assembly -> render -> loss ->
+    #      backward -> masked-grid Adam, against the same iteration with the upstream torch flow
+    #      (index_put of val_grad, torch get_samples, torch.optim.Adam) around the same renderer
+    if rank == 0:
+        from attentive_dfprior_b200 import mapper_ops as M
+        import time
+        mdl = A.DF().to(dev)
+        H, W = cam["H"], cam["W"]
+        intr = (cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+        frames = []
+        for f in range(5):
+            pose = synth.make_pose(scene, f).to(dev)
+            frames.append((synth.make_depth_image(scene, pose, device=dev, seed=f), torch.rand(H, W, 3, device=dev), pose))
+        n_pix = 200
+        keys = ("grid_low", "grid_high", "grid_color")
+        t0 = time.perf_counter()
+        masks = {k: M.frustum_mask(frames[0][2], scene.bound, scene.grids[k].shape[2:], frames[0][0], H, W, *intr) for k in keys}
+        torch.cuda.synchronize()
+        ms_mask = timeit(lambda: [M.frustum_mask(frames[0][2], scene.bound, scene.grids[k].shape[2:], frames[0][0], H, W, *intr) for k in keys], 2, 5)
+        frac = {k: float(masks[k].float().mean()) for k in keys}
+        lrs = {"grid_low": 0.1, "grid_high": 0.005, "grid_color": 0.005}
+
+        grids_f = {k: scene.grids[k].detach().clone(memory_format=torch.preserve_format).requires_grad_(True) for k in keys}
+        opt_g = M.MaskedGridAdam(grids_f, masks)
+        opt_d = torch.optim.Adam(mdl.parameters(), lr=0.005, fused=True)
+
+        def fused_iter():
+            idx = torch.randint(H * W, (5, n_pix), device=dev)
+            ro, rd, gd, gc = M.assemble_rays(frames, idx, H, W, *intr, scene.bound)
+            d, u, c, w = renderer.render_batch_ray(grids_f, mdl, rd, ro, dev, scene.tsdf_volume, scene.tsdf_bnds, "color", gt_depth=gd)
+            loss = M.mapper_loss(d, c, w, gd, gc, 0.2, False, True)
+            loss.backward()
+            opt_g.step(lrs)
+            opt_d.step(); opt_d.zero_grad()
+        ms_fused = timeit(fused_iter, 5, 15)
+
+        # upstream flow of the rows (Mapper.py:351-361, 383-388, 414-449, 457-482) in torch on the same device
+        vals = {k: scene.grids[k].detach().clone(memory_format=torch.preserve_format) for k in keys}
+        bmask = {k: masks[k].bool()[None, None].expand(vals[k].shape) for k in keys}
+        vgrad = {k: vals[k][bmask[k]].clone().requires_grad_(True) for k in keys}
+        opt_t = torch.optim.Adam([{"params": list(mdl.parameters()), "lr": 0.005}] + [{"params": [vgrad[k]], "lr": lrs[k]} for k in keys])
+        bound_d = scene.bound.to(dev)
+
+        def torch_iter():
+            c = {}
+            for k in keys:
+                v = vals[k]
+                v[bmask[k]] = vgrad[k]
+                c[k] = v
+            ros, rds, gds, gcs = [], [], [], []
+            for depth, color, pose in frames:
+                o, dd, gdep, gcol = A.common.get_samples(0, H, 0, W, n_pix, H, W, *intr, pose, depth, color, dev)
+                ros.append(o.float()); rds.append(dd.float()); gds.append(gdep.float()); gcs.append(gcol.float())
+            ro, rd, gd, gc = torch.cat(ros), torch.cat(rds), torch.cat(gds), torch.cat(gcs)
+            with torch.no_grad():
+                t = (bound_d.unsqueeze(0) - ro.unsqueeze(-1)) / rd.unsqueeze(-1)
+                t, _ = torch.min(torch.max(t, dim=2)[0], dim=1)
+                inside = t >= gd
+            ro, rd, gd, gc = ro[inside], rd[inside], gd[inside], gc[inside]
+            d, u, col, w = renderer.render_batch_ray(c, mdl, rd, ro, dev, scene.tsdf_volume, scene.tsdf_bnds, "color", gt_depth=gd)
+            dm = gd > 0
+            loss = torch.abs(gd[dm] - d[dm]).sum() + 0.2 * torch.abs(gc - col).sum()
+            loss.backward()
+            opt_t.step(); opt_t.zero_grad()
+            for k in keys:
+                v = vals[k].detach()
+                v[bmask[k]] = vgrad[k].clone().detach()
+                vals[k] = v
+        ms_torch = timeit(torch_iter, 5, 15)
+
+        # the Adam kernel alone on the colour grid: 7 float streams over the masked voxels + the mask bytes
+        gk = grids_f["grid_color"]
+        gbuf = torch.randn_like(gk)
+        ms_adam = timeit(lambda: opt_g.step({"grid_color": 0.005}, grads={"grid_color": gbuf}), 3, 9)
+        nvox = gk.shape[2] * gk.shape[3] * gk.shape[4]
+        adam_bytes = frac["grid_color"] * nvox * 32 * 4 * 7 + nvox
+        out.append({"workload": "mapper_iteration_5x200px_color", "ms_fused_rows": ms_fused, "ms_torch_rows": ms_torch,
+                    "frustum_masks_3grids_ms": ms_mask, "mask_fraction": frac,
+                    "masked_adam_color_grid_ms": ms_adam, "masked_adam_GBps": adam_bytes / ms_adam / 1e6})
+        del grids_f, vals, vgrad, opt_g, opt_t, bmask
 
     # ---- config 4: full-frame render_img 1200x680, chunk-sharded across ranks
     gt_img = synth.make_depth_image(scene, c2w, device=dev, seed=1)
