@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "dfp_device.cuh"
+#include "dfp_planes.cuh"
 
 namespace dfp {
 
@@ -136,14 +137,15 @@ static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with
     const int64_t nsp = (ns + 127) / 128 * 128;          // tile-major arrays cover whole 128-sample tiles
     for (int d = 0; d < 3; ++d) {
         const bool used = act && (d == 0 || (d == 1 && stage >= DFP_STAGE_HIGH) || (d == 2 && stage == DFP_STAGE_COLOR));
-        w.act_h[d] = (float*)take(used ? nsp * 160 * 4 : 0);
+        w.act_h[d] = (float*)take(used ? pl::array_bytes(nsp, pl::F_H) : 0);
         w.act_m[d] = (uint32_t*)take(used ? nsp * 5 * 4 : 0);
-        w.act_c[d] = (float*)take(used ? nsp * (d == 1 ? 64 : 32) * 4 : 0);
+        w.act_c[d] = (float*)take(used ? pl::array_bytes(nsp, pl::f_cx(d == 1 ? 64 : 32)) : 0);
         if (!used) { w.act_h[d] = nullptr; w.act_m[d] = nullptr; w.act_c[d] = nullptr; }
     }
-    w.sc_e = (float*)take(act ? nsp * 96 * 4 : 0);
-    w.sc_dh = (float*)take(act ? nsp * 160 * 4 : 0);
-    w.sc_darg = (float*)take(act ? nsp * 96 * 4 : 0);
+    w.sc_e = (float*)take(act ? pl::array_bytes(nsp, pl::F_EX) : 0);
+    w.sc_dh = (float*)take(act ? pl::array_bytes(nsp, pl::F_DH) : 0);
+    w.sc_darg = (float*)take(act ? pl::array_bytes(nsp, pl::F_DL0) : 0);
+    w.sc_dl1 = (float*)take(act ? pl::array_bytes(nsp, pl::F_DL1) : 0);
     return off;
 }
 
@@ -524,7 +526,7 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
     da.gparams = g->params_packed; da.dp = want_dp ? w.dp : nullptr;
     // tensor-core backward (needs the activations saved by the tensor-core forward): K1 = delta chain, K2 = weight grads
     const bool tcb = use_tensor_cores() && (flags & DFP_FLAG_SAVE_ACT) && w.act_h[0] != nullptr && tc_backward_level() > 0;
-    da.sc_e = w.sc_e; da.sc_dh = w.sc_dh; da.sc_darg = w.sc_darg;
+    da.sc_e = w.sc_e; da.sc_dh = w.sc_dh; da.sc_darg = w.sc_darg; da.sc_dl1 = w.sc_dl1;
     auto run = [&](auto dec_tag) -> int {
         constexpr int DEC = decltype(dec_tag)::value;
         if (!tcb) return launch_decoder_bwd<DEC, MODE>(da, st);

@@ -9,6 +9,7 @@
 // the dense grid gradient (vector reductions), d(point) for the Tracker, and -- for kernel 2 (dfp_dec_dw_tc.cu) --
 // the per-block deltas, sin(arg) and d(arg) in the feature-major scratch arrays.
 #include "dfp_device.cuh"
+#include "dfp_planes.cuh"
 #include "dfp_tc.cuh"
 
 namespace dfp {
@@ -149,9 +150,10 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             float dacc[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) dacc[j] = ((m >> j) & 1u) ? dh[j] : 0.f;
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) a.sc_dh[tm_index(ia, i * 32 + c0 + j, 160)] = dh[j];
+            if (a.gparams) {                                  // operands of kernel 2 (rows past the end carry zero deltas)
+                pl::store16(reinterpret_cast<unsigned char*>(a.sc_dh), pl::F_DH, i_raw, i * 32 + c0, dh);
+                pl::store16(reinterpret_cast<unsigned char*>(a.sc_darg), pl::F_DL0, i_raw, 8 + pl::dl0_pos(i) * 32 + c0, dacc);
+                if (i == 3) pl::store16(reinterpret_cast<unsigned char*>(a.sc_dl1), pl::F_DL1, i_raw, c0, dacc);
             }
             tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 32, dh);            // for d_c += dh_i * Wc_i
             tc::tmem_store_split16(tl + T::T_A + 64, tl + T::T_A + 96, dacc);     // for dh_{i-1} = dacc_i * W_i
@@ -177,10 +179,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
         }
         // block 0: fc_c[0] path, then the embedding
         {
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) a.sc_dh[tm_index(ia, c0 + j, 160)] = dh[j];
-            }
+            if (a.gparams) pl::store16(reinterpret_cast<unsigned char*>(a.sc_dh), pl::F_DH, i_raw, c0, dh);
             tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 32, dh);
             tc::wait_st();
             tc::fence_before_sync();
@@ -193,6 +192,17 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             const uint32_t m0 = m_next >> c0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) dh[j] = ((m0 >> j) & 1u) ? dh[j] : 0.f;      // dacc_0
+            if (a.gparams) {
+                pl::store16(reinterpret_cast<unsigned char*>(a.sc_dl1), pl::F_DL1, i_raw, 32 + c0, dh);
+                if (hf == 0) {                                // upstream gradient, padded to 8 columns
+                    float d8[8];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) d8[o] = 0.f;
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) d8[o] = dout[o];
+                    pl::store8(reinterpret_cast<unsigned char*>(a.sc_darg), pl::F_DL0, i_raw, 0, d8);
+                }
+            }
             tc::mbar_wait(bar, parity); parity ^= 1;
             tc::fence_after_sync();
             // A = [dacc_0 | dacc_3]: hi in columns 0..63, lo in 64..127
@@ -252,13 +262,14 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                     gp2 = fmaf(sm[T::S_B + 2 * EMB_PAD + k], da[kk], gp2);
                 }
             }
-            if (valid && a.gparams) {
-#pragma unroll
-                for (int kk = 0; kk < 16; ++kk) {
-                    a.sc_e[tm_index(ia, ch * 32 + c0 + kk, 96)] = sn[kk];
-                    a.sc_darg[tm_index(ia, ch * 32 + c0 + kk, 96)] = da[kk];
-                }
+            if (a.gparams) {
+                pl::store16(reinterpret_cast<unsigned char*>(a.sc_e), pl::F_EX, i_raw, ch * 32 + c0, sn);
+                pl::store16(reinterpret_cast<unsigned char*>(a.sc_dl1), pl::F_DL1, i_raw, 64 + ch * 32 + c0, da);
             }
+        }
+        if (a.gparams && hf == 0) {                           // the point itself (A operand of embedder._B's gradient)
+            const float p8[8] = {pf[0], pf[1], pf[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+            pl::store8(reinterpret_cast<unsigned char*>(a.sc_e), pl::F_EX, i_raw, 96, p8);
         }
         float d_c[16];
         tc::tmem_ld16(tl + T::T_DC, d_c);

@@ -1,105 +1,56 @@
 // Tensor-core decoder backward, kernel 2 of 2: every parameter gradient of one decoder as outer products over
-// samples,  dW = A^T * Delta,  on the tcgen05 tensor cores, organised as a streaming GEMM pipeline.
+// samples,  dW = A^T * Delta,  on the tcgen05 tensor cores, fed by bulk copies.
 //
-// The decoder's parameter tensors are cut into "products" of one 32-feature A block times one 32-column delta block
-// (pts_linears.1..4, output_linear, fc_c.i per 32 features, the three 32-wide chunks of the embedding against the
-// deltas of blocks 0 and 3, embedder._B).  The kernel runs in two passes (pass 0: pts_linears.1..4, output_linear,
-// fc_c; pass 1: the embedding-side products) so that the accumulators of ALL products of a pass fit the 512 TMEM
-// columns and stay resident for the CTA's lifetime; a CTA then walks  tile (outer) x product (inner): every operand
-// block comes from HBM once per tile and its re-stagings for other products hit L2.  Sixteen
-// producer warps load the saved activations / deltas (feature-major arrays written by the forward and by kernel 1),
-// split them to TF32 hi/lo and store them as row-per-sample swizzled tiles (the MN-major operand layout of
-// dfp_tc.cuh) into a 3-stage shared-memory ring; a ninth warp issues the SS-mode tcgen05.mma chains (K = 128 samples
-// per stage) and hands the stage back through tcgen05.commit.  (An earlier product-outer variant re-read every operand
-// from HBM for each product: 13.9 GB per decoder at 65 536 rays, ncu profiles/r01.)  The MMAs are M = 64: rows 0..31 are the product, row 32 (from a
-// constant-one feature block addressed as the A operand's second MN block) the bias sums.  The accumulator (32 TMEM
-// columns) lives in one of two TMEM sets, so flushing product p (one atomic pass per CTA
-// and product) overlaps the MMAs of product p+1.  No per-sample or per-tile atomics.
+// The forward and kernel 1 leave their per-sample operands in global memory as bf16 hi/mid "planes" already in the
+// tensor cores' MN-major operand layout (dfp_planes.cuh).  This kernel therefore never touches a value in registers:
+// one thread streams 32-sample slices of the planes into a 3-stage shared-memory ring with cp.async.bulk (completion
+// counted in bytes on an mbarrier), one thread issues SS-mode tcgen05.mma chains whose accumulators stay resident in
+// TMEM for the CTA's lifetime, and tcgen05.commit hands the stage back.  (The previous version staged fp32
+// feature-major scratch through registers -- 32 scalar loads + tf32 split + 16 shared stores per thread and block --
+// and was bound by the load/store unit, not by the MMAs: profiles/r01, "K2 without MMAs" experiment.)
+//
+// Products per 16 samples (each as hi*hi' + hi*mid' + mid*hi'), by pass:
+//   pass 0   P : H[0:128)   x DL0[8:136)   M=128 N=128  diagonal 32x32 blocks = pts_linears.4/.2/.1/.3 (hidden part)
+//            O : H[128:192) x DL0[0:104)   M=64  N=104  rows 0..31 x dout = output_linear; the constant-1 row gives
+//                                                       output_linear.bias and pts_linears.4/.2/.1 biases
+//            C : CX[0:..)   x DH[0:160)    M=64/128 N=160  fc_c.0..4 weights; constant-1 row = their biases
+//   pass 1   E : EX[0:128)  x DL1[0:160)   M=128 N=160  rows 0..92 x dacc3|dacc0 = pts_linears.3 (embedding part) / .0,
+//                                                       row 93 (constant 1) = their biases, rows 96..98 x darg = embedder._B
+// Feature ranges that run past an array (H[168:192), CX beyond CD+8, EX[104:128)) read whatever finite plane data
+// follows in the stage and only produce accumulator rows nobody reads.  One atomic flush per CTA and pass.
 #include "dfp_device.cuh"
+#include "dfp_planes.cuh"
 #include "dfp_tc.cuh"
 
 namespace dfp {
 
 namespace dw {
-constexpr int BLK = 4096;                     // one [128][32] f32 tile (16 KB)
-constexpr uint32_t BLK_BYTES = BLK * 4;
-constexpr int NSTAGE = 2;
-constexpr int STAGE = 5 * BLK;                // A_hi | A_lo | B0 | B1 | B2  (an item = one A block against up to 3 delta blocks)
-constexpr int ONES = NSTAGE * STAGE;          // constant-one A block (column 0 == 1): second MN block of every hi operand
-constexpr int ZERO = ONES + BLK;              // zero block: second MN block of every lo operand
-constexpr int FLOATS = ZERO + BLK;
+constexpr int NST = 3;                        // ring depth
+constexpr int QS = 32;                        // samples per stage (4 groups of 8)
 constexpr int MAX_TILES = 1024;               // active tiles of one CTA
-constexpr int PRODUCERS = 256;               // threads staging one item (128 A rows + 128 B rows)
-constexpr int GROUPS = 2;                     // producer groups working on alternating items
+constexpr int THREADS = 192;                  // warp 0: tile list + producer, warp 1: MMA issuer, warps 2..5: flush
+__host__ __device__ constexpr uint32_t piece(int F) { return 64u * (uint32_t)F; }          // one plane, 32 samples
+template <int CD, int PASS> __host__ __device__ constexpr uint32_t stage_bytes() {
+    return PASS == 0 ? 2u * (piece(pl::F_H) + piece(pl::f_cx(CD)) + piece(pl::F_DH) + piece(pl::F_DL0)) : 2u * (piece(pl::F_EX) + piece(pl::F_DL1));
+}
 }  // namespace dw
 
-struct DwProduct {
-    int kind;      // 0: pts_linears.i  1: output_linear  2: fc_c.i (feature half hf)  3: embedding chunk cb x delta of block `which`  4: embedder._B chunk cb
-    int i, hf, cb, which;
-};
-
-template <int CD>
-__device__ __forceinline__ DwProduct dw_product(int p) {
-    DwProduct d = {0, 0, 0, 0, 0};
-    constexpr int NC = 5 * (CD / 32);
-    if (p < 4) { d.kind = 0; d.i = p + 1; }
-    else if (p == 4) { d.kind = 1; }
-    else if (p < 5 + NC) { d.kind = 2; d.i = (p - 5) % 5; d.hf = (p - 5) / 5; }
-    else if (p < 5 + NC + 6) { d.kind = 3; d.cb = (p - 5 - NC) % 3; d.which = ((p - 5 - NC) / 3) ? 3 : 0; }
-    else { d.kind = 4; d.cb = p - 5 - NC - 6; }
-    return d;
-}
-template <int CD> __host__ __device__ constexpr int dw_num_products() { return 5 + 5 * (CD / 32) + 6 + 3; }
-
-// An item = up to three products that share their A block; its MMAs are N = 32 * nprod wide (the transposed SS-mode
-// TF32 MMA has a high fixed cost, ~27 ns measured, so fewer and wider MMAs win).  slot = first 32-column TMEM slot.
-struct DwItem { int nprod; int prod[3]; int slot; };
-template <int CD, int PASS> __host__ __device__ constexpr int dw_num_items() { return PASS == 0 ? 5 + 2 * (CD / 32) : 4; }
-template <int CD, int PASS>
-__device__ __forceinline__ DwItem dw_item(int it) {
-    DwItem d = {1, {0, 0, 0}, 0};
-    if (PASS == 0) {
-        if (it < 5) { d.prod[0] = it; d.slot = it; return d; }                 // pts_linears.1..4, output_linear
-        const int hf = (it - 5) >> 1, second = (it - 5) & 1;                   // fc_c: (c half, [dh_0 dh_1 dh_2]) and (c half, [dh_3 dh_4])
-        const int base = 5 + hf * 5 + (second ? 3 : 0);
-        d.nprod = second ? 2 : 3;
-        d.prod[0] = base; d.prod[1] = base + 1; d.prod[2] = base + 2;
-        d.slot = base;
-        return d;
-    }
-    constexpr int B0 = 5 + 5 * (CD / 32);
-    if (it < 3) { d.nprod = 2; d.prod[0] = B0 + it; d.prod[1] = B0 + 3 + it; d.slot = 2 * it; return d; }   // sin chunk x [dacc_0 | dacc_3]
-    d.nprod = 3; d.prod[0] = B0 + 6; d.prod[1] = B0 + 7; d.prod[2] = B0 + 8; d.slot = 6;                        // point x [darg chunks]
-    return d;
-}
-
-// write 32 values of sample-row `row` into a swizzled [128][32] tile, as eight 16-byte stores
-__device__ __forceinline__ void tile_store_row(float* tile, int row, const float (&v)[32]) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        float* dst = tile + row * 32 + ((((q >> 1) ^ row) & 3) << 3) + ((q & 1) << 2);
-        *reinterpret_cast<float4*>(dst) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    }
-}
-// 32 consecutive features of a tile-major F-feature array (tm_index) for sample s (zeros when !valid)
-__device__ __forceinline__ void load_features(const float* __restrict__ base, int F, int64_t s, int f0, bool valid, float (&v)[32]) {
-    const float* p = base + tm_index(s, f0, F);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = valid ? __ldg(p + j * 128) : 0.f;
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
-}
-
 template <int DEC, int PASS>
-__global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_dw_tc(const DecArgs a) {
+__global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs a) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
     constexpr int NOUT = (DEC == 2) ? 4 : 1;
-    constexpr int NI = dw_num_items<CD, PASS>();                     // items per tile: 7 / 9 (pass 0), 4 (pass 1)
+    constexpr int FCX = pl::f_cx(CD);
+    constexpr int MC = (CD == 32) ? 64 : 128;                        // M of the fc_c product
     using L = DecOff<CD>;
+    constexpr uint32_t STAGE = dw::stage_bytes<CD, PASS>();
+    // byte offsets of the pieces inside a stage
+    constexpr uint32_t O_H = 0, O_CX = O_H + 2 * dw::piece(pl::F_H), O_DH = O_CX + 2 * dw::piece(FCX), O_DL0 = O_DH + 2 * dw::piece(pl::F_DH);
+    constexpr uint32_t O_EX = 0, O_DL1 = O_EX + 2 * dw::piece(pl::F_EX);
+    // TMEM columns
+    constexpr uint32_t T_P = 0, T_O = 128, T_C = 232, T_E = 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
-    __shared__ __align__(8) uint64_t full_bar[dw::NSTAGE], empty_bar[dw::NSTAGE], done_bar;
+    unsigned char* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full_bar[dw::NST], empty_bar[dw::NST], done_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ int tile_list[dw::MAX_TILES];
     __shared__ int n_active_s;
@@ -107,11 +58,11 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
     const int64_t n = dec_items(a);
     const int64_t tiles = (n + 127) / 128;
 
-    for (int i = tid; i < dw::FLOATS; i += blockDim.x) sm[i] = 0.f;
+    // the stage ring must never hold NaN bit patterns where the over-long feature ranges read: clear it once
+    for (uint32_t i = tid; i < dw::NST * STAGE / 16; i += dw::THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) n_active_s = 0;
     __syncthreads();
-    if (tid < 128) sm[dw::ONES + tc::mn_tile_index(tid, 0)] = 1.0f;          // ZERO block stays zero
-    // the CTA's tiles that carry any upstream gradient (kernel 1 wrote scratch only for those), in order
+    // the CTA's tiles that carry any upstream gradient (kernel 1 wrote its planes only for those), in order
     if (warp == 0) {
         int cnt = 0;
         for (int64_t tile = blockIdx.x; tile < tiles && cnt < dw::MAX_TILES; tile += gridDim.x) {
@@ -128,9 +79,9 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
         }
         if (lane == 0) n_active_s = cnt;
     }
-    if (warp == 3) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+    if (warp == 1) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
     if (tid == 0) {
-        for (int i = 0; i < dw::NSTAGE; ++i) { tc::mbar_init(&full_bar[i], dw::PRODUCERS); tc::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < dw::NST; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
         tc::mbar_init(&done_bar, 1);
         tc::fence_mbar_init();
     }
@@ -141,168 +92,137 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
     const uint32_t tb = tmem_base_s;
     const int n_active = n_active_s;
     const uint32_t sm_base = tc::smem_u32(sm);
+    const uint32_t total = 4u * (uint32_t)n_active;                  // stages: (tile, quarter)
 
     if (n_active > 0) {
-        if (warp == dw::GROUPS * dw::PRODUCERS / 32) {
-            // ===================== MMA issuer (one lane) =====================
+        if (warp == 0) {
+            // ===================== producer: bulk copies of plane slices =====================
             if (lane == 0) {
-                const uint32_t total = (uint32_t)NI * (uint32_t)n_active;
-                for (uint32_t q = 0; q < total; ++q) {                   // q = tile * NI + item (tile-outer)
-                    const int st = q % dw::NSTAGE;
-                    const DwItem it = dw_item<CD, PASS>((int)(q % NI));
-                    tc::mbar_wait(&full_bar[st], (q / dw::NSTAGE) & 1);
+                const unsigned char* gH = reinterpret_cast<const unsigned char*>(a.act_h);
+                const unsigned char* gCX = reinterpret_cast<const unsigned char*>(a.act_c);
+                const unsigned char* gDH = reinterpret_cast<const unsigned char*>(a.sc_dh);
+                const unsigned char* gDL0 = reinterpret_cast<const unsigned char*>(a.sc_darg);
+                const unsigned char* gEX = reinterpret_cast<const unsigned char*>(a.sc_e);
+                const unsigned char* gDL1 = reinterpret_cast<const unsigned char*>(a.sc_dl1);
+                for (uint32_t q = 0; q < total; ++q) {
+                    const int st = q % dw::NST;
+                    if (q >= dw::NST) tc::mbar_wait(&empty_bar[st], ((q / dw::NST) - 1) & 1);     // MMAs of the previous use are done
+                    const int64_t tile = tile_list[q >> 2];
+                    const uint32_t quarter = q & 3;
+                    const uint32_t dst = sm_base + st * STAGE;
+                    tc::mbar_arrive_expect_tx(&full_bar[st], STAGE);
+                    auto copy = [&](const unsigned char* g, int F, uint32_t off) {
+                        for (int plane = 0; plane < 2; ++plane)
+                            tc::bulk_copy_g2s(dst + off + plane * dw::piece(F), g + (tile * 2 + plane) * (int64_t)(256 * F) + quarter * dw::piece(F),
+                                              dw::piece(F), &full_bar[st]);
+                    };
+                    if (PASS == 0) { copy(gH, pl::F_H, O_H); copy(gCX, FCX, O_CX); copy(gDH, pl::F_DH, O_DH); copy(gDL0, pl::F_DL0, O_DL0); }
+                    else { copy(gEX, pl::F_EX, O_EX); copy(gDL1, pl::F_DL1, O_DL1); }
+                }
+            }
+        } else if (warp == 1) {
+            // ===================== MMA issuer =====================
+            if (lane == 0) {
+                for (uint32_t q = 0; q < total; ++q) {
+                    const int st = q % dw::NST;
+                    tc::mbar_wait(&full_bar[st], (q / dw::NST) & 1);
                     tc::fence_after_sync();
-                    const uint32_t sa = sm_base + st * dw::STAGE * 4;
-                    const uint32_t a_hi = sa, a_lo = sa + dw::BLK_BYTES, b = sa + 2 * dw::BLK_BYTES;
-                    // M = 64: rows 0..31 = the products, row 32 = column sums of the delta tiles (constant-one block)
-                    tc::mma_outer64(tb + it.slot * 32, a_hi, sm_base + dw::ONES * 4 - a_hi, a_lo, sm_base + dw::ZERO * 4 - a_lo, b,
-                                    32 * it.nprod, q >= (uint32_t)NI);
+                    const uint32_t s0 = sm_base + st * STAGE;
+                    auto prod = [&](uint32_t d_col, int M, int N, uint32_t a_off, int FA, int fa0, uint32_t b_off, int FB, int fb0) {
+                        const uint32_t idesc = tc::idesc_bf16_mn(M, N);
+                        const uint32_t ga = 16u * FA, gb = 16u * FB;                       // bytes per 8-sample group
+                        for (uint32_t ks = 0; ks < 2; ++ks) {                              // 16 samples = two groups per MMA
+                            const uint32_t ah = s0 + a_off + (fa0 >> 3) * 128 + ks * 2 * ga, bh = s0 + b_off + (fb0 >> 3) * 128 + ks * 2 * gb;
+                            tc::mma_planes(tb + d_col, ah, ah + dw::piece(FA), ga, bh, bh + dw::piece(FB), gb, idesc, q > 0 || ks > 0);
+                        }
+                    };
+                    if (PASS == 0) {
+                        prod(T_P, 128, 128, O_H, pl::F_H, 0, O_DL0, pl::F_DL0, 8);
+                        prod(T_O, 64, 104, O_H, pl::F_H, 128, O_DL0, pl::F_DL0, 0);
+                        prod(T_C, MC, 160, O_CX, FCX, 0, O_DH, pl::F_DH, 0);
+                    } else {
+                        prod(T_E, 128, 160, O_EX, pl::F_EX, 0, O_DL1, pl::F_DL1, 0);
+                    }
                     tc::mma_commit(&empty_bar[st]);                      // stage reusable once these MMAs have read it
                 }
                 tc::mma_commit(&done_bar);                               // everything accumulated
             }
         } else {
-            // ===================== producers (256 threads) + flush (warp 0) =====================
-            const int pgrp = tid / dw::PRODUCERS;                  // this thread's producer group
-            const int half = (tid % dw::PRODUCERS) >> 7;           // 0: stages A (and delta block 2), 1: stages delta blocks 0 and 1
-            const int row = tid & 127;
+            // ===================== flush (warps 2..5 = TMEM lane quarters 2, 3, 0, 1), once per CTA =====================
+            tc::mbar_wait(&done_bar, 0);
+            tc::fence_after_sync();
             float* g = a.gparams + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR));
-            // the A block (32 features) of product p for sample s
-            auto load_A = [&](const DwProduct& pr, int64_t s, int64_t sid, bool valid, float (&v)[32]) {
-                if (pr.kind == 0) load_features(a.act_h, 160, s, (pr.i - 1) * 32, valid, v);
-                else if (pr.kind == 1) load_features(a.act_h, 160, s, 4 * 32, valid, v);
-                else if (pr.kind == 2) load_features(a.act_c, CD, s, pr.hf * 32, valid, v);
-                else if (pr.kind == 3) load_features(a.sc_e, 96, s, pr.cb * 32, valid, v);
-                else {
-                    float pw[3] = {0.f, 0.f, 0.f};
-                    if (valid) {
-                        if (a.ps.pts == nullptr) {
-                            const int64_t r = sid / a.ps.S;
-                            double pq[3];
-                            const float o[3] = {a.ps.rays_o[3 * r], a.ps.rays_o[3 * r + 1], a.ps.rays_o[3 * r + 2]};
-                            const float d[3] = {a.ps.rays_d[3 * r], a.ps.rays_d[3 * r + 1], a.ps.rays_d[3 * r + 2]};
-                            ray_point(o, d, a.ps.z[sid], pq);
-                            pw[0] = (float)pq[0]; pw[1] = (float)pq[1]; pw[2] = (float)pq[2];
-                        } else if (a.ps.pts_f64) {
-                            const double* pq = reinterpret_cast<const double*>(a.ps.pts) + 3 * sid;
-                            pw[0] = (float)pq[0]; pw[1] = (float)pq[1]; pw[2] = (float)pq[2];
-                        } else {
-                            const float* pq = reinterpret_cast<const float*>(a.ps.pts) + 3 * sid;
-                            pw[0] = pq[0]; pw[1] = pq[1]; pw[2] = pq[2];
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = j < 3 ? pw[j] : 0.f;
-                }
-            };
-            // the delta block (32 columns) of product p for sample s
-            auto load_B = [&](const DwProduct& pr, int64_t s, int64_t sid, bool valid, float (&v)[32]) {
-                if (pr.kind == 0 || pr.kind == 3) {
-                    const int blk = pr.kind == 0 ? pr.i : pr.which;
-                    load_features(a.sc_dh, 160, s, blk * 32, valid, v);
-                    const uint32_t m = a.act_m[tm_index(s, blk, 5)];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
-                } else if (pr.kind == 1) {
-                    float d4[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (valid) {
-                        if (NOUT == 1) d4[0] = a.dout[sid];
-                        else { const float4 x = *reinterpret_cast<const float4*>(a.dout + 4 * sid); d4[0] = x.x; d4[1] = x.y; d4[2] = x.z; }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = j < 4 ? d4[j] : 0.f;     // colour: the 4th output carries no gradient
-                } else if (pr.kind == 2) {
-                    load_features(a.sc_dh, 160, s, pr.i * 32, valid, v);
-                } else {
-                    load_features(a.sc_darg, 96, s, pr.cb * 32, valid, v);
-                }
-            };
-            // items are numbered q = tile * NI + item (tile-outer); this group stages the items with q % GROUPS == pgrp
-            const uint32_t total = (uint32_t)NI * (uint32_t)n_active;
-            for (uint32_t q = (uint32_t)pgrp; q < total; q += dw::GROUPS) {
-                const int st = q % dw::NSTAGE;
-                const DwItem it = dw_item<CD, PASS>((int)(q % NI));
-                const int64_t i_raw = (int64_t)tile_list[q / NI] * 128 + row;
-                const bool valid = i_raw < n;
-                const int64_t s = valid ? i_raw : n - 1;             // list position (saved activations / scratch index)
-                const int64_t sid = dec_sample(a, s);                // sample id (points, dout)
-                float v0[32], v1[32];
-                // half 0: the A block and (if present) delta block 2;  half 1: delta blocks 0 and (if present) 1
-                const bool second = half == 0 ? it.nprod > 2 : it.nprod > 1;
-                if (half == 0) {
-                    load_A(dw_product<CD>(it.prod[0]), s, sid, valid, v0);
-                    if (second) load_B(dw_product<CD>(it.prod[2]), s, sid, valid, v1);
-                } else {
-                    load_B(dw_product<CD>(it.prod[0]), s, sid, valid, v0);
-                    if (second) load_B(dw_product<CD>(it.prod[1]), s, sid, valid, v1);
-                }
-                if (q >= dw::NSTAGE) tc::mbar_wait(&empty_bar[st], ((q / dw::NSTAGE) - 1) & 1);      // MMAs of the previous use are done
-                float* stage = sm + st * dw::STAGE;
-                if (half == 0) {
-                    float hi[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { hi[j] = tc::tf32_rna(v0[j]); v0[j] = tc::tf32_rna(v0[j] - hi[j]); }
-                    tile_store_row(stage, row, hi);
-                    tile_store_row(stage + dw::BLK, row, v0);
-                    if (second) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v1[j] = tc::tf32_rna(v1[j]);
-                        tile_store_row(stage + 4 * dw::BLK, row, v1);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v0[j] = tc::tf32_rna(v0[j]);
-                    tile_store_row(stage + 2 * dw::BLK, row, v0);
-                    if (second) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v1[j] = tc::tf32_rna(v1[j]);
-                        tile_store_row(stage + 3 * dw::BLK, row, v1);
-                    }
-                }
-                tc::fence_proxy_async();
-                mbar_arrive(&full_bar[st]);
-            }
-            // ---- flush (warps 0..2), once per CTA: accumulator row m is TMEM lane (m/16)*32 + m%16; row 32 holds the bias sums
-            if (warp < 3) {
-                tc::mbar_wait(&done_bar, 0);
-                tc::fence_after_sync();
-#pragma unroll 1
-                for (int pp = 0; pp < NI * 3; ++pp) {
-                    const DwItem it = dw_item<CD, PASS>(pp / 3);
-                    const int blk = pp % 3;
-                    if (blk >= it.nprod) continue;
-                    const DwProduct pr = dw_product<CD>(it.prod[blk]);
-                    float d[32];
-                    tc::tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + (it.slot + blk) * 32, d);
+            const int qtr = warp & 3;
+            const uint32_t tl = tb + ((uint32_t)(qtr * 32) << 16);
+            const int row128 = qtr * 32 + lane;                          // accumulator row of an M = 128 product
+            const int row64 = lane < 16 ? qtr * 16 + lane : -1;          // ... of an M = 64 product (lane (m/16)*32 + m%16)
+            float d[32];
+            if (PASS == 0) {
+                {   // P: this warp's rows are H block `qtr`; only the matching delta block is a parameter
+                    tc::tmem_ld32(tl + T_P + qtr * 32, d);
                     tc::wait_ld();
-                    if (lane < 16) {
-                        const int k = warp * 16 + lane;                 // accumulator row
-                        if (k == 32) {                                   // bias sums
-                            if (pr.kind == 0) { for (int j = 0; j < 32; ++j) atomicAdd(g + L::BP + pr.i * 32 + j, d[j]); }
-                            else if (pr.kind == 1) { for (int j = 0; j < NOUT; ++j) atomicAdd(g + L::BO + j, d[j]); }
-                            else if (pr.kind == 2 && pr.hf == 0) { for (int j = 0; j < 32; ++j) atomicAdd(g + L::BC + pr.i * 32 + j, d[j]); }
-                            else if (pr.kind == 3 && pr.cb == 0 && pr.which == 0) { for (int j = 0; j < 32; ++j) atomicAdd(g + L::BP + j, d[j]); }
-                        } else if (k < 32) {
-                            if (pr.kind == 0) {
+                    const int li = qtr == 0 ? 4 : qtr == 1 ? 2 : qtr == 2 ? 1 : 3;
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) atomicAdd(g + L::WH + (pr.i - 1) * 1024 + k * 32 + j, d[j]);
-                            } else if (pr.kind == 1) {
+                    for (int j = 0; j < 32; ++j) atomicAdd(g + L::WH + (li - 1) * 1024 + lane * 32 + j, d[j]);
+                }
+                {   // O: columns [dout8 | dacc4 | dacc2 | dacc1]
+                    float d8[8];
+                    {
+                        uint32_t v[8];
+                        tc::tmem_ld8(tl + T_O, v);
+                        tc::wait_ld();
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) if (j < NOUT) atomicAdd(g + L::WO + j * 32 + k, d[j]);
-                            } else if (pr.kind == 2) {
+                        for (int j = 0; j < 8; ++j) d8[j] = __uint_as_float(v[j]);
+                    }
+                    if (row64 >= 0 && row64 < 32) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) atomicAdd(g + L::WC + pr.i * CD * 32 + (pr.hf * 32 + k) * 32 + j, d[j]);
-                            } else if (pr.kind == 3) {
-                                const int kk = pr.cb * 32 + k;
-                                if (kk < EMB) {
+                        for (int o = 0; o < NOUT; ++o) atomicAdd(g + L::WO + o * 32 + row64, d8[o]);
+                    } else if (row64 == 32) {
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j) atomicAdd(g + L::W03 + kk * 64 + (pr.which ? 32 : 0) + j, d[j]);
-                                }
-                            } else if (k < 3) {
+                        for (int o = 0; o < NOUT; ++o) atomicAdd(g + L::BO + o, d8[o]);
+                    }
+#pragma unroll 1
+                    for (int b = 0; b < 3; ++b) {
+                        tc::tmem_ld32(tl + T_O + 8 + b * 32, d);
+                        tc::wait_ld();
+                        const int li = b == 0 ? 4 : b == 1 ? 2 : 1;
+                        if (row64 == 32) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) if (pr.cb * 32 + j < EMB) atomicAdd(g + L::B + k * EMB_PAD + pr.cb * 32 + j, d[j]);
-                            }
+                            for (int j = 0; j < 32; ++j) atomicAdd(g + L::BP + li * 32 + j, d[j]);
                         }
+                    }
+                }
+#pragma unroll 1
+                for (int i = 0; i < 5; ++i) {   // C: fc_c.i
+                    tc::tmem_ld32(tl + T_C + i * 32, d);
+                    tc::wait_ld();
+                    const int row = (MC == 64) ? row64 : row128;
+                    if (row >= 0 && row < CD) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) atomicAdd(g + L::WC + i * CD * 32 + row * 32 + j, d[j]);
+                    } else if (row == CD) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) atomicAdd(g + L::BC + i * 32 + j, d[j]);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int b = 0; b < 5; ++b) {   // E: columns [dacc3 | dacc0 | darg 0..95]
+                    tc::tmem_ld32(tl + T_E + b * 32, d);
+                    tc::wait_ld();
+                    const int m = row128;
+                    if (b < 2) {
+                        const int coff = b == 0 ? 32 : 0, li = b == 0 ? 3 : 0;
+                        if (m < EMB) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) atomicAdd(g + L::W03 + m * 64 + coff + j, d[j]);
+                        } else if (m == EMB) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) atomicAdd(g + L::BP + li * 32 + j, d[j]);
+                        }
+                    } else if (m >= 96 && m < 99) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if ((b - 2) * 32 + j < EMB) atomicAdd(g + L::B + (m - 96) * EMB_PAD + (b - 2) * 32 + j, d[j]);
                     }
                 }
             }
@@ -310,22 +230,23 @@ __global__ void __launch_bounds__(dw::GROUPS * dw::PRODUCERS + 32, 1) k_decoder_
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 3) tc::tmem_dealloc(tb, 512);
+    if (warp == 1) tc::tmem_dealloc(tb, 512);
 }
 
 template <int DEC>
 int launch_decoder_dw_tc(const DecArgs& a, cudaStream_t st) {
-    const size_t smem = dw::FLOATS * sizeof(float) + 1024;
-    int rc = set_smem(k_decoder_dw_tc<DEC, 0>, smem);
+    constexpr int CD = (DEC == 1) ? 64 : 32;
+    const size_t smem0 = dw::NST * dw::stage_bytes<CD, 0>() + 1024, smem1 = dw::NST * dw::stage_bytes<CD, 1>() + 1024;
+    int rc = set_smem(k_decoder_dw_tc<DEC, 0>, smem0);
     if (rc) return rc;
-    if ((rc = set_smem(k_decoder_dw_tc<DEC, 1>, smem))) return rc;
+    if ((rc = set_smem(k_decoder_dw_tc<DEC, 1>, smem1))) return rc;
     const int64_t tiles = (a.n + 127) / 128;
     int blocks = grid_for(tiles, 1, num_sms());
     const int64_t min_blocks = (tiles + dw::MAX_TILES - 1) / dw::MAX_TILES;      // a CTA lists at most MAX_TILES tiles
     if (blocks < min_blocks) blocks = (int)min_blocks;
-    DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC, 0><<<blocks, dw::GROUPS * dw::PRODUCERS + 32, smem, st>>>(a));
+    DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC, 0><<<blocks, dw::THREADS, smem0, st>>>(a));
     DFP_LAUNCH_CHECK("k_decoder_dw_tc");
-    DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC, 1><<<blocks, dw::GROUPS * dw::PRODUCERS + 32, smem, st>>>(a));
+    DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC, 1><<<blocks, dw::THREADS, smem1, st>>>(a));
     DFP_LAUNCH_CHECK("k_decoder_dw_tc");
     return DFP_OK;
 }

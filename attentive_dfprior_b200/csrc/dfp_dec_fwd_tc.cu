@@ -9,6 +9,7 @@
 // A CTA runs two independent 128-sample groups (one for the 64-feature high decoder) so that one group's
 // epilogue overlaps the other group's MMAs.
 #include "dfp_device.cuh"
+#include "dfp_planes.cuh"
 #include "dfp_tc.cuh"
 
 namespace dfp {
@@ -119,17 +120,16 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             float c[16];
             gather_features16(a.grid, tri_setup(xn, a.grid.W, a.grid.H, a.grid.D), hf, c);
             tc::tmem_store_split16(tl + T::T_C_HI, tl + T::T_C_LO, c);
-            if (a.act_c && valid) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) a.act_c[tm_index(ia, 16 * hf + k, CD)] = c[k];
+            // saved operands go out as bf16 planes at the row's own position (every row of a tile is written: rows past
+            // the end repeat the last sample, their deltas are zero in the backward)
+            if (a.act_c) {
+                pl::store16(reinterpret_cast<unsigned char*>(a.act_c), pl::f_cx(CD), i_raw, 16 * hf, c);
+                if (hf == 0) pl::store_ones8(reinterpret_cast<unsigned char*>(a.act_c), pl::f_cx(CD), i_raw, CD);
             }
             if (DEC == 1) {
                 gather_features16(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), hf, c);
                 tc::tmem_store_split16(tl + T::T_C_HI + 32, tl + T::T_C_LO + 32, c);
-                if (a.act_c && valid) {
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) a.act_c[tm_index(ia, 32 + 16 * hf + k, CD)] = c[k];
-                }
+                if (a.act_c) pl::store16(reinterpret_cast<unsigned char*>(a.act_c), pl::f_cx(CD), i_raw, 32 + 16 * hf, c);
             }
         }
         // Fourier embedding in three 32-wide K chunks (16 per thread), each accumulated into D03 = [z0 | skip part of z3]
@@ -181,10 +181,10 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                 m |= (pre > 0.f ? 1u : 0u) << j;
                 h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + 16 * hf + j]);
             }
-            if (a.act_h && valid) {                                   // kept for the backward (DFP_FLAG_SAVE_ACT)
-                reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, 0, 5))[hf] = (uint16_t)m;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) a.act_h[tm_index(ia, 16 * hf + j, 160)] = h[j];
+            if (a.act_h) {                                            // kept for the backward (DFP_FLAG_SAVE_ACT)
+                if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, 0, 5))[hf] = (uint16_t)m;
+                pl::store16(reinterpret_cast<unsigned char*>(a.act_h), pl::F_H, i_raw, pl::h_pos(0) * 32 + 16 * hf, h);
+                if (hf == 0) pl::store_ones8(reinterpret_cast<unsigned char*>(a.act_h), pl::F_H, i_raw, 160);
             }
         }
 #pragma unroll 1
@@ -222,10 +222,9 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                 m |= (pre > 0.f ? 1u : 0u) << j;
                 h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + i * 32 + 16 * hf + j]);
             }
-            if (a.act_h && valid) {
-                reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, i, 5))[hf] = (uint16_t)m;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) a.act_h[tm_index(ia, i * 32 + 16 * hf + j, 160)] = h[j];
+            if (a.act_h) {
+                if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, i, 5))[hf] = (uint16_t)m;
+                pl::store16(reinterpret_cast<unsigned char*>(a.act_h), pl::F_H, i_raw, pl::h_pos(i) * 32 + 16 * hf, h);
             }
         }
         // output layer: each half sums its 16 inputs, the lower half adds the upper half's partial and the bias

@@ -92,13 +92,15 @@ struct Ws {                        // per-sample workspace arrays (NS samples)
     float* d_rgb;                  // [NS][4]
     float* dp;                     // [NS][3] gradient w.r.t. the sample point
     // DFP_FLAG_SAVE_ACT: activations of the three decoders kept by the tensor-core forward, tile-major (tm_index)
-    float* act_h[3];               // [160][NS]: inputs of pts_linears.1..4 and of output_linear
-    uint32_t* act_m[3];            // [5][NS]:   ReLU masks of pts_linears.0..4
-    float* act_c[3];               // [CD][NS]:  gathered grid features
+    // bf16 plane arrays (dfp_planes.cuh; the float* type is only a handle)
+    float* act_h[3];               // H:  inputs of pts_linears.1..4 and of output_linear + constant 1
+    uint32_t* act_m[3];            // [5][NS] tile-major: ReLU masks of pts_linears.0..4
+    float* act_c[3];               // CX: gathered grid features + constant 1
     // scratch shared by the decoders during the tensor-core backward
-    float* sc_e;                   // [96][NS]  sin(embedding argument)
-    float* sc_dh;                  // [160][NS] gradient of each block's output (before the ReLU mask)
-    float* sc_darg;                // [96][NS]  gradient of the embedding arguments
+    float* sc_e;                   // EX:  sin(embedding argument), point
+    float* sc_dh;                  // DH:  gradient of each block's output (before the ReLU mask)
+    float* sc_darg;                // DL0: upstream gradient and masked deltas of blocks 4, 2, 1, 3
+    float* sc_dl1;                 // DL1: masked deltas of blocks 3, 0 and the gradient of the embedding arguments
 };
 
 
@@ -309,7 +311,7 @@ struct DecArgs {
     float* gparams;          // packed parameter gradient or null
     float* dp;               // [n][3] accumulated, or null
     // tensor-core training path (DFP_FLAG_SAVE_ACT): saved activations / backward scratch, feature-major with stride n
-    float* act_h; uint32_t* act_m; float* act_c; float* sc_e; float* sc_dh; float* sc_darg;
+    float* act_h; uint32_t* act_m; float* act_c; float* sc_e; float* sc_dh; float* sc_darg; float* sc_dl1;   // see Ws
     // optional compacted sample list (device): the kernel then processes samples list[0..*count) only and indexes the
     // saved activations / scratch by list position.  Used for the high decoder, whose output and gradient only matter
     // on TSDF-band samples (decoder.py:326-333: f_add_m_occ is read under the band mask only).

@@ -61,6 +61,40 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- bulk asynchronous copies (TMA, 1-D): global -> shared, completion counted in bytes on an mbarrier ----
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- bf16 operands, both MN-major (row-per-sample), no swizzle: see dfp_planes.cuh for the layout ----
+__host__ __device__ constexpr uint32_t idesc_bf16_mn(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ uint64_t smem_desc_plane(uint32_t saddr, uint32_t group_bytes) {      // LBO = 8-sample group stride, SBO = 128
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((group_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+// D (+)= A^T B over 16 samples with the two-plane split: hi*hi' + hi*mid' + mid*hi' (small terms first)
+__device__ __forceinline__ void mma_planes(uint32_t d_tmem, uint32_t a_hi, uint32_t a_mid, uint32_t a_group_bytes, uint32_t b_hi,
+                                           uint32_t b_mid, uint32_t b_group_bytes, uint32_t idesc, bool accumulate) {
+    const uint64_t ah = smem_desc_plane(a_hi, a_group_bytes), am = smem_desc_plane(a_mid, a_group_bytes);
+    const uint64_t bh = smem_desc_plane(b_hi, b_group_bytes), bm = smem_desc_plane(b_mid, b_group_bytes);
+    mma_bf16_ss(d_tmem, am, bh, idesc, accumulate ? 1u : 0u);
+    mma_bf16_ss(d_tmem, ah, bm, idesc, 1u);
+    mma_bf16_ss(d_tmem, ah, bh, idesc, 1u);
+}
+
 // ---- descriptors ----
 // shared-memory matrix descriptor, K-major, SWIZZLE_NONE (see header comment for the layout)
 __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

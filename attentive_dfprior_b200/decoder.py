@@ -135,9 +135,10 @@ class ParamPack:
 def decoder_param_list(decoders):
     """The 79 tensors in state_dict order; works for this package's DF and for the reference's own DF."""
     ps = list(decoders.parameters())
-    if len(ps) != L.N_PARAM_TENSORS or sum(p.numel() for p in ps) != L.N_PARAMS:
+    if len(ps) != L.N_PARAM_TENSORS or (not decoders.__dict__.get("_dfp_checked") and sum(p.numel() for p in ps) != L.N_PARAMS):
         raise ValueError(f"expected {L.N_PARAM_TENSORS} decoder tensors / {L.N_PARAMS} parameters, "
                          f"got {len(ps)} / {sum(p.numel() for p in ps)}")
+    decoders.__dict__["_dfp_checked"] = True          # shapes of a module's parameters do not change: count them once
     return ps
 
 

@@ -41,6 +41,9 @@ _bounds = _BoundsCache()
 _tables = {}
 
 
+_cfg_cache = {}
+
+
 def _cfg_struct(stage: str, n_samples: int, n_surface: int, n_importance: int = 0, flags: int = 0) -> L.DfpCfg:
     key = (n_samples, n_surface)
     tab = _tables.get(key)
@@ -49,6 +52,10 @@ def _cfg_struct(stage: str, n_samples: int, n_surface: int, n_importance: int = 
         ts = torch.linspace(0., 1., steps=max(n_surface, 1)).double()      # Renderer.py:183-184
         tab = (tv.tolist(), (1. - tv).tolist(), ts.tolist(), (1. - ts).tolist())
         _tables[key] = tab
+    ckey = (stage, n_samples, n_surface, n_importance, flags)
+    cfg = _cfg_cache.get(ckey)                       # read-only once built: shared between calls
+    if cfg is not None:
+        return cfg
     cfg = L.DfpCfg()
     cfg.stage = L.STAGES[stage]
     cfg.n_samples, cfg.n_surface, cfg.n_importance = n_samples, n_surface, n_importance
@@ -59,6 +66,7 @@ def _cfg_struct(stage: str, n_samples: int, n_surface: int, n_importance: int = 
     for i in range(n_surface):
         cfg.t_surf[i] = tab[2][i]
         cfg.one_minus_t_surf[i] = tab[3][i]
+    _cfg_cache[ckey] = cfg
     return cfg
 
 
@@ -156,12 +164,9 @@ def _param_grads(gp, params, needs):
         return [None] * len(params)
     flat = torch.empty(L.N_PARAMS, device=gp.device, dtype=torch.float32)
     L.check(L.lib().dfp_unpack_param_grads(gp.data_ptr(), flat.data_ptr(), _stream()))
-    out, off = [], 0
-    for p, need in zip(params, needs):
-        n = p.numel()
-        out.append(flat[off:off + n].view(p.shape).to(p.dtype) if need else None)
-        off += n
-    return out
+    # one C++ call makes the 79 shaped views (a Python slice/view/to per tensor cost 0.4 ms per step, measured)
+    views = torch._C._nn.unflatten_dense_tensors(flat, list(params))
+    return [(v if v.dtype == p.dtype else v.to(p.dtype)) if need else None for v, p, need in zip(views, params, needs)]
 
 
 # ----------------------------------------------------------------------------------------
