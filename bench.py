@@ -188,11 +188,33 @@ def cpu_baseline(scene_cpu_factory, budget_s=20.0):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+NCU_SUMMARY = "profiles/r01_ncu_full_summary_planes.csv"
+
+
+def ncu_traffic(kernels):
+    """DRAM bytes (read + write) of the named kernels' launches during ONE step of the default workload, from the
+    committed `ncu --set full` capture of `bench.py --steps 1` (profiles/); None when the file is missing."""
+    path = os.path.join(REPO, NCU_SUMMARY)
+    if not os.path.exists(path):
+        return None
+    import csv
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    total = 0.0
+    for r in rows[2:]:
+        if any(k in r[ik] for k in kernels):
+            total += float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
+    return total or None
+
+
 def run_ours(args):
     import attentive_dfprior_b200 as A
     from attentive_dfprior_b200 import _lib as L
     from attentive_dfprior_b200 import dist as D
     from attentive_dfprior_b200 import synth
+    from attentive_dfprior_b200 import mapper_ops as M
     from attentive_dfprior_b200.config import default_cfg, slam_namespace
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,8 +255,11 @@ def run_ours(args):
         A.decoder.param_pack_of(model).key = None                      # decoders change every mapping iteration: re-pack
         d, u, c, w = D.render_batch_ray_sharded(renderer, grids, model, rd, ro, scene.tsdf_volume, scene.tsdf_bnds,
                                                 STAGE, g, group=group)
-        m = g > 0
-        loss = torch.abs(g[m] - d[m]).sum() + 0.2 * torch.abs(gc - c).sum()          # src/Mapper.py:457-469
+        if args.torch_loss:
+            m = g > 0
+            loss = torch.abs(g[m] - d[m]).sum() + 0.2 * torch.abs(gc - c).sum()      # src/Mapper.py:457-469 as torch ops
+        else:
+            loss = M.mapper_loss(d, c, w, g, gc, 0.2, False, True)                   # the same loss as one kernel (+ gradient)
         loss.backward()
         return loss
 
@@ -325,7 +350,9 @@ def run_ours(args):
         step_gbs = value / world * BYTES_PER_RAY[STAGE] / 1e9
         roofline = {"bound": "hbm", "kernel": top_op + " (" + " + ".join(k for k in kernels if k in kt) + ")",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": ncu_traffic(kernels) if (n == 65536 and world == 1) else None,
+                    "traffic_source": NCU_SUMMARY + " (dram read+write of these kernels' launches in one step, ncu --set full)",
+                    "peak_source": peak_src,
                     "kernel_share_of_step": op_ms[top_op] * prof_steps / total_kernel_ms if total_kernel_ms else None,
                     "algorithmic_bytes_per_step": bytes_per_step, "op_ms_per_step": op_ms[top_op],
                     "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak,
@@ -341,7 +368,7 @@ def run_ours(args):
                        "tsdf": list(scene.tsdf_volume.shape[2:]), "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": f"ray-sharded dp{world}" + (" + NCCL all-reduce of grid/decoder grads" if world > 1 else ""),
                        "mlp": "tcgen05 3xTF32 tensor-core path" if os.environ.get("DFP_TENSOR_CORES", "1") != "0" else "fp32 SIMT",
-                       "loss": "Mapper depth L1 + 0.2 colour L1"},
+                       "loss": "Mapper depth L1 + 0.2 colour L1" + (" (torch ops)" if args.torch_loss else " (mapper_ops.mapper_loss kernel)")},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
@@ -369,6 +396,7 @@ def main():
     ap.add_argument("--channels-first", action="store_true", help="keep the grids channels-first (transposed per call)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-small", action="store_true")
+    ap.add_argument("--torch-loss", action="store_true", help="Mapper loss as torch ops (boolean indexing, host sync) instead of the loss kernel")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
