@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                 for (int kk = 0; kk < 16; ++kk) {
                     const int k = ch * 32 + c0 + kk;
                     float s1 = (k == EMB) ? 1.f : 0.f, c1 = 0.f;    // column 93 of the sin array: constant 1 (bias of block 0 in kernel 2)
-                    if (k < EMB) sincos_cw(embed_arg(sm + T::S_B, pf, k), s1, c1);
+                    if (k < EMB) sincos_sfu(embed_arg(sm + T::S_B, pf, k), s1, c1);
                     sn[kk] = s1;
                     da[kk] = de[kk] * c1;
                 }
@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                     for (int u = 0; u < 16; ++u) if (u == kk) { sn[u] = s1; da[u] = de[u] * c1; }
                 }
             }
+            if (a.dp != nullptr) {                            // d(point) through the embedding: Tracker only
 #pragma unroll
             for (int kk = 0; kk < 16; ++kk) {
                 const int k = ch * 32 + c0 + kk;
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                     gp1 = fmaf(sm[T::S_B + EMB_PAD + k], da[kk], gp1);
                     gp2 = fmaf(sm[T::S_B + 2 * EMB_PAD + k], da[kk], gp2);
                 }
+            }
             }
             if (a.gparams) {
                 pl::store16(reinterpret_cast<unsigned char*>(a.sc_e), pl::F_EX, i_raw, ch * 32 + c0, sn);

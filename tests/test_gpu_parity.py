@@ -17,9 +17,27 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def rel_err(a, b):
+MARGINS = {}
+
+
+def rel_err(a, b, tag=None):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
-    return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+    e = float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+    if tag is not None:
+        MARGINS[tag] = max(MARGINS.get(tag, 0.0), e)
+    return e
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_margins():
+    """With DFP_PARITY_LOG=<file> the measured errors of the tagged comparisons are written out (profiles/ evidence)."""
+    yield
+    import json
+    import os
+    path = os.environ.get("DFP_PARITY_LOG")
+    if path and MARGINS:
+        with open(path, "w") as f:
+            json.dump(MARGINS, f, indent=1, sort_keys=True)
 
 
 def build(inp, channels_last=False):
@@ -218,16 +236,17 @@ def test_room0_mapping_batch_matches_oracle():
     renderer = A.Renderer(default_cfg(), None, slam_namespace(scene.bound, sc.tsdf_bnds))
     d, u, c, w = renderer.render_batch_ray(grids, model, rays_d.to(DEV), rays_o.to(DEV), DEV, sc.tsdf_volume, sc.tsdf_bnds,
                                            "color", gt_depth=gt.to(DEV))
-    assert rel_err(d, d_ref) <= 1e-4 and rel_err(u, u_ref) <= 1e-4 and rel_err(c, c_ref) <= 1e-4 and rel_err(w, w_ref) <= 1e-4
+    assert rel_err(d, d_ref, "room0_1000.depth") <= 1e-4 and rel_err(u, u_ref, "room0_1000.uncertainty") <= 1e-4
+    assert rel_err(c, c_ref, "room0_1000.color") <= 1e-4 and rel_err(w, w_ref, "room0_1000.weight") <= 1e-4
     gtd = gt.to(DEV)
     m = gtd > 0
     (torch.abs(gtd[m] - d[m]).sum() + 0.2 * torch.abs(gt_color.to(DEV) - c).sum()).backward()
     for k in grids:
-        assert rel_err(grids[k].grad, grids_cpu[k].grad) <= 1e-3, k
+        assert rel_err(grids[k].grad, grids_cpu[k].grad, "room0_1000.grad." + k) <= 1e-3, k
     named = dict(model.named_parameters())
     for k, v in params.items():
         if v.grad is not None and float(v.grad.abs().max()) > 0:
-            assert rel_err(named[k].grad, v.grad) <= 1e-3, k
+            assert rel_err(named[k].grad, v.grad, "room0_1000.grad.decoders(max over tensors)") <= 1e-3, k
 
 
 def test_properties_at_full_size():
