@@ -527,6 +527,10 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
     // tensor-core backward (needs the activations saved by the tensor-core forward): K1 = delta chain, K2 = weight grads
     const bool tcb = use_tensor_cores() && (flags & DFP_FLAG_SAVE_ACT) && w.act_h[0] != nullptr && tc_backward_level() > 0;
     da.sc_e = w.sc_e; da.sc_dh = w.sc_dh; da.sc_darg = w.sc_darg; da.sc_dl1 = w.sc_dl1;
+    {   // timing experiments (results become wrong): which part of K1 costs what
+        static const int dbg = getenv("DFP_DEBUG_SKIP") ? atoi(getenv("DFP_DEBUG_SKIP")) : 0;
+        da.dbg = dbg;
+    }
     auto run = [&](auto dec_tag) -> int {
         constexpr int DEC = decltype(dec_tag)::value;
         if (!tcb) return launch_decoder_bwd<DEC, MODE>(da, st);

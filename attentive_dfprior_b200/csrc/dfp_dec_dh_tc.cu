@@ -87,6 +87,10 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float part[2][6][128];                                  // d(point) partial sums of the upper halves
+    // feature gradients of a tile (rows padded against bank conflicts) and each sample's cell / continuous index, for the
+    // cooperative scatter: carved from the dynamic allocation behind the weights
+    float (*s_dc)[128][36] = reinterpret_cast<float (*)[128][36]>(sm + T::FLOATS);
+    int (*s_tri)[128][6] = reinterpret_cast<int (*)[128][6]>(sm + T::FLOATS + 2 * 128 * 36);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int grp = tid >> 8, gt = tid & 255;
@@ -108,6 +112,8 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
     const int64_t n = dec_items(a);
     const int64_t tiles = (n + 127) / 128;
     const bool issuer = (gt == 0);
+    const bool planes = a.gparams != nullptr && !(a.dbg & 1);
+    const bool do_mma = !(a.dbg & 4);
     const float bmax = embed_bmax(sm + T::S_B);
     const int c0 = 16 * hf;
 
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             float dacc[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) dacc[j] = ((m >> j) & 1u) ? dh[j] : 0.f;
-            if (a.gparams) {                                  // operands of kernel 2 (rows past the end carry zero deltas)
+            if (planes) {                                     // operands of kernel 2 (rows past the end carry zero deltas)
                 pl::store16(reinterpret_cast<unsigned char*>(a.sc_dh), pl::F_DH, i_raw, i * 32 + c0, dh);
                 pl::store16(reinterpret_cast<unsigned char*>(a.sc_darg), pl::F_DL0, i_raw, 8 + pl::dl0_pos(i) * 32 + c0, dacc);
                 if (i == 3) pl::store16(reinterpret_cast<unsigned char*>(a.sc_dl1), pl::F_DL1, i_raw, c0, dacc);
@@ -162,9 +168,9 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             tc::named_bar_sync(3 + grp, 256);
             if (issuer) {
                 tc::fence_after_sync();
-                tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + (T::WC + i * 1024) * 4, wlo + (T::WC + i * 1024) * 4,
+                if (do_mma) tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + (T::WC + i * 1024) * 4, wlo + (T::WC + i * 1024) * 4,
                                   32, 32, 4096u, i != 4);
-                tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A + 64, tb + T::T_A + 96, whi + (T::WH + (i - 1) * 1024) * 4,
+                if (do_mma) tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A + 64, tb + T::T_A + 96, whi + (T::WH + (i - 1) * 1024) * 4,
                                   wlo + (T::WH + (i - 1) * 1024) * 4, 32, 32, 4096u, false);
                 tc::mma_commit(bar);
             }
@@ -179,20 +185,20 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
         }
         // block 0: fc_c[0] path, then the embedding
         {
-            if (a.gparams) pl::store16(reinterpret_cast<unsigned char*>(a.sc_dh), pl::F_DH, i_raw, c0, dh);
+            if (planes) pl::store16(reinterpret_cast<unsigned char*>(a.sc_dh), pl::F_DH, i_raw, c0, dh);
             tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 32, dh);
             tc::wait_st();
             tc::fence_before_sync();
             tc::named_bar_sync(3 + grp, 256);
             if (issuer) {
                 tc::fence_after_sync();
-                tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + T::WC * 4, wlo + T::WC * 4, 32, 32, 4096u, true);
+                if (do_mma) tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + T::WC * 4, wlo + T::WC * 4, 32, 32, 4096u, true);
                 tc::mma_commit(bar);
             }
             const uint32_t m0 = m_next >> c0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) dh[j] = ((m0 >> j) & 1u) ? dh[j] : 0.f;      // dacc_0
-            if (a.gparams) {
+            if (planes) {
                 pl::store16(reinterpret_cast<unsigned char*>(a.sc_dl1), pl::F_DL1, i_raw, 32 + c0, dh);
                 if (hf == 0) {                                // upstream gradient, padded to 8 columns
                     float d8[8];
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             tc::named_bar_sync(3 + grp, 256);
             if (issuer) {
                 tc::fence_after_sync();
-                tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A, tb + T::T_A + 64, whi + T::W03 * 4, wlo + T::W03 * 4, 64, 96, 8192u, false);
+                if (do_mma) tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A, tb + T::T_A + 64, whi + T::W03 * 4, wlo + T::W03 * 4, 64, 96, 8192u, false);
                 tc::mma_commit(bar);
             }
         }
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                 for (int kk = 0; kk < 16; ++kk) {
                     const int k = ch * 32 + c0 + kk;
                     float s1 = (k == EMB) ? 1.f : 0.f, c1 = 0.f;    // column 93 of the sin array: constant 1 (bias of block 0 in kernel 2)
-                    if (k < EMB) sincos_sfu(embed_arg(sm + T::S_B, pf, k), s1, c1);
+                    if (k < EMB && !(a.dbg & 8)) sincos_sfu(embed_arg(sm + T::S_B, pf, k), s1, c1);
                     sn[kk] = s1;
                     da[kk] = de[kk] * c1;
                 }
@@ -264,12 +270,12 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                 }
             }
             }
-            if (a.gparams) {
+            if (planes) {
                 pl::store16(reinterpret_cast<unsigned char*>(a.sc_e), pl::F_EX, i_raw, ch * 32 + c0, sn);
                 pl::store16(reinterpret_cast<unsigned char*>(a.sc_dl1), pl::F_DL1, i_raw, 64 + ch * 32 + c0, da);
             }
         }
-        if (a.gparams && hf == 0) {                           // the point itself (A operand of embedder._B's gradient)
+        if (planes && hf == 0) {                              // the point itself (A operand of embedder._B's gradient)
             const float p8[8] = {pf[0], pf[1], pf[2], 0.f, 0.f, 0.f, 0.f, 0.f};
             pl::store8(reinterpret_cast<unsigned char*>(a.sc_e), pl::F_EX, i_raw, 96, p8);
         }
@@ -278,8 +284,44 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
         tc::wait_ld();
         const bool want_coord = a.dp != nullptr;
         float gn[3] = {0.f, 0.f, 0.f};
-        if (a.ggrid && !want_coord) scatter_features16_agg(a.grid, a.ggrid, tri, hf, d_c, valid && any);     // whole warp
-        else if (valid && any && (a.ggrid || want_coord)) scatter_features16(a.grid, a.ggrid, tri, hf, d_c, want_coord, gn);
+        if (a.dbg & 2) {
+        } else if (a.ggrid && !want_coord) {
+            // Cooperative scatter.  A thread's own reduction would touch 32 different lines per warp instruction (one
+            // 16-byte piece per lane, ~2 cycles of the load/store unit each: measured, this was half of the kernel).
+            // Instead the tile's feature gradients go through shared memory and eight lanes add one corner's whole
+            // 128-byte line (32 channels): four lines per warp instruction.
+            {
+                float* row = &s_dc[grp][r][16 * hf];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(row + 4 * q) = make_float4(d_c[4 * q], d_c[4 * q + 1], d_c[4 * q + 2], d_c[4 * q + 3]);
+                if (hf == 0) {
+                    int* tr = &s_tri[grp][r][0];
+                    tr[0] = (valid && any) ? tri.x0 : -1;     // -1: no gradient for this sample
+                    tr[1] = tri.y0; tr[2] = tri.z0;
+                    tr[3] = __float_as_int(tri.ix); tr[4] = __float_as_int(tri.iy); tr[5] = __float_as_int(tri.iz);
+                }
+            }
+            tc::named_bar_sync(3 + grp, 256);
+            const int sub = gt >> 3, q = gt & 7;
+#pragma unroll 1
+            for (int it = 0; it < 32; ++it) {
+                const int pair = it * 32 + sub;               // (sample, corner): the 4 sub-groups of a warp share the sample
+                const int smp = pair >> 3, cn = pair & 7;
+                const int* tr = &s_tri[grp][smp][0];
+                Tri t;
+                t.x0 = tr[0];
+                if (t.x0 < 0) continue;
+                t.y0 = tr[1]; t.z0 = tr[2];
+                t.ix = __int_as_float(tr[3]); t.iy = __int_as_float(tr[4]); t.iz = __int_as_float(tr[5]);
+                int x, y, z;
+                if (!tri_corner(t, cn, a.grid.W, a.grid.H, a.grid.D, x, y, z)) continue;
+                const float wgt = tri_weight(t, cn);
+                const float4 v = *reinterpret_cast<const float4*>(&s_dc[grp][smp][4 * q]);
+                red_add_v4(a.ggrid + (((int64_t)z * a.grid.H + y) * a.grid.W + x) * CDIM + 4 * q, v.x * wgt, v.y * wgt, v.z * wgt, v.w * wgt);
+            }
+        } else if (valid && any && (a.ggrid || want_coord)) {
+            scatter_features16(a.grid, a.ggrid, tri, hf, d_c, want_coord, gn);
+        }
         if (want_coord) {                                            // uniform: the two halves of a sample add up in the lower one
             if (hf == 1) {
                 part[grp][0][r] = gn[0]; part[grp][1][r] = gn[1]; part[grp][2][r] = gn[2];
@@ -302,7 +344,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
 
 template <int DEC, int MODE>
 int launch_decoder_dh_tc(const DecArgs& a, cudaStream_t st) {
-    const size_t smem = DhLayout::FLOATS * sizeof(float) + 1024;
+    const size_t smem = (DhLayout::FLOATS + 2 * 128 * 36 + 2 * 128 * 6) * sizeof(float) + 1024;
     int rc = set_smem(k_decoder_dh_tc<DEC, MODE>, smem);
     if (rc) return rc;
     const int64_t tiles = (a.n + 127) / 128;

@@ -270,7 +270,7 @@ __device__ __forceinline__ void scatter_features16(const DfpGrid& g, float* ggri
 // segmented shuffle reduction and only the head lane of a run issues the vector reductions, which cuts the number of
 // atomics that serialise on hot voxels in L2.  Must be called by all 32 lanes; `active` masks lanes without a gradient.
 __device__ __forceinline__ void scatter_features16_agg(const DfpGrid& g, float* ggrid, const Tri& t, int hf, const float (&dc)[16],
-                                                       bool active) {
+                                                       bool active, int dbg = 0) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int cell = active ? (t.z0 * g.H + t.y0) * g.W + t.x0 : -1 - lane;       // inactive lanes never merge
@@ -278,7 +278,8 @@ __device__ __forceinline__ void scatter_features16_agg(const DfpGrid& g, float* 
     const unsigned same = __ballot_sync(full, lane < 31 && nxt == cell);          // bit i: lanes i and i+1 share a cell
     const int run = __ffs(~(same >> lane)) - 1;                                   // lanes after this one that continue its run
     const bool head = active && (lane == 0 || !((same >> (lane - 1)) & 1u));
-    const int maxrun = __reduce_max_sync(full, run);
+    int maxrun = __reduce_max_sync(full, run);
+    if (dbg & 32) maxrun = 0;                                                      // timing experiment: no aggregation (double counts)
 #pragma unroll 1
     for (int cn = 0; cn < 8; ++cn) {
         int x, y, z;
@@ -298,8 +299,13 @@ __device__ __forceinline__ void scatter_features16_agg(const DfpGrid& g, float* 
         }
         if (head && ok) {
             float* dst = ggrid + (((int64_t)z * g.H + y) * g.W + x) * CDIM + 16 * hf;
+            if (dbg & 16) {                                                        // timing experiment: plain stores instead of reductions
 #pragma unroll
-            for (int q = 0; q < 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
         }
     }
 }
@@ -331,6 +337,7 @@ struct DecArgs {
     // saved activations / scratch by list position.  Used for the high decoder, whose output and gradient only matter
     // on TSDF-band samples (decoder.py:326-333: f_add_m_occ is read under the band mask only).
     const int* list; const int* count;
+    int dbg;                       // DFP_DEBUG_SKIP bits (timing experiments only): 1 plane stores, 2 scatter, 4 chain MMAs, 8 sincos
 };
 // number of work items and the sample id of item idx
 __device__ __forceinline__ int64_t dec_items(const DecArgs& a) { return a.list ? (int64_t)*a.count : a.n; }
