@@ -28,6 +28,8 @@ struct TcLayout {                                   // shared memory, in floats
     static constexpr int S_BO = S_WO + 128;         // [4]
     static constexpr int FLOATS = S_BO + 4;
     static constexpr int GROUPS = (CD == 32) ? 2 : 1;
+    static constexpr int GATHER = (FLOATS + 3) / 4 * 4;                                   // staging of the cooperative gather
+    static constexpr int TOTAL = GATHER + GROUPS * 128 * (CD + 4) + GROUPS * 128 * (CD == 64 ? 12 : 6);
     // TMEM columns of one group
     static constexpr int T_C_HI = 0, T_C_LO = CD, T_X_HI = 2 * CD, T_X_LO = 2 * CD + 32;
     static constexpr int T_D03 = 2 * CD + 64, T_DH = 2 * CD + 128, T_DC = 2 * CD + 160;
@@ -82,6 +84,11 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float part[2][4][128];                                  // output-layer partial sums of the upper halves
+    // cooperative gather staging behind the weights: interpolated features [group][128][CD + 4] (padded rows) and the
+    // samples' cell / continuous index per grid
+    constexpr int C_W = CD + 4, TRI_W = (DEC == 1) ? 12 : 6;
+    float* s_c = sm + T::GATHER;
+    int* s_tri = reinterpret_cast<int*>(s_c + T::GROUPS * 128 * C_W);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int grp = tid >> 8, gt = tid & 255;                         // group, thread within the group
@@ -116,9 +123,60 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
         normalize(p, box, xn);
         const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
         const bool fast = embed_fast_ok(pf, bmax);
-        {   // trilinear features (this half's 16 channels) -> A_C
+        {   // trilinear features -> A_C.  Cooperative gather: a thread fetching its own 16 channels touches 32 different
+            // lines per warp instruction (one 16-byte piece per lane); instead eight lanes fetch one corner's whole
+            // 128-byte line and the interpolated features go to their owners through shared memory.
+            if (hf == 0) {
+                const Tri t0 = tri_setup(xn, a.grid.W, a.grid.H, a.grid.D);
+                int* tr = &s_tri[grp * 128 * TRI_W + r * TRI_W];
+                tr[0] = t0.x0; tr[1] = t0.y0; tr[2] = t0.z0;
+                tr[3] = __float_as_int(t0.ix); tr[4] = __float_as_int(t0.iy); tr[5] = __float_as_int(t0.iz);
+                if (DEC == 1) {
+                    const Tri t1 = tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D);
+                    tr[6] = t1.x0; tr[7] = t1.y0; tr[8] = t1.z0;
+                    tr[9] = __float_as_int(t1.ix); tr[10] = __float_as_int(t1.iy); tr[11] = __float_as_int(t1.iz);
+                }
+            }
+            tc::named_bar_sync(3 + grp, 256);
+            {
+                const int sub = gt >> 3, q = gt & 7;
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    const int smp = j * 32 + sub;
+                    const int* tr = &s_tri[grp * 128 * TRI_W + smp * TRI_W];
+#pragma unroll
+                    for (int gsel = 0; gsel < (DEC == 1 ? 2 : 1); ++gsel) {
+                        const DfpGrid& g = gsel == 0 ? a.grid : a.grid_low;
+                        Tri t;
+                        t.x0 = tr[6 * gsel]; t.y0 = tr[6 * gsel + 1]; t.z0 = tr[6 * gsel + 2];
+                        t.ix = __int_as_float(tr[6 * gsel + 3]); t.iy = __int_as_float(tr[6 * gsel + 4]); t.iz = __int_as_float(tr[6 * gsel + 5]);
+                        float4 v[8];
+                        float wgt[8];
+#pragma unroll
+                        for (int cn = 0; cn < 8; ++cn) {
+                            int x, y, z;
+                            const bool ok = tri_corner(t, cn, g.W, g.H, g.D, x, y, z);
+                            wgt[cn] = tri_weight(t, cn);
+                            v[cn] = ok ? __ldg(reinterpret_cast<const float4*>(g.data + (((int64_t)z * g.H + y) * g.W + x) * CDIM) + q)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int cn = 0; cn < 8; ++cn) {
+                            acc.x = fmaf(v[cn].x, wgt[cn], acc.x); acc.y = fmaf(v[cn].y, wgt[cn], acc.y);
+                            acc.z = fmaf(v[cn].z, wgt[cn], acc.z); acc.w = fmaf(v[cn].w, wgt[cn], acc.w);
+                        }
+                        *reinterpret_cast<float4*>(&s_c[(grp * 128 + smp) * C_W + 32 * gsel + 4 * q]) = acc;
+                    }
+                }
+            }
+            tc::named_bar_sync(3 + grp, 256);
             float c[16];
-            gather_features16(a.grid, tri_setup(xn, a.grid.W, a.grid.H, a.grid.D), hf, c);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 v = *reinterpret_cast<const float4*>(&s_c[(grp * 128 + r) * C_W + 16 * hf + 4 * q4]);
+                c[4 * q4] = v.x; c[4 * q4 + 1] = v.y; c[4 * q4 + 2] = v.z; c[4 * q4 + 3] = v.w;
+            }
             tc::tmem_store_split16(tl + T::T_C_HI, tl + T::T_C_LO, c);
             // saved operands go out as bf16 planes at the row's own position (every row of a tile is written: rows past
             // the end repeat the last sample, their deltas are zero in the backward)
@@ -127,7 +185,11 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                 if (hf == 0) pl::store_ones8(reinterpret_cast<unsigned char*>(a.act_c), pl::f_cx(CD), i_raw, CD);
             }
             if (DEC == 1) {
-                gather_features16(a.grid_low, tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D), hf, c);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 v = *reinterpret_cast<const float4*>(&s_c[(grp * 128 + r) * C_W + 32 + 16 * hf + 4 * q4]);
+                    c[4 * q4] = v.x; c[4 * q4 + 1] = v.y; c[4 * q4 + 2] = v.z; c[4 * q4 + 3] = v.w;
+                }
                 tc::tmem_store_split16(tl + T::T_C_HI + 32, tl + T::T_C_LO + 32, c);
                 if (a.act_c) pl::store16(reinterpret_cast<unsigned char*>(a.act_c), pl::f_cx(CD), i_raw, 32 + 16 * hf, c);
             }
@@ -257,7 +319,7 @@ template <int DEC, int MODE>
 int launch_decoder_fwd_tc(const DecArgs& a, cudaStream_t st) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
     using T = TcLayout<CD>;
-    const size_t smem = T::FLOATS * sizeof(float);
+    const size_t smem = T::TOTAL * sizeof(float);
     int rc = set_smem(k_decoder_fwd_tc<DEC, MODE>, smem);
     if (rc) return rc;
     const int64_t tiles = (a.n + 127) / 128;
