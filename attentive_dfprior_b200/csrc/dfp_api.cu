@@ -146,6 +146,8 @@ static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with
     w.sc_dh = (float*)take(act ? pl::array_bytes(nsp, pl::F_DH) : 0);
     w.sc_darg = (float*)take(act ? pl::array_bytes(nsp, pl::F_DL0) : 0);
     w.sc_dl1 = (float*)take(act ? pl::array_bytes(nsp, pl::F_DL1) : 0);
+    w.att_act = (float*)take(act && stage >= DFP_STAGE_HIGH ? (size_t)nsp * ATT_ACT * 4 : 0);
+    if (!(act && stage >= DFP_STAGE_HIGH)) w.att_act = nullptr;
     return off;
 }
 
@@ -499,6 +501,7 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
         memset(&aa, 0, sizeof(aa));
         aa.params = params; aa.band_list = w.band_list; aa.band_count = w.band_count;
         aa.low = w.low; aa.high = w.high; aa.tsdf = w.tsdf; aa.fused = w.fused; aa.w_attn = w.w_attn;
+        aa.act = (flags & DFP_FLAG_SAVE_ACT) ? w.att_act : nullptr;
         if ((rc = launch_attn_fwd(aa, n, st))) return rc;
     }
     return DFP_OK;
@@ -518,6 +521,7 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
         aa.ps = ps; aa.tsdf_bnds = to_bounds(sc->tsdf_bnds); aa.vol = sc->tsdf;
         aa.d_fused = w.d_fused; aa.g_w = g_w; aa.d_low = w.d_low; aa.d_high = w.d_high;
         aa.dp = want_dp ? w.dp : nullptr; aa.gparams = g->params_packed;
+        aa.act = (flags & DFP_FLAG_SAVE_ACT) ? w.att_act : nullptr;
         if ((rc = launch_attn_bwd<MODE>(aa, n, st))) return rc;
     }
     DecArgs da;

@@ -22,6 +22,19 @@ __global__ void __launch_bounds__(NT) k_attn_fwd(const AttArgs a) {
         const float f = attention_fwd_thread(A, x0, x1, w, st);
         a.fused[s] = f;
         a.w_attn[s] = w;
+        if (a.act) {                                           // kept for the backward (DFP_FLAG_SAVE_ACT): no recompute there
+            float* dst = a.act + att_act_index(i, 0);
+#pragma unroll 8
+            for (int k = 0; k < 64; ++k) dst[k * 32] = st.h1[k];
+#pragma unroll 8
+            for (int k = 0; k < 128; ++k) dst[(64 + k) * 32] = st.h2[k];
+#pragma unroll 8
+            for (int k = 0; k < 128; ++k) dst[(192 + k) * 32] = st.h3[k];
+#pragma unroll 8
+            for (int k = 0; k < 64; ++k) dst[(320 + k) * 32] = st.h4[k];
+            dst[384 * 32] = st.a0;
+            dst[385 * 32] = st.a1;
+        }
     }
 }
 
@@ -50,8 +63,22 @@ __global__ void __launch_bounds__(NT) k_attn_bwd(const AttArgs a) {
         const float x0 = a.high[s] + a.low[s];
         const AttLogit lg = tsdf_logit(a.tsdf[s]);
         AttState st;
-        float w;
-        attention_fwd_thread(A, x0, lg.inv, w, st);
+        if (a.act) {                                           // activations saved by k_attn_fwd
+            const float* src = a.act + att_act_index(valid ? i : count - 1, 0);
+#pragma unroll 8
+            for (int k = 0; k < 64; ++k) st.h1[k] = src[k * 32];
+#pragma unroll 8
+            for (int k = 0; k < 128; ++k) st.h2[k] = src[(64 + k) * 32];
+#pragma unroll 8
+            for (int k = 0; k < 128; ++k) st.h3[k] = src[(192 + k) * 32];
+#pragma unroll 8
+            for (int k = 0; k < 64; ++k) st.h4[k] = src[(320 + k) * 32];
+            st.a0 = src[384 * 32];
+            st.a1 = src[385 * 32];
+        } else {
+            float w;
+            attention_fwd_thread(A, x0, lg.inv, w, st);
+        }
         float dx0, dx1;
         attention_bwd_thread<WANT_PARAMS>(A, OFF_ATT, x0, lg.inv, st, g_out, g_w, dx0, dx1, sink);
         if (valid) {

@@ -101,6 +101,7 @@ struct Ws {                        // per-sample workspace arrays (NS samples)
     float* sc_dh;                  // DH:  gradient of each block's output (before the ReLU mask)
     float* sc_darg;                // DL0: upstream gradient and masked deltas of blocks 4, 2, 1, 3
     float* sc_dl1;                 // DL1: masked deltas of blocks 3, 0 and the gradient of the embedding arguments
+    float* att_act;                // fusion MLP activations per band-list position (AttArgs::act)
 };
 
 
@@ -354,7 +355,11 @@ struct AttArgs {
     // backward
     PointSrc ps; Bounds tsdf_bnds; DfpTsdf vol;
     const float* d_fused; const float* g_w; float* d_low; float* d_high; float* dp; float* gparams;
+    float* act;                    // saved activations of the fusion MLP (ATT_ACT floats per band-list position), or null
 };
+// h1 (64) | h2 (128) | h3 (128) | h4 (64) | a0 a1 | pad: index ((pos/32)*ATT_ACT + f)*32 + pos%32, so a warp's 32 positions coalesce
+constexpr int ATT_ACT = 388;
+__device__ __forceinline__ int64_t att_act_index(int pos, int f) { return ((int64_t)(pos >> 5) * ATT_ACT + f) * 32 + (pos & 31); }
 
 
 // ------------------------------------------------------------------------------------------
