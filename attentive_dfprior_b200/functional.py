@@ -143,19 +143,29 @@ def _needed_grids(stage):
 
 
 def _grads_struct(ctx, needs_grid, need_params, dev):
-    """Allocate zeroed gradient sinks and the C struct pointing at them."""
+    """Allocate zeroed gradient sinks and the C struct pointing at them.
+
+    All sinks are views of ONE flat zero-filled buffer (one memset; one all-reduce when the batch is sharded over
+    ranks).  Grid gradients are channels-last views ([1,C,D,H,W] logical shape over an NDHWC slice)."""
     g = L.DfpGrads()
-    ggrids = {}
-    for key in GRID_KEYS:
-        if needs_grid.get(key) and ctx.grids_cl.get(key) is not None:
-            t = torch.zeros_like(ctx.grids_cl[key], memory_format=torch.preserve_format)
-            ggrids[key] = t
-            setattr(g, key, t.data_ptr())
+    want = [k for k in GRID_KEYS if needs_grid.get(k) and ctx.grids_cl.get(k) is not None]
+    sizes = [ctx.grids_cl[k].numel() for k in want]
+    npk = int(L.lib().dfp_packed_param_floats()) if need_params else 0
+    pad = lambda n: (n + 63) // 64 * 64                              # keep every slice 256-byte aligned
+    total = sum(pad(n) for n in sizes) + npk
+    flat = torch.zeros(total, device=dev, dtype=torch.float32) if total else None
+    ggrids, off = {}, 0
+    for k, n in zip(want, sizes):
+        _, C_, D_, H_, W_ = ctx.grids_cl[k].shape
+        t = flat[off:off + n].view(1, D_, H_, W_, C_).permute(0, 4, 1, 2, 3)
+        ggrids[k] = t
+        setattr(g, k, t.data_ptr())
+        off += pad(n)
     gp = None
     if need_params:
-        gp = torch.zeros(int(L.lib().dfp_packed_param_floats()), device=dev, dtype=torch.float32)
+        gp = flat[off:off + npk]
         g.params_packed = gp.data_ptr()
-    return g, ggrids, gp
+    return g, ggrids, gp, flat
 
 
 def _param_grads(gp, params, needs):
@@ -216,7 +226,7 @@ class _RenderBatchRay(torch.autograd.Function):
         needs_grid = {"grid_low": need[3], "grid_high": need[4], "grid_color": need[5]}
         need_params = any(need[6:])
         with torch.cuda.device(dev):
-            g, ggrids, gp = _grads_struct(k, needs_grid, need_params, dev)
+            g, ggrids, gp, flat = _grads_struct(k, needs_grid, need_params, dev)
             d_o = torch.empty_like(k.ro) if (need[1] or need[2]) else None
             d_d = torch.empty_like(k.rd) if (need[1] or need[2]) else None
             g.rays_o, g.rays_d = _ptr(d_o), _ptr(d_d)
@@ -239,11 +249,8 @@ class _RenderBatchRay(torch.autograd.Function):
             if aux.group is not None:
                 # ray-sharded data parallelism: sum the replicated state's gradients over the ranks (NCCL)
                 import torch.distributed as dist
-                works = [dist.all_reduce(t, group=aux.group, async_op=True) for t in ggrids.values()]
-                if gp is not None:
-                    works.append(dist.all_reduce(gp, group=aux.group, async_op=True))
-                for wk in works:
-                    wk.wait()
+                if flat is not None:
+                    dist.all_reduce(flat, group=aux.group)           # grids + packed parameters in one collective
             pgrads = _param_grads(gp, k.params, need[6:])
         return (None, d_o if need[1] else None, d_d if need[2] else None,
                 ggrids.get("grid_low"), ggrids.get("grid_high"), ggrids.get("grid_color"), *pgrads)
@@ -319,7 +326,7 @@ class _EvalPoints(torch.autograd.Function):
         needs_grid = {"grid_low": need[2], "grid_high": need[3], "grid_color": need[4]}
         need_params = any(need[5:])
         with torch.cuda.device(dev):
-            g, ggrids, gp = _grads_struct(k, needs_grid, need_params, dev)
+            g, ggrids, gp, flat = _grads_struct(k, needs_grid, need_params, dev)
             d_p = torch.empty_like(k.p) if need[1] else None
             g.points = _ptr(d_p)
             gr = g_raw.detach().float().contiguous() if g_raw is not None else None
