@@ -33,6 +33,14 @@ def chunk_aligned_range(n: int, chunk: int, rank: int, world: int):
     return min(lo * chunk, n), min(hi * chunk, n)
 
 
+def interleaved_shard(n: int, rank: int, world: int) -> torch.Tensor:
+    """Indices rank, rank + world, rank + 2*world, ... < n.  Dealing a mapping batch (rays of several keyframes, frame
+    after frame) to the ranks this way gives every rank the same mix of frames; a contiguous split (``shard_range``)
+    hands each rank whole frames, and the cost of a ray depends on its frame's pose (how much of it lies inside the
+    bound / the TSDF band), which showed up as a 15 % load imbalance at 8 GPUs."""
+    return torch.arange(rank, n, world, dtype=torch.int64)
+
+
 def global_depth_max(gt_depth: torch.Tensor, group) -> torch.Tensor:
     import torch.distributed as dist
     m = gt_depth.detach().float().max().reshape(1)

@@ -229,6 +229,8 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
+        if os.environ.get("BENCH_NO_COLLECTIVE") == "1":     # experiment: independent replicas (no gradient exchange)
+            group = None
     L.lib()
 
     n = args.rays                                   # rays per GPU per step (weak scaling)
@@ -238,8 +240,13 @@ def run_ours(args):
     renderer = A.Renderer(default_cfg(), None, slam_namespace(scene.bound, scene.tsdf_bnds))
     grids = {k: v.requires_grad_(True) for k, v in scene.grids.items()}
     params = list(model.parameters())
-    # every rank draws its own rays of the same synthetic frame
-    rays_o, rays_d, gt, gt_color = synth.make_rays(scene, n, seed=100 + rank, device=dev)
+    # the global batch is n rays from each of `world` synthetic keyframes (one camera pose per frame); it is dealt to
+    # the ranks interleaved, so every rank renders the same mix of frames (a contiguous split gives each rank one
+    # frame, whose cost differs by up to 15 % with the pose: measured, profiles/r01 scaling notes)
+    parts = [synth.make_rays(scene, n, seed=100 + k, device=dev) for k in range(world)]
+    mine = D.interleaved_shard(n * world, rank, world).to(dev)
+    rays_o, rays_d, gt, gt_color = (torch.cat([p[i] for p in parts])[mine].contiguous() for i in range(4))
+    del parts
     host = [t.cpu().pin_memory() for t in (rays_o, rays_d, gt, gt_color)]
     h2d = sum(t.numel() * t.element_size() for t in host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -292,6 +299,8 @@ def run_ours(args):
         clocks = sampler.stop() if sampler else None
         launches = L.launch_count() - l0
         ms = sum(a.elapsed_time(b) for a, b in evs)
+        if os.environ.get("BENCH_RANK_TIMES") == "1":          # diagnostics: every rank's own time (stderr)
+            print(f"[rank {rank}] {ms / steps:.3f} ms/step", file=sys.stderr, flush=True)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if group is not None:
             torch.distributed.barrier()

@@ -53,3 +53,17 @@ def _worker(rank, world, port):
 
 def test_gloo_world2():
     mp.spawn(_worker, args=(2, 29533), nprocs=2, join=True)
+
+
+def test_interleaved_shard_partitions_the_batch():
+    from attentive_dfprior_b200 import dist as D
+    n, world = 1003, 8
+    shards = [D.interleaved_shard(n, r, world) for r in range(world)]
+    allidx = torch.cat(shards).sort().values
+    assert torch.equal(allidx, torch.arange(n))
+    assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+    # every rank sees every contiguous block (frame) of the batch in the same proportion
+    block = n // 4
+    for s in shards:
+        counts = [int(((s >= b * block) & (s < (b + 1) * block)).sum()) for b in range(4)]
+        assert max(counts) - min(counts) <= 1
