@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
 #pragma unroll
                 for (int kk = 0; kk < 16; ++kk) {
                     const int k = ch * 32 + 16 * hf + kk;
-                    e[kk] = (k < EMB) ? sin_sfu(embed_arg(sm + T::S_B, pf, k)) : 0.f;
+                    e[kk] = (k < EMB) ? sin_cw(embed_arg(sm + T::S_B, pf, k)) : 0.f;   // full-precision polynomial: forward errors move ReLU masks
                 }
             } else {
 #pragma unroll 1

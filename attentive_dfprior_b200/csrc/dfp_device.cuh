@@ -218,15 +218,16 @@ __device__ __forceinline__ void scatter_features(const DfpGrid& g, float* ggrid,
     gn[0] = gx * t.gx; gn[1] = gy * t.gy; gn[2] = gz * t.gz;
 }
 
-// sin / cos of an embedding argument for the tensor-core kernels: two-constant Cody-Waite reduction to [-pi, pi] (exact
+// sin / cos of an embedding argument for the delta-chain kernel: two-constant Cody-Waite reduction to [-pi, pi] (exact
 // to ~1e-7 for |x| < 4.8e4, the range embed_fast_ok guarantees) and then the special-function unit, whose absolute
-// error on that interval is 2^-21.  7 instructions instead of ~30 for the polynomial sincos_cw (kept in the fp32 SIMT
-// path); measured effect on the outputs is ~1e-6 relative, two orders inside the forward tolerance.
+// error on that interval is 2^-21.  7 instructions instead of ~30 for the polynomial sincos_cw.  Backward only: there
+// the values enter gradients smoothly.  The FORWARD keeps the polynomial sin_cw -- a 1e-6 forward error moves enough
+// ReLU masks of the fusion MLP to show up as a 1e-2 relative error in its (tiny) parameter gradients on a 64-ray batch
+// (found by __graft_entry__.smoke()).
 __device__ __forceinline__ float reduce_2pi(float x) {
     const float k = rintf(x * 0.15915494309189535f);
     return fmaf(-k, -1.7484555e-7f, fmaf(-k, 6.2831854820251465f, x));
 }
-__device__ __forceinline__ float sin_sfu(float x) { return __sinf(reduce_2pi(x)); }
 __device__ __forceinline__ void sincos_sfu(float x, float& s, float& c) {
     const float r = reduce_2pi(x);
     s = __sinf(r);
@@ -265,52 +266,6 @@ __device__ __forceinline__ void scatter_features16(const DfpGrid& g, float* ggri
     gn[0] = gx * t.gx; gn[1] = gy * t.gy; gn[2] = gz * t.gz;
 }
 
-// Warp-aggregated variant of scatter_features16 (grid gradient only).  The lanes of a warp hold consecutive samples of a
-// ray, which often fall into the same grid cell (always for the 16 near-surface samples, and for most neighbours in the
-// coarse low grid); all rays also start in the camera's cell.  Runs of adjacent lanes in one cell are summed with a
-// segmented shuffle reduction and only the head lane of a run issues the vector reductions, which cuts the number of
-// atomics that serialise on hot voxels in L2.  Must be called by all 32 lanes; `active` masks lanes without a gradient.
-__device__ __forceinline__ void scatter_features16_agg(const DfpGrid& g, float* ggrid, const Tri& t, int hf, const float (&dc)[16],
-                                                       bool active, int dbg = 0) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int cell = active ? (t.z0 * g.H + t.y0) * g.W + t.x0 : -1 - lane;       // inactive lanes never merge
-    const int nxt = __shfl_down_sync(full, cell, 1);
-    const unsigned same = __ballot_sync(full, lane < 31 && nxt == cell);          // bit i: lanes i and i+1 share a cell
-    const int run = __ffs(~(same >> lane)) - 1;                                   // lanes after this one that continue its run
-    const bool head = active && (lane == 0 || !((same >> (lane - 1)) & 1u));
-    int maxrun = __reduce_max_sync(full, run);
-    if (dbg & 32) maxrun = 0;                                                      // timing experiment: no aggregation (double counts)
-#pragma unroll 1
-    for (int cn = 0; cn < 8; ++cn) {
-        int x, y, z;
-        const bool ok = tri_corner(t, cn, g.W, g.H, g.D, x, y, z);                 // a property of the cell: uniform over a run
-        const float wgt = (ok && active) ? tri_weight(t, cn) : 0.f;
-        float v[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = dc[k] * wgt;
-#pragma unroll 1
-        for (int d = 1; d <= maxrun; d <<= 1) {                                    // segmented suffix sums within each run
-            const bool take = run >= d;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const float o = __shfl_down_sync(full, v[k], d);
-                v[k] += take ? o : 0.f;
-            }
-        }
-        if (head && ok) {
-            float* dst = ggrid + (((int64_t)z * g.H + y) * g.W + x) * CDIM + 16 * hf;
-            if (dbg & 16) {                                                        // timing experiment: plain stores instead of reductions
-#pragma unroll
-                for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-        }
-    }
-}
-
 __device__ __forceinline__ void load_weights_to_smem(float* dst, const float* __restrict__ src, int nfloats) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
     float4* d4 = reinterpret_cast<float4*>(dst);
@@ -338,7 +293,7 @@ struct DecArgs {
     // saved activations / scratch by list position.  Used for the high decoder, whose output and gradient only matter
     // on TSDF-band samples (decoder.py:326-333: f_add_m_occ is read under the band mask only).
     const int* list; const int* count;
-    int dbg;                       // DFP_DEBUG_SKIP bits (timing experiments only): 1 plane stores, 2 scatter, 4 chain MMAs, 8 sincos
+    int dbg;                       // DFP_DEBUG_SKIP bits (timing experiments only, results become wrong): 1 plane stores, 2 scatter, 4 chain MMAs, 8 sincos
 };
 // number of work items and the sample id of item idx
 __device__ __forceinline__ int64_t dec_items(const DecArgs& a) { return a.list ? (int64_t)*a.count : a.n; }

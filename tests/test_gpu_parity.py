@@ -306,3 +306,11 @@ def test_errors_are_loud():
     with pytest.raises(ValueError):
         renderer.render_batch_ray(grids, model, inp["rays_d"].to(DEV)[:0], inp["rays_o"].to(DEV)[:0], DEV, tsdf, tb, "low",
                                   gt_depth=inp["gt_depth"].to(DEV)[:0])
+
+
+def test_smoke_case_64_rays():
+    """The driver's smoke() case as a test: 64 rays of the small scene.  With so few band samples the fusion MLP's
+    parameter gradients are tiny sums, so this is the case that notices forward errors moving ReLU masks (it caught an
+    SFU-based sin in the forward kernel that every larger case tolerated)."""
+    import __graft_entry__ as G
+    G.smoke()
