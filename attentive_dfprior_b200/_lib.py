@@ -137,6 +137,7 @@ SYMBOLS = {
     "dfp_set_tc_backward": (C.c_int, [C.c_int]),
     "dfp_probe_tc": (C.c_int, [C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
     "dfp_probe_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p]),
+    "dfp_probe_bf16_k": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "dfp_selftest_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dfp_timing_enable": (C.c_int, [C.c_int]),
     "dfp_timing_collect": (C.c_int, [C.c_char_p, C.c_size_t]),

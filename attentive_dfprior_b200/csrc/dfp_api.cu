@@ -594,6 +594,11 @@ int dfp_probe_tc(float* D, int32_t N, int32_t b_mn, int32_t lbo, int32_t sbo, in
     if (!D) return fail(DFP_ERR_INVALID, "null argument");
     return launch_tc_probe(D, N, b_mn, lbo, sbo, k_hot, layout_type, start_off, (cudaStream_t)stream);
 }
+int dfp_probe_bf16_k(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b,
+                     int32_t sbo_b, void* stream) {
+    if (!A || !W || !D) return fail(DFP_ERR_INVALID, "null argument");
+    return launch_tc_probe_bf16_k(A, W, D, K, N, lbo_a, sbo_a, lbo_b, sbo_b, (cudaStream_t)stream);
+}
 int dfp_probe_bf16(const float* A, const float* B, float* D, int32_t N, int32_t fmt, int32_t layout_type, int32_t lbo_a, int32_t lbo_b,
                    int32_t sbo, int32_t kstep_a, int32_t kstep_b, void* stream) {
     if (!A || !B || !D) return fail(DFP_ERR_INVALID, "null argument");

@@ -416,5 +416,7 @@ int launch_tc_selftest(const float* A, const float* W, float* D, int K, int N, i
 int launch_tc_probe(float* D, int N, int b_mn, int lbo, int sbo, int k_hot, int layout_type, int start_off, cudaStream_t st);
 int launch_tc_probe_bf16(const float* A, const float* B, float* D, int N, int fmt, int layout_type, int lbo_a, int lbo_b, int sbo,
                          int kstep_a, int kstep_b, cudaStream_t st);
+int launch_tc_probe_bf16_k(const float* A, const float* W, float* D, int K, int N, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
+                           cudaStream_t st);
 
 }  // namespace dfp

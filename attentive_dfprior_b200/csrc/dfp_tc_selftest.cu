@@ -338,6 +338,71 @@ __global__ void __launch_bounds__(128) k_tc_probe_bf16(const float* __restrict__
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tbase, 128);
 }
+// bf16 K-major probe for the planned attention chain: D[128 x N] = A[128 x K] * W[N x K]^T with A stored in the PLANE
+// layout ([8-sample group][8-feature chunk][sample][feature], dfp_planes.cuh) read as a K-major operand whose MN
+// dimension is the sample (candidate: LBO = 128 between feature chunks, SBO = 16 K between sample groups) and W in the
+// canonical K-major core-matrix layout ((k/8) * N*16 + n*16 + (k%8)*2 bytes; candidate LBO = N*16, SBO = 128).
+__global__ void __launch_bounds__(128) k_tc_probe_bf16_k(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ D,
+                                                         int K, int N, int lbo_a, int sbo_a, int lbo_b, int sbo_b) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* sa = sm;                 // A planes (hi only): 128 x K bf16 <= 32 KB
+    unsigned char* sb = sm + 32768;         // W: N x K bf16 <= 32 KB
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+    __syncthreads();
+    for (int f = 0; f < K; ++f)
+        *reinterpret_cast<__nv_bfloat16*>(sa + (tid >> 3) * 16 * K + (f >> 3) * 128 + (tid & 7) * 16 + (f & 7) * 2) = __float2bfloat16_rn(A[tid * K + f]);
+    for (int i = tid; i < N * K; i += 128) {
+        const int n = i / K, k = i % K;
+        *reinterpret_cast<__nv_bfloat16*>(sb + (k >> 3) * N * 16 + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(W[n * K + k]);
+    }
+    if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 128); tc::tmem_relinquish(); }
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    if (tid == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);   // both K-major
+        auto desc = [&](uint32_t addr, uint32_t lbo, uint32_t sbo) {
+            return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+        };
+        for (int ks = 0; ks < K / 16; ++ks) {                 // 16 features per MMA = two 8-feature chunks
+            const uint64_t da = desc(tc::smem_u32(sa) + ks * 2 * 128, (uint32_t)lbo_a, (uint32_t)sbo_a);
+            const uint64_t db = desc(tc::smem_u32(sb) + ks * 2 * N * 16, (uint32_t)lbo_b, (uint32_t)sbo_b);
+            tc::mma_bf16_ss(tbase, da, db, idesc, ks > 0 ? 1u : 0u);
+        }
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[8];
+        tc::tmem_ld8(lane_base + c0, v);
+        tc::wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) D[tid * N + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 128);
+}
+int launch_tc_probe_bf16_k(const float* A, const float* W, float* D, int K, int N, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
+                           cudaStream_t st) {
+    if (K < 16 || K > 128 || K % 16 || N < 16 || N > 128 || N % 16) return fail(DFP_ERR_INVALID, "bad probe shape");
+    const size_t smem = 65536 + 1024;
+    int rc = set_smem(k_tc_probe_bf16_k, smem);
+    if (rc) return rc;
+    DFP_TIMED("k_tc_probe_bf16_k", st, k_tc_probe_bf16_k<<<1, 128, smem, st>>>(A, W, D, K, N, lbo_a, sbo_a, lbo_b, sbo_b));
+    DFP_LAUNCH_CHECK("k_tc_probe_bf16_k");
+    return DFP_OK;
+}
+
 int launch_tc_probe_bf16(const float* A, const float* B, float* D, int N, int fmt, int layout_type, int lbo_a, int lbo_b, int sbo,
                          int kstep_a, int kstep_b, cudaStream_t st) {
     if (N < 16 || N > 128 || N % 16) return fail(DFP_ERR_INVALID, "bad probe shape");

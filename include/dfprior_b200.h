@@ -290,6 +290,9 @@ int dfp_probe_tc(float* D, int32_t N, int32_t b_mn, int32_t lbo, int32_t sbo, in
 /* development probe of the bf16 MN-major (row-per-sample) operand layouts used by the weight-gradient kernel */
 int dfp_probe_bf16(const float* A, const float* B, float* D, int32_t N, int32_t fmt, int32_t layout_type, int32_t lbo_a, int32_t lbo_b,
                    int32_t sbo, int32_t kstep_a, int32_t kstep_b, void* stream);
+/* development probe (not yet run on hardware): the plane layout read as a K-major bf16 A operand whose MN dimension is the sample */
+int dfp_probe_bf16_k(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b,
+                     int32_t sbo_b, void* stream);
 /* tensor-core self test: D[128,N] = A[128,K] * W[N,K]^T through the tcgen05/TMEM path (split=1: 3xTF32) */
 int dfp_selftest_tc(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t split, void* stream);
 int dfp_timing_enable(int on);

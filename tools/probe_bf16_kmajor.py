@@ -1,0 +1,25 @@
+"""Hardware probe for the planned attention chain (run on the GPU box; NOT yet run): can the plane layout be read as a
+K-major bf16 A operand with the sample as the MN dimension?  Prints the max error of D = A W^T for the candidate
+descriptor readings."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from attentive_dfprior_b200 import _lib as L
+
+lib = L.lib()
+torch.manual_seed(0)
+dev = "cuda:0"
+for K, N in ((64, 128), (128, 128), (128, 64), (32, 32)):
+    A = torch.randn(128, K, device=dev).bfloat16().float()
+    W = torch.randn(N, K, device=dev).bfloat16().float()
+    ref = (A.double() @ W.double().t()).float()
+    cands = [("A: lbo=128 sbo=16K | W: lbo=N*16 sbo=128", 128, 16 * K, N * 16, 128),
+             ("A: lbo=16K sbo=128 | W: lbo=N*16 sbo=128", 16 * K, 128, N * 16, 128),
+             ("A: lbo=128 sbo=16K | W: lbo=128 sbo=N*16", 128, 16 * K, 128, N * 16),
+             ("A: lbo=16K sbo=128 | W: lbo=128 sbo=N*16", 16 * K, 128, 128, N * 16)]
+    for name, la, sa, lb, sb in cands:
+        D = torch.zeros(128, N, device=dev)
+        L.check(lib.dfp_probe_bf16_k(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N, la, sa, lb, sb, None))
+        torch.cuda.synchronize()
+        err = (D - ref).abs().max().item()
+        print(f"K={K:4d} N={N:4d} {name:44s} max_err={err:.3e} {'OK' if err < 1e-3 else ''}")
