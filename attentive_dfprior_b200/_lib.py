@@ -13,8 +13,9 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfprior_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 FLAG_SAVE_ACT = 1
+FLAG_SIMT = 2
 MAX_RAY_SAMPLES = 64
 N_PARAM_TENSORS = 79
 N_PARAMS = 86029
@@ -133,12 +134,6 @@ SYMBOLS = {
     "dfp_assemble_rays": (C.c_int, [C.POINTER(DfpRayBatch), C.POINTER(DfpRayBatchOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "dfp_mapper_loss": (C.c_int, [C.POINTER(DfpMapLoss), C.c_void_p]),
     "dfp_launch_count": (C.c_int64, []),
-    "dfp_set_tensor_cores": (C.c_int, [C.c_int]),
-    "dfp_set_tc_backward": (C.c_int, [C.c_int]),
-    "dfp_probe_tc": (C.c_int, [C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
-    "dfp_probe_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p]),
-    "dfp_probe_bf16_k": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
-    "dfp_selftest_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dfp_timing_enable": (C.c_int, [C.c_int]),
     "dfp_timing_collect": (C.c_int, [C.c_char_p, C.c_size_t]),
 }

@@ -24,5 +24,5 @@ def default_cfg():
 def slam_namespace(bound, tsdf_bnds, cam=None):
     """The attributes Renderer/Mesher read from the SLAM object (src/utils/Renderer.py:19-23)."""
     cam = cam or DEFAULT_CFG["cam"]
-    return SimpleNamespace(bound=bound, vol_bnds=tsdf_bnds, H=cam["H"], W=cam["W"], fx=cam["fx"], fy=cam["fy"],
+    return SimpleNamespace(bound=bound, vol_bnds=tsdf_bnds, tsdf_bnds=tsdf_bnds, H=cam["H"], W=cam["W"], fx=cam["fx"], fy=cam["fy"],
                            cx=cam["cx"], cy=cam["cy"])

@@ -78,32 +78,11 @@ void timing_end(cudaStream_t st) {
     if (!g_recs.empty()) cudaEventRecord(g_recs.back().b, st);
 }
 
-// tensor-core (tcgen05) MLP path: on by default, DFP_TENSOR_CORES=0 or dfp_set_tensor_cores(0) selects the fp32 SIMT kernels
-static std::atomic<int> g_tc{-1};
-bool use_tensor_cores() {
-    int v = g_tc.load(std::memory_order_relaxed);
-    if (v < 0) {
-        const char* e = getenv("DFP_TENSOR_CORES");
-        v = (e && e[0] == '0') ? 0 : 1;
-        g_tc.store(v);
-    }
-    return v != 0;
-}
-
-// DFP_TC_BACKWARD: 0 = SIMT recompute backward, 1 = tensor-core delta chain + SIMT weight gradients (debug),
-// 2 (default) = tensor-core delta chain and weight gradients
-static std::atomic<int> g_tcb{-1};
-static int tc_backward_level() {
-    int v = g_tcb.load(std::memory_order_relaxed);
-    if (v < 0) {
-        const char* e = getenv("DFP_TC_BACKWARD");
-        v = e ? atoi(e) : 2;
-        g_tcb.store(v);
-    }
-    return v;
-}
-// the saved-activation path exists only on the tensor-core kernels
-static int train_flags(int flags) { return use_tensor_cores() ? (flags & DFP_FLAG_SAVE_ACT) : 0; }
+// Which MLP kernels a call uses is decided by the call's own flags (DfpCfg.flags / DfpPoints.flags), never by process
+// state: default = tcgen05 tensor-core kernels; DFP_FLAG_SIMT selects the fp32 SIMT kernels (in-tree cross-check).
+// The saved-activation training path (DFP_FLAG_SAVE_ACT) exists only on the tensor-core kernels.
+static inline bool flags_tc(int flags) { return (flags & DFP_FLAG_SIMT) == 0; }
+static int train_flags(int flags) { return flags_tc(flags) ? (flags & DFP_FLAG_SAVE_ACT) : DFP_FLAG_SIMT; }
 
 static int g_num_sms = 0;
 int num_sms() {
@@ -476,7 +455,7 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
     memset(&da, 0, sizeof(da));
     da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params;
     int rc;
-    const bool tcp = use_tensor_cores();
+    const bool tcp = flags_tc(flags);
     const bool save = tcp && (flags & DFP_FLAG_SAVE_ACT);
     auto set_act = [&](int d) {
         da.act_h = save ? w.act_h[d] : nullptr; da.act_m = save ? w.act_m[d] : nullptr; da.act_c = save ? w.act_c[d] : nullptr;
@@ -529,12 +508,8 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
     da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params;
     da.gparams = g->params_packed; da.dp = want_dp ? w.dp : nullptr;
     // tensor-core backward (needs the activations saved by the tensor-core forward): K1 = delta chain, K2 = weight grads
-    const bool tcb = use_tensor_cores() && (flags & DFP_FLAG_SAVE_ACT) && w.act_h[0] != nullptr && tc_backward_level() > 0;
+    const bool tcb = flags_tc(flags) && (flags & DFP_FLAG_SAVE_ACT) && w.act_h[0] != nullptr;
     da.sc_e = w.sc_e; da.sc_dh = w.sc_dh; da.sc_darg = w.sc_darg; da.sc_dl1 = w.sc_dl1;
-    {   // timing experiments (results become wrong): which part of K1 costs what
-        static const int dbg = getenv("DFP_DEBUG_SKIP") ? atoi(getenv("DFP_DEBUG_SKIP")) : 0;
-        da.dbg = dbg;
-    }
     auto run = [&](auto dec_tag) -> int {
         constexpr int DEC = decltype(dec_tag)::value;
         if (!tcb) return launch_decoder_bwd<DEC, MODE>(da, st);
@@ -542,10 +517,7 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
         da.list = (DEC == 1) ? w.band_list : nullptr; da.count = (DEC == 1) ? w.band_count : nullptr;   // as in the forward
         int r = launch_decoder_dh_tc<DEC, MODE>(da, st);
         if (r || !da.gparams) return r;
-        if (tc_backward_level() >= 2) return launch_decoder_dw_tc<DEC>(da, st);
-        DecArgs pa = da;                    // level 1 (debug): parameter gradients from the SIMT kernel
-        pa.ggrid = nullptr; pa.dp = nullptr;
-        return launch_decoder_bwd<DEC, MODE>(pa, st);
+        return launch_decoder_dw_tc<DEC>(da, st);
     };
     if (hi) {
         da.grid = sc->high; da.grid_low = sc->low; da.dout = w.d_high; da.ggrid = g->grid_high;
@@ -583,36 +555,6 @@ extern "C" {
 int dfp_abi_version(void) { return DFP_ABI_VERSION; }
 const char* dfp_last_error(void) { return g_err; }
 int64_t dfp_packed_param_floats(void) { return PACKED_FLOATS; }
-
-int dfp_selftest_tc(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t split, void* stream) {
-    if (!A || !W || !D) return fail(DFP_ERR_INVALID, "null argument");
-    return launch_tc_selftest(A, W, D, K, N, split, (cudaStream_t)stream);
-}
-
-int dfp_probe_tc(float* D, int32_t N, int32_t b_mn, int32_t lbo, int32_t sbo, int32_t k_hot, int32_t layout_type,
-                 int32_t start_off, void* stream) {
-    if (!D) return fail(DFP_ERR_INVALID, "null argument");
-    return launch_tc_probe(D, N, b_mn, lbo, sbo, k_hot, layout_type, start_off, (cudaStream_t)stream);
-}
-int dfp_probe_bf16_k(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b,
-                     int32_t sbo_b, void* stream) {
-    if (!A || !W || !D) return fail(DFP_ERR_INVALID, "null argument");
-    return launch_tc_probe_bf16_k(A, W, D, K, N, lbo_a, sbo_a, lbo_b, sbo_b, (cudaStream_t)stream);
-}
-int dfp_probe_bf16(const float* A, const float* B, float* D, int32_t N, int32_t fmt, int32_t layout_type, int32_t lbo_a, int32_t lbo_b,
-                   int32_t sbo, int32_t kstep_a, int32_t kstep_b, void* stream) {
-    if (!A || !B || !D) return fail(DFP_ERR_INVALID, "null argument");
-    return launch_tc_probe_bf16(A, B, D, N, fmt, layout_type, lbo_a, lbo_b, sbo, kstep_a, kstep_b, (cudaStream_t)stream);
-}
-
-int dfp_set_tensor_cores(int on) {
-    g_tc.store(on ? 1 : 0);
-    return DFP_OK;
-}
-int dfp_set_tc_backward(int level) {
-    g_tcb.store(level);
-    return DFP_OK;
-}
 
 int64_t dfp_launch_count(void) { return (int64_t)g_launches.load(); }
 

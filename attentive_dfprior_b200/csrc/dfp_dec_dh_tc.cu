@@ -112,8 +112,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
     const int64_t n = dec_items(a);
     const int64_t tiles = (n + 127) / 128;
     const bool issuer = (gt == 0);
-    const bool planes = a.gparams != nullptr && !(a.dbg & 1);
-    const bool do_mma = !(a.dbg & 4);
+    const bool planes = a.gparams != nullptr;
     const float bmax = embed_bmax(sm + T::S_B);
     const int c0 = 16 * hf;
 
@@ -168,9 +167,9 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             tc::named_bar_sync(3 + grp, 256);
             if (issuer) {
                 tc::fence_after_sync();
-                if (do_mma) tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + (T::WC + i * 1024) * 4, wlo + (T::WC + i * 1024) * 4,
+                tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + (T::WC + i * 1024) * 4, wlo + (T::WC + i * 1024) * 4,
                                   32, 32, 4096u, i != 4);
-                if (do_mma) tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A + 64, tb + T::T_A + 96, whi + (T::WH + (i - 1) * 1024) * 4,
+                tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A + 64, tb + T::T_A + 96, whi + (T::WH + (i - 1) * 1024) * 4,
                                   wlo + (T::WH + (i - 1) * 1024) * 4, 32, 32, 4096u, false);
                 tc::mma_commit(bar);
             }
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             tc::named_bar_sync(3 + grp, 256);
             if (issuer) {
                 tc::fence_after_sync();
-                if (do_mma) tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + T::WC * 4, wlo + T::WC * 4, 32, 32, 4096u, true);
+                tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + T::WC * 4, wlo + T::WC * 4, 32, 32, 4096u, true);
                 tc::mma_commit(bar);
             }
             const uint32_t m0 = m_next >> c0;
@@ -219,7 +218,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             tc::named_bar_sync(3 + grp, 256);
             if (issuer) {
                 tc::fence_after_sync();
-                if (do_mma) tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A, tb + T::T_A + 64, whi + T::W03 * 4, wlo + T::W03 * 4, 64, 96, 8192u, false);
+                tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A, tb + T::T_A + 64, whi + T::W03 * 4, wlo + T::W03 * 4, 64, 96, 8192u, false);
                 tc::mma_commit(bar);
             }
         }
@@ -245,7 +244,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                 for (int kk = 0; kk < 16; ++kk) {
                     const int k = ch * 32 + c0 + kk;
                     float s1 = (k == EMB) ? 1.f : 0.f, c1 = 0.f;    // column 93 of the sin array: constant 1 (bias of block 0 in kernel 2)
-                    if (k < EMB && !(a.dbg & 8)) sincos_sfu(embed_arg(sm + T::S_B, pf, k), s1, c1);
+                    if (k < EMB) sincos_sfu(embed_arg(sm + T::S_B, pf, k), s1, c1);
                     sn[kk] = s1;
                     da[kk] = de[kk] * c1;
                 }
@@ -284,8 +283,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
         tc::wait_ld();
         const bool want_coord = a.dp != nullptr;
         float gn[3] = {0.f, 0.f, 0.f};
-        if (a.dbg & 2) {
-        } else if (a.ggrid && !want_coord) {
+        if (a.ggrid && !want_coord) {
             // Cooperative scatter.  A thread's own reduction would touch 32 different lines per warp instruction (one
             // 16-byte piece per lane, ~2 cycles of the load/store unit each: measured, this was half of the kernel).
             // Instead the tile's feature gradients go through shared memory and eight lanes add one corner's whole

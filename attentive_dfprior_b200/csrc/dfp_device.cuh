@@ -293,7 +293,6 @@ struct DecArgs {
     // saved activations / scratch by list position.  Used for the high decoder, whose output and gradient only matter
     // on TSDF-band samples (decoder.py:326-333: f_add_m_occ is read under the band mask only).
     const int* list; const int* count;
-    int dbg;                       // DFP_DEBUG_SKIP bits (timing experiments only, results become wrong): 1 plane stores, 2 scatter, 4 chain MMAs, 8 sincos
 };
 // number of work items and the sample id of item idx
 __device__ __forceinline__ int64_t dec_items(const DecArgs& a) { return a.list ? (int64_t)*a.count : a.n; }
@@ -407,16 +406,9 @@ inline Bounds to_bounds(const double b[3][2]) {
 template <int DEC, int MODE> int launch_decoder_fwd(const DecArgs& a, cudaStream_t st);
 template <int DEC, int MODE> int launch_decoder_bwd(const DecArgs& a, cudaStream_t st);
 template <int DEC, int MODE> int launch_decoder_fwd_tc(const DecArgs& a, cudaStream_t st);   // tcgen05 path
-bool use_tensor_cores();
 template <int DEC, int MODE> int launch_decoder_dh_tc(const DecArgs& a, cudaStream_t st);      // backward K1: delta chain
 template <int DEC> int launch_decoder_dw_tc(const DecArgs& a, cudaStream_t st);                // backward K2: weight gradients
 int launch_attn_fwd(const AttArgs& a, int64_t n, cudaStream_t st);
 template <int MODE> int launch_attn_bwd(const AttArgs& a, int64_t n, cudaStream_t st);
-int launch_tc_selftest(const float* A, const float* W, float* D, int K, int N, int split, cudaStream_t st);
-int launch_tc_probe(float* D, int N, int b_mn, int lbo, int sbo, int k_hot, int layout_type, int start_off, cudaStream_t st);
-int launch_tc_probe_bf16(const float* A, const float* B, float* D, int N, int fmt, int layout_type, int lbo_a, int lbo_b, int sbo,
-                         int kstep_a, int kstep_b, cudaStream_t st);
-int launch_tc_probe_bf16_k(const float* A, const float* W, float* D, int K, int N, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
-                           cudaStream_t st);
 
 }  // namespace dfp

@@ -107,29 +107,28 @@ class mlp_tsdf(nn.Module):
 
 
 class ParamPack:
-    """Packed device copy of a decoder module's 79 parameters, refreshed when they change."""
+    """Gathers a decoder module's 79 parameters into the kernels' packed layout.
 
-    def __init__(self):
-        self.key = None
-        self.packed = None
-        self.tensors = None
+    Every call packs afresh into its OWN buffer (one small kernel, 344 KB from the caching allocator).  Round 1 cached
+    the packed copy keyed on ``(data_ptr, _version)``: writes through ``param.data`` / raw pointers (``p.data.copy_``,
+    an external fused optimiser) do not bump ``_version`` and kept stale weights in use, and one shared buffer meant a
+    second forward after an optimiser step overwrote the weights an earlier, not-yet-run backward still pointed at.
+    A private copy per forward has neither problem: its backward sees exactly the weights its forward used."""
 
     def get(self, tensors):
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
-        if key != self.key:
-            lib = L.lib()
-            dev = tensors[0].device
-            if self.packed is None or self.packed.device != dev:
-                self.packed = torch.zeros(int(lib.dfp_packed_param_floats()), device=dev, dtype=torch.float32)
-            keep = [t.detach() if (t.dtype == torch.float32 and t.is_contiguous()) else t.detach().float().contiguous()
-                    for t in tensors]
-            arr = (C.c_void_p * L.N_PARAM_TENSORS)(*[t.data_ptr() for t in keep])
-            with torch.cuda.device(dev):
-                L.check(lib.dfp_pack_params(C.cast(arr, C.POINTER(C.c_void_p)), self.packed.data_ptr(),
-                                            torch.cuda.current_stream().cuda_stream))
-            self.key = key
-            self.tensors = keep
-        return self.packed
+        lib = L.lib()
+        dev = tensors[0].device
+        packed = torch.zeros(int(lib.dfp_packed_param_floats()), device=dev, dtype=torch.float32)   # padding stays zero
+        keep = [t.detach() if (t.dtype == torch.float32 and t.is_contiguous()) else t.detach().float().contiguous()
+                for t in tensors]
+        arr = (C.c_void_p * L.N_PARAM_TENSORS)(*[t.data_ptr() for t in keep])
+        with torch.cuda.device(dev):
+            L.check(lib.dfp_pack_params(C.cast(arr, C.POINTER(C.c_void_p)), packed.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream))
+        return packed
+
+
+_PACK = ParamPack()
 
 
 def decoder_param_list(decoders):
@@ -143,11 +142,7 @@ def decoder_param_list(decoders):
 
 
 def param_pack_of(decoders) -> ParamPack:
-    pk = decoders.__dict__.get("_dfp_pack")
-    if pk is None:
-        pk = ParamPack()
-        decoders.__dict__["_dfp_pack"] = pk      # plain attribute: not a parameter/buffer, dropped by deepcopy-safe getstate below
-    return pk
+    return _PACK
 
 
 class DF(nn.Module):
@@ -178,8 +173,6 @@ class DF(nn.Module):
         memo[id(self)] = new
         import copy
         for k, v in self.__dict__.items():
-            if k == "_dfp_pack":
-                continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         return new
 

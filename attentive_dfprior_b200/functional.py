@@ -8,6 +8,7 @@ and ``gt_depth`` never receive gradients.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, Optional
 
 import torch
@@ -18,23 +19,34 @@ GRID_KEYS = ("grid_low", "grid_high", "grid_color")
 
 
 # ----------------------------------------------------------------------------------------
-# small caches (all keyed on data_ptr + version so in-place optimiser updates invalidate them)
+# bounds
 # ----------------------------------------------------------------------------------------
 class _BoundsCache:
-    """[3,2] bound tensors -> python floats without a device sync on every call."""
+    """[3,2] bound tensors -> python floats.
+
+    CPU tensors (``bound`` as the reference keeps it, src/DF_Prior.py:185-194) are read on every call: ``tolist`` of six
+    doubles costs microseconds.  CUDA tensors (``tsdf_bnds``, src/DF_Prior.py:87) need a device->host copy, so their
+    values are remembered -- per tensor OBJECT, held through a weak reference and checked for identity and version on
+    every hit.  Nothing is keyed on addresses: a freed tensor's address (and ``id``) is handed to the next allocation at
+    once, and an address-keyed cache then returns the previous scene's box (round-1 bug: 16-50 % wrong outputs when a
+    second scene was rendered in the same process)."""
 
     def __init__(self):
         self.d = {}
 
     def get(self, t: torch.Tensor):
-        key = (t.data_ptr(), t._version, str(t.device))
-        v = self.d.get(key)
-        if v is None:
-            if len(self.d) > 64:
-                self.d.clear()
-            v = t.detach().to("cpu").double().reshape(3, 2).tolist()
-            self.d[key] = v
-        return v
+        if not t.is_cuda:
+            return t.detach().double().reshape(3, 2).tolist()
+        key = id(t)
+        hit = self.d.get(key)
+        if hit is not None:
+            ref, version, vals = hit
+            if ref() is t and version == t._version:
+                return vals
+        vals = t.detach().to("cpu").double().reshape(3, 2).tolist()
+        d = self.d
+        self.d[key] = (weakref.ref(t, lambda _r, k=key: d.pop(k, None)), t._version, vals)
+        return vals
 
 
 _bounds = _BoundsCache()
@@ -182,7 +194,31 @@ def _param_grads(gp, params, needs):
 # ----------------------------------------------------------------------------------------
 # Renderer.render_batch_ray
 # ----------------------------------------------------------------------------------------
+# A training call keeps per-sample operands for its backward in the workspace.  Above this many bytes the call is run
+# in ray chunks instead: the forward keeps nothing, and the backward re-runs each chunk's forward right before that
+# chunk's backward (one extra forward, bounded memory).  SURVEY 8d's 1 048 576-ray variant needs this.
+WORKSPACE_BUDGET_BYTES = 24 << 30
+
+
 class _RenderBatchRay(torch.autograd.Function):
+    @staticmethod
+    def _fwd_call(aux, scene, packed, ro, rd, gt, dmax, lo, hi, flags, outs, want_aux):
+        """One dfp_render_fwd over rays [lo, hi); returns the workspace it wrote."""
+        lib = L.lib()
+        n = hi - lo
+        depth, unc, color, weight, z, raw = outs
+        S = weight.shape[1]
+        cfg = _cfg_struct(aux.stage, aux.n_samples, aux.n_surface, aux.n_importance, flags)
+        rays = L.DfpRays(ro[lo:hi].data_ptr(), rd[lo:hi].data_ptr(), _ptr(gt[lo:hi]) if gt is not None else None, n,
+                         aux.chunk, _ptr(dmax))
+        ws_bytes = int(lib.dfp_render_workspace_bytes(n, S, aux.chunk, L.STAGES[aux.stage], flags))
+        ws = torch.empty(ws_bytes, device=ro.device, dtype=torch.uint8)
+        out = L.DfpRenderOut(depth[lo:hi].data_ptr(), unc[lo:hi].data_ptr(), color[lo:hi].data_ptr(), weight[lo:hi].data_ptr(),
+                             _ptr(z[lo:hi]) if want_aux else None, _ptr(raw[lo:hi]) if want_aux else None)
+        L.check(lib.dfp_render_fwd(C.byref(scene), packed.data_ptr(), C.byref(rays), C.byref(cfg), C.byref(out),
+                                   ws.data_ptr(), ws_bytes, _stream()))
+        return ws, ws_bytes, rays, cfg
+
     @staticmethod
     def forward(ctx, aux, rays_o, rays_d, grid_low, grid_high, grid_color, *params):
         lib = L.lib()
@@ -196,25 +232,37 @@ class _RenderBatchRay(torch.autograd.Function):
         grids_cl = {k: (_grid_ndhwc(given[k]) if k in _needed_grids(aux.stage) else None) for k in GRID_KEYS}
         packed = aux.pack.get(list(params))
         scene = _scene_struct(grids_cl, aux.tsdf_volume, aux.tsdf_bnds, aux.bound)
-        flags = L.FLAG_SAVE_ACT if any(ctx.needs_input_grad) else 0
-        cfg = _cfg_struct(aux.stage, aux.n_samples, aux.n_surface, aux.n_importance, flags)
-        rays = L.DfpRays(ro.data_ptr(), rd.data_ptr(), _ptr(gt), N, aux.chunk, _ptr(aux.depth_max))
+        train = any(ctx.needs_input_grad)
+        flags = (L.FLAG_SIMT if aux.simt else 0) | (L.FLAG_SAVE_ACT if train else 0)
         depth = torch.empty(N, device=dev, dtype=torch.float64)
         unc = torch.empty(N, device=dev, dtype=torch.float64)
         color = torch.empty(N, 3, device=dev, dtype=torch.float32)
         weight = torch.empty(N, S, 1, device=dev, dtype=torch.float32)
         z = torch.empty(N, S, device=dev, dtype=torch.float64) if aux.want_aux else None
         raw = torch.empty(N, S, 4, device=dev, dtype=torch.float32) if aux.want_aux else None
-        ws_bytes = int(lib.dfp_render_workspace_bytes(N, S, aux.chunk, L.STAGES[aux.stage], flags))
-        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        out = L.DfpRenderOut(depth.data_ptr(), unc.data_ptr(), color.data_ptr(), weight.data_ptr(), _ptr(z), _ptr(raw))
-        L.check(lib.dfp_render_fwd(C.byref(scene), packed.data_ptr(), C.byref(rays), C.byref(cfg), C.byref(out),
-                                   ws.data_ptr(), ws_bytes, _stream()))
+        outs = (depth, unc, color, weight, z, raw)
+        dmax = aux.depth_max
+        # ray chunks for calls whose saved operands would not fit the budget (training calls only; render_img's
+        # chunk-exact maxima are a forward-only feature and keep the single-call path)
+        per_ray = int(lib.dfp_render_workspace_bytes(1 << 14, S, 0, L.STAGES[aux.stage], flags)) >> 14
+        step = N
+        if train and aux.chunk == 0 and N * per_ray > aux.ws_budget:
+            step = max(1, int(aux.ws_budget // max(per_ray, 1)))
+            if gt is not None and dmax is None:
+                dmax = gt.max().reshape(1)                   # the far clamp uses the max of the WHOLE batch (Renderer.py:159,195)
+        keep = _Ctx(ro=ro, rd=rd, grids_cl=grids_cl, packed=packed, N=N, S=S, params=params, flags=flags, scene=scene,
+                    dmax=dmax, step=step, ws=None, ws_bytes=0)
+        if step >= N:
+            keep.ws, keep.ws_bytes, _, _ = _RenderBatchRay._fwd_call(aux, scene, packed, ro, rd, gt, dmax, 0, N, flags, outs,
+                                                                     aux.want_aux)
+        else:
+            for lo in range(0, N, step):                     # nothing kept: the backward recomputes chunk by chunk
+                _RenderBatchRay._fwd_call(aux, scene, packed, ro, rd, gt, dmax, lo, min(N, lo + step),
+                                          flags & ~L.FLAG_SAVE_ACT, outs, aux.want_aux)
         if aux.want_aux:
             aux.z_vals, aux.raw = z, raw
         ctx.aux = aux
-        ctx.keep = _Ctx(ro=ro, rd=rd, grids_cl=grids_cl, packed=packed, ws=ws, ws_bytes=ws_bytes, N=N, S=S,
-                        params=params, tsdf=aux.tsdf_volume, flags=flags)
+        ctx.keep = keep
         return depth, unc, color, weight
 
     @staticmethod
@@ -229,23 +277,30 @@ class _RenderBatchRay(torch.autograd.Function):
             g, ggrids, gp, flat = _grads_struct(k, needs_grid, need_params, dev)
             d_o = torch.empty_like(k.ro) if (need[1] or need[2]) else None
             d_d = torch.empty_like(k.rd) if (need[1] or need[2]) else None
-            g.rays_o, g.rays_d = _ptr(d_o), _ptr(d_d)
-            keep_alive = []
 
             def prep(t, dtype):
-                if t is None:
-                    return None
-                t = t.detach().to(dtype).contiguous()
-                keep_alive.append(t)
-                return t.data_ptr()
+                return None if t is None else t.detach().to(dtype).contiguous()
 
-            og = L.DfpRenderOutGrad(prep(g_depth, torch.float64), prep(g_unc, torch.float64),
-                                    prep(g_color, torch.float32), prep(g_weight, torch.float32))
-            scene = _scene_struct(k.grids_cl, k.tsdf, aux.tsdf_bnds, aux.bound)
-            cfg = _cfg_struct(aux.stage, aux.n_samples, aux.n_surface, aux.n_importance, k.flags)
-            rays = L.DfpRays(k.ro.data_ptr(), k.rd.data_ptr(), _ptr(aux.gt_depth), k.N, aux.chunk, _ptr(aux.depth_max))
-            L.check(lib.dfp_render_bwd(C.byref(scene), k.packed.data_ptr(), C.byref(rays), C.byref(cfg), C.byref(og),
-                                       C.byref(g), k.ws.data_ptr(), k.ws_bytes, _stream()))
+            gd, gu, gc, gw = (prep(g_depth, torch.float64), prep(g_unc, torch.float64), prep(g_color, torch.float32),
+                              prep(g_weight, torch.float32))
+            gt = aux.gt_depth
+            sl = lambda t, lo, hi: None if t is None else t[lo:hi].data_ptr()
+            for lo in range(0, k.N, k.step):
+                hi = min(k.N, lo + k.step)
+                if k.ws is not None:
+                    ws, ws_bytes = k.ws, k.ws_bytes
+                    cfg = _cfg_struct(aux.stage, aux.n_samples, aux.n_surface, aux.n_importance, k.flags)
+                    rays = L.DfpRays(k.ro.data_ptr(), k.rd.data_ptr(), _ptr(gt), k.N, aux.chunk, _ptr(k.dmax))
+                else:                                        # chunked call: this chunk's forward again, keeping its operands
+                    scratch = (torch.empty(hi - lo, device=dev, dtype=torch.float64), torch.empty(hi - lo, device=dev, dtype=torch.float64),
+                               torch.empty(hi - lo, 3, device=dev), torch.empty(hi - lo, k.S, 1, device=dev), None, None)
+                    ws, ws_bytes, rays, cfg = _RenderBatchRay._fwd_call(aux, k.scene, k.packed, k.ro[lo:hi], k.rd[lo:hi],
+                                                                        None if gt is None else gt[lo:hi], k.dmax, 0, hi - lo,
+                                                                        k.flags, scratch, False)
+                g.rays_o, g.rays_d = sl(d_o, lo, hi), sl(d_d, lo, hi)
+                og = L.DfpRenderOutGrad(sl(gd, lo, hi), sl(gu, lo, hi), sl(gc, lo, hi), sl(gw, lo, hi))
+                L.check(lib.dfp_render_bwd(C.byref(k.scene), k.packed.data_ptr(), C.byref(rays), C.byref(cfg), C.byref(og),
+                                           C.byref(g), ws.data_ptr(), ws_bytes, _stream()))
             if aux.group is not None:
                 # ray-sharded data parallelism: sum the replicated state's gradients over the ranks (NCCL)
                 import torch.distributed as dist
@@ -257,11 +312,13 @@ class _RenderBatchRay(torch.autograd.Function):
 
 
 def render_batch_ray(c, decoders, rays_d, rays_o, tsdf_volume, tsdf_bnds, bound, stage, gt_depth=None,
-                     n_samples=32, n_surface=16, n_importance=0, chunk=0, want_aux=False, depth_max=None, group=None):
+                     n_samples=32, n_surface=16, n_importance=0, chunk=0, want_aux=False, depth_max=None, group=None,
+                     simt=False, workspace_budget=None):
     """Functional form of Renderer.render_batch_ray (src/utils/Renderer.py:110-255).
 
     Returns ``(depth [N] f64, uncertainty [N] f64, color [N,3] f32, weight [N,S,1] f32)``; with
-    ``want_aux`` also a dict holding the sorted sample depths and the pre-sigmoid raw values."""
+    ``want_aux`` also a dict holding the sorted sample depths and the pre-sigmoid raw values.
+    ``simt`` evaluates the MLPs with the fp32 SIMT kernels (cross-check of the tensor-core path)."""
     from .decoder import decoder_param_list, param_pack_of
     _require_cuda(rays_o, rays_d, tsdf_volume)
     if stage not in L.STAGES:
@@ -274,7 +331,8 @@ def render_batch_ray(c, decoders, rays_d, rays_o, tsdf_volume, tsdf_bnds, bound,
                chunk=int(chunk), gt_depth=gt, tsdf_volume=tsdf_volume.detach() if tsdf_volume is not None else None,
                tsdf_bnds=tsdf_bnds, bound=bound, pack=param_pack_of(decoders), want_aux=want_aux,
                depth_max=None if depth_max is None else depth_max.detach().reshape(-1)[:1].float().contiguous(),
-               group=group)
+               group=group, simt=bool(simt),
+               ws_budget=WORKSPACE_BUDGET_BYTES if workspace_budget is None else int(workspace_budget))
     dummy = rays_o.new_zeros(())
     gl = c.get("grid_low")
     gh = c.get("grid_high") if stage != "low" else None
@@ -304,7 +362,7 @@ class _EvalPoints(torch.autograd.Function):
         grids_cl = {k: (_grid_ndhwc(given[k]) if k in _needed_grids(aux.stage) else None) for k in GRID_KEYS}
         packed = aux.pack.get(list(params))
         scene = _scene_struct(grids_cl, aux.tsdf_volume, aux.tsdf_bnds, aux.bound)
-        flags = L.FLAG_SAVE_ACT if any(ctx.needs_input_grad) else 0
+        flags = (L.FLAG_SIMT if aux.simt else 0) | (L.FLAG_SAVE_ACT if any(ctx.needs_input_grad) else 0)
         P = L.DfpPoints(p.data_ptr(), 1 if p.dtype == torch.float64 else 0, 1 if aux.apply_bound_mask else 0, n, flags, 0)
         raw = torch.empty(n, 4, device=dev, dtype=torch.float32)
         w = torch.empty(n, device=dev, dtype=torch.float32)
@@ -314,7 +372,7 @@ class _EvalPoints(torch.autograd.Function):
                                    raw.data_ptr(), w.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
         ctx.aux = aux
         ctx.keep = _Ctx(p=p, grids_cl=grids_cl, packed=packed, ws=ws, ws_bytes=ws_bytes, n=n, params=params,
-                        tsdf=aux.tsdf_volume, flags=flags)
+                        scene=scene, flags=flags)
         return raw, w
 
     @staticmethod
@@ -331,7 +389,7 @@ class _EvalPoints(torch.autograd.Function):
             g.points = _ptr(d_p)
             gr = g_raw.detach().float().contiguous() if g_raw is not None else None
             gw = g_w.detach().float().contiguous() if g_w is not None else None
-            scene = _scene_struct(k.grids_cl, k.tsdf, aux.tsdf_bnds, aux.bound)
+            scene = k.scene                      # the forward's own scene record (grids, TSDF and both boxes as it saw them)
             P = L.DfpPoints(k.p.data_ptr(), 1 if k.p.dtype == torch.float64 else 0, 1 if aux.apply_bound_mask else 0, k.n,
                             k.flags, 0)
             L.check(lib.dfp_points_bwd(C.byref(scene), k.packed.data_ptr(), C.byref(P), L.STAGES[aux.stage],
@@ -340,7 +398,7 @@ class _EvalPoints(torch.autograd.Function):
         return (None, d_p, ggrids.get("grid_low"), ggrids.get("grid_high"), ggrids.get("grid_color"), *pgrads)
 
 
-def eval_points(p, decoders, c, tsdf_volume, tsdf_bnds, bound, stage="color", apply_bound_mask=True):
+def eval_points(p, decoders, c, tsdf_volume, tsdf_bnds, bound, stage="color", apply_bound_mask=True, simt=False):
     """Point query: ``raw [P,4]``, ``w [P]``.  With ``apply_bound_mask`` it is Renderer/Mesher.eval_points
     (occupancy 100 outside the bound, Renderer.py:51-64); without, the bare DF.forward (decoder.py:307-353)."""
     from .decoder import decoder_param_list, param_pack_of
@@ -351,7 +409,8 @@ def eval_points(p, decoders, c, tsdf_volume, tsdf_bnds, bound, stage="color", ap
         raise ValueError("eval_points needs at least one point")
     params = decoder_param_list(decoders)
     aux = _Ctx(stage=stage, tsdf_volume=tsdf_volume.detach() if tsdf_volume is not None else None,
-               tsdf_bnds=tsdf_bnds, bound=bound, pack=param_pack_of(decoders), apply_bound_mask=apply_bound_mask)
+               tsdf_bnds=tsdf_bnds, bound=bound, pack=param_pack_of(decoders), apply_bound_mask=apply_bound_mask,
+               simt=bool(simt))
     dummy = p.new_zeros((), dtype=torch.float32)
     gl = c.get("grid_low")
     gh = c.get("grid_high") if stage != "low" else None

@@ -25,7 +25,10 @@ class Mesher(object):
         self.resolution = cfg["meshing"]["resolution"]
         self.level_set = cfg["meshing"].get("level_set", 0)
         self.bound = slam.bound
-        self.tsdf_bnds = slam.vol_bnds
+        # the reference's Mesher reads slam.tsdf_bnds (Mesher.py:56), its Renderer slam.vol_bnds (Renderer.py:21)
+        self.tsdf_bnds = getattr(slam, "tsdf_bnds", None)
+        if self.tsdf_bnds is None:
+            self.tsdf_bnds = slam.vol_bnds
         mcb = cfg.get("mapping", {}).get("marching_cubes_bound")
         self.marching_cubes_bound = (torch.from_numpy(np.array(mcb) * self.scale) if mcb is not None
                                      else slam.bound.clone())

@@ -76,13 +76,15 @@ def make_scene(kind: str = "room0", seed: int = 0, device="cpu", c_dim: int = 32
             v = v.contiguous(memory_format=torch.channels_last_3d)
         grids["grid_" + name] = v
 
-    # TSDF: dims = ceil(L / voxel) per axis, upper bound = lower + dims * voxel (src/fusion.py:38-43)
-    b = np.array(raw, dtype=np.float64)
-    dims = np.ceil((b[:, 1] - b[:, 0]) / voxel).astype(int)
+    # TSDF over the (rounded) scene box: dims = ceil(L / voxel) per axis, upper bound = lower + dims * voxel
+    # (src/fusion.py:38-43); room0 at 4/256 m gives [X,Y,Z] = [758,574,451]
+    b = bound.numpy().astype(np.float64).copy()
+    dims = np.ceil(np.round((b[:, 1] - b[:, 0]) / voxel, 9)).astype(int)
     tb = b.copy()
     tb[:, 1] = tb[:, 0] + dims * voxel
-    centre = (b[:, 0] + b[:, 1]) / 2
-    half = (b[:, 1] - b[:, 0]) / 2 * 0.8
+    braw = np.array(raw, dtype=np.float64)                            # the analytic room sits in the unrounded box
+    centre = (braw[:, 0] + braw[:, 1]) / 2
+    half = (braw[:, 1] - braw[:, 0]) / 2 * 0.8
     room_lo, room_hi = centre - half, centre + half
     ax = [torch.arange(int(dims[k]), dtype=torch.float32, device=device) * voxel + float(tb[k, 0])
           for k in range(3)]

@@ -112,67 +112,87 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm: the reference algorithm (oracle port) on the host cores
 # ------------------------------------------------------------------------------------------------
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def workload_config(n, world, channels_first=False, tsdf_shape=None, extra=None):
+    """The `config` object both arms print: it names the workload, not the implementation."""
+    cfg = {"workload": "replica_room0_mapping_iteration", "stage": STAGE, "rays_per_gpu_per_step": n,
+           "samples_per_ray": S, "grids": "low[21,28,37] high/color[43,56,74] x32",
+           "tsdf": tsdf_shape, "loss": "Mapper depth L1 + 0.2 colour L1",
+           "parallelism": f"ray-sharded dp{world}" + (" + all-reduce of grid/decoder grads" if world > 1 else ""),
+           "l2": "GPU arm: flushed between timed steps (256 MiB write)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def oracle_step_factory(scene, n_total, n_sample, device="cpu"):
+    """One mapping step of the reference algorithm (oracle port) on `n_sample` rays of the `n_total`-ray batch the
+    kernels are benchmarked on (same generator, same seed): returns (step_fn, n_sample)."""
     from attentive_dfprior_b200 import synth
     from oracle import dfprior_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    n = args.ref_rays
-    scene = synth.make_scene("room0", seed=0, high_std=1e-2)
-    params = {k: v.requires_grad_(True) for k, v in O.init_decoder_params(0).items()}
-    grids = {k: v.requires_grad_(True) for k, v in scene.grids.items()}
-    rays_o, rays_d, gt, gt_color = synth.make_rays(scene, n, seed=1)
+    params = {k: v.to(device).requires_grad_(True) for k, v in O.init_decoder_params(0).items()}
+    grids = {k: v.to(device).requires_grad_(True) for k, v in scene.grids.items()}
+    rays_o, rays_d, gt, gt_color = synth.make_rays(scene, n_total, seed=100)
+    n_sample = min(n_sample, n_total)
+    idx = torch.arange(0, n_total, n_total // n_sample)[:n_sample]              # an even sample of the batch
+    rays_o, rays_d, gt, gt_color = (t[idx].to(device) for t in (rays_o, rays_d, gt, gt_color))
+    tsdf, tb = scene.tsdf_volume.to(device), scene.tsdf_bnds.to(device)
 
     def step():
         for t in list(params.values()) + list(grids.values()):
             t.grad = None
-        d, u, c, w = O.render_batch_ray(params, grids, rays_d, rays_o, scene.tsdf_volume, scene.tsdf_bnds, scene.bound,
-                                        STAGE, gt)
+        d, u, c, w = O.render_batch_ray(params, grids, rays_d, rays_o, tsdf, tb, scene.bound, STAGE, gt)
         loss = O.mapper_loss(d, c, w, gt, gt_color, STAGE)
         loss.backward()
         return float(loss)
 
+    return step, n_sample
+
+
+def run_reference(args):
+    """The reference arm: the reference's algorithm for the path (its PyTorch ops, restated in oracle/ and pinned
+    bit-exactly to the reference's outputs; the reference itself is Python and does not exist on the GPU box) on the
+    host cores, or with --device cuda on the GPU as the honest GPU comparator.  Same workload / config as our arm;
+    each step is a bounded sample of the batch (stated in cpu_baseline.sample)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from attentive_dfprior_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = args.device
+    scene = synth.make_scene("room0", seed=0, high_std=1e-2)
+    step, n = oracle_step_factory(scene, args.rays, args.ref_rays, dev)
+    sync = torch.cuda.synchronize if dev != "cpu" else (lambda: None)
     for _ in range(args.warmup):
         step()
+    sync()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
+    sync()
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
-    sample = f"{n} rays/step x {args.steps} steps, room0 shapes, stage {STAGE}, fwd+bwd, torch CPU {cores} threads"
+    where = f"torch CPU {cores} threads" if dev == "cpu" else f"torch {dev} (fp32, allow_tf32=False)"
+    sample = (f"each step = {n} rays sampled evenly from the {args.rays}-ray batch, x {args.steps} steps, stage {STAGE}, "
+              f"fwd+bwd, oracle port of the reference's PyTorch path, {where}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "replica_room0_mapping_iteration", "stage": STAGE, "rays_per_step": n,
-                   "samples_per_ray": S, "note": "oracle port of the reference PyTorch path on host cores"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.rays, args.gpus, tsdf_shape=list(scene.tsdf_volume.shape[2:])),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores if dev == "cpu" else 0, "kind": "port", "sample": sample,
+                         "device": dev},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def cpu_baseline(scene_cpu_factory, budget_s=20.0):
+def cpu_baseline(scene_cpu, n_total, budget_s=20.0):
     """Bounded sample of the same workload through the oracle on the host cores (rank 0, N=1 only)."""
-    from attentive_dfprior_b200 import synth
-    from oracle import dfprior_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    scene = scene_cpu_factory()
-    n = 1000
-    params = {k: v.requires_grad_(True) for k, v in O.init_decoder_params(0).items()}
-    grids = {k: v.requires_grad_(True) for k, v in scene.grids.items()}
-    rays_o, rays_d, gt, gt_color = synth.make_rays(scene, n, seed=1)
-
-    def step():
-        for t in list(params.values()) + list(grids.values()):
-            t.grad = None
-        d, u, c, w = O.render_batch_ray(params, grids, rays_d, rays_o, scene.tsdf_volume, scene.tsdf_bnds, scene.bound,
-                                        STAGE, gt)
-        O.mapper_loss(d, c, w, gt, gt_color, STAGE).backward()
-
+    step, n = oracle_step_factory(scene_cpu, n_total, 1024, "cpu")
     step()
     t0 = time.perf_counter()
     reps = 0
@@ -181,32 +201,67 @@ def cpu_baseline(scene_cpu_factory, budget_s=20.0):
         reps += 1
     dt = time.perf_counter() - t0
     return {"value": n * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{reps} x {n}-ray mapping steps (stage {STAGE}, fwd+bwd, room0 shapes) through the oracle, "
-                      f"torch CPU {cores} threads"}
+            "sample": f"{reps} steps of {n} rays sampled evenly from the {n_total}-ray batch (stage {STAGE}, fwd+bwd, room0 shapes) "
+                      f"through the oracle, torch CPU {cores} threads"}
+
+
+def torch_gpu_baseline(scene_cpu, n_total, n_sample=8192, reps=5):
+    """The reference's PyTorch ops for the same step on the B200 itself (BASELINE.md section 2 / SURVEY 8d: the honest GPU
+    comparator): the oracle port on cuda:0, fp32 with TF32 off, CUDA-event timed."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    step, n = oracle_step_factory(scene_cpu, n_total, n_sample, "cuda:0")
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    return {"value": n / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "kind": "port on cuda:0",
+            "sample": f"{reps} steps of {n} rays sampled evenly from the {n_total}-ray batch, torch {torch.__version__} eager, "
+                      f"fp32 (allow_tf32=False), loss .item() closes each step"}
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-NCU_SUMMARY = "profiles/r01_ncu_full_summary_planes.csv"
+NCU_TRAFFIC = "profiles/ncu_traffic.json"       # written by tools/ncu_summarize.py from an `ncu --set full` capture of this bench
+
+
+def kernel_source_hash():
+    """sha256 over the CUDA sources + public header: identifies the build a profile was taken from (there is no .git on
+    the GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    roots = [os.path.join(REPO, "attentive_dfprior_b200", "csrc"), os.path.join(REPO, "include")]
+    for root in roots:
+        for name in sorted(os.listdir(root)):
+            if name.endswith((".cu", ".cuh", ".h", ".inl")):
+                h.update(name.encode())
+                h.update(open(os.path.join(root, name), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def ncu_traffic(kernels):
     """DRAM bytes (read + write) of the named kernels' launches during ONE step of the default workload, from the
-    committed `ncu --set full` capture of `bench.py --steps 1` (profiles/); None when the file is missing."""
-    path = os.path.join(REPO, NCU_SUMMARY)
+    committed `ncu --set full` capture (profiles/ncu_traffic.json).  Returns (bytes or None, note): None when there is
+    no capture or when it was taken from different kernel sources than the ones being benchmarked."""
+    path = os.path.join(REPO, NCU_TRAFFIC)
     if not os.path.exists(path):
-        return None
-    import csv
-    rows = list(csv.reader(open(path)))
-    hdr, units = rows[0], rows[1]
-    ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
-    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        return None, "no ncu capture committed"
+    d = json.load(open(path))
+    mine = kernel_source_hash()
+    if d.get("source_hash") != mine:
+        return None, f"ncu capture is from sources {d.get('source_hash')}, benchmarked sources are {mine}: not reported"
     total = 0.0
-    for r in rows[2:]:
-        if any(k in r[ik] for k in kernels):
-            total += float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
-    return total or None
+    for name, rec in d.get("kernels", {}).items():
+        if any(k == name or name.startswith(k + "<") for k in kernels):
+            total += rec["dram_bytes_per_step"]
+    return (total or None), f"{NCU_TRAFFIC} (ncu --set full, {d.get('command', '?')}; sources {mine})"
 
 
 def run_ours(args):
@@ -259,7 +314,6 @@ def run_ours(args):
 
     def step(ro, rd, g, gc):
         zero_grads()
-        A.decoder.param_pack_of(model).key = None                      # decoders change every mapping iteration: re-pack
         d, u, c, w = D.render_batch_ray_sharded(renderer, grids, model, rd, ro, scene.tsdf_volume, scene.tsdf_bnds,
                                                 STAGE, g, group=group)
         if args.torch_loss:
@@ -319,23 +373,71 @@ def run_ours(args):
     # because the steps contain collectives, rank 0 reports
     prof_steps = 3
     kt = L.kernel_times(lambda: [step_dev() for _ in range(prof_steps)])
-    # the reference's own batch size (1000 mapping pixels per step over all ranks) as a latency figure
-    small = None
-    if not args.no_small:
-        n_small = max(1, 1000 // world)
-        ro, rd, g, gc = synth.make_rays(scene, n_small, seed=7 + rank, device=dev)
-        small_step = lambda: step(ro, rd, g, gc)
-        for _ in range(5):
-            small_step()
+    # the reference's own operating points as latency figures, device-resident and end to end (pinned host buffers in,
+    # loss / pose gradient out): Mapper 1000 pixels per step (configs/Replica/replica.yaml:23), Tracker 200 (:12-13)
+    def time_loop(fn, reps=30, warm=8):
+        for _ in range(warm):
+            fn()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(20):
-            small_step()
+        for _ in range(reps):
+            fn()
         b.record()
         torch.cuda.synchronize()
-        small = {"rays_per_step": n_small * world, "ms_per_step": a.elapsed_time(b) / 20,
-                 "rays_per_s": n_small * world * 20 / (a.elapsed_time(b) / 1e3)}
+        return a.elapsed_time(b) / reps
+
+    small = tracker = None
+    if not args.no_small:
+        n_small = max(1, 1000 // world)
+        sm_dev = synth.make_rays(scene, n_small, seed=7 + rank, device=dev)
+        sm_host = [t.cpu().pin_memory() for t in sm_dev]
+        ms_dev = time_loop(lambda: step(*sm_dev))
+        ms_e2e_small = time_loop(lambda: float(step(*[t.to(dev, non_blocking=True) for t in sm_host])))
+        small = {"rays_per_step": n_small * world, "ms_per_step": ms_dev, "rays_per_s": n_small * world / (ms_dev / 1e3),
+                 "e2e": {"ms_per_step": ms_e2e_small, "value": n_small * world / (ms_e2e_small / 1e3), "unit": UNIT,
+                         "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in sm_host), "d2h_bytes_per_step": 8}}
+        if world == 1:
+            # Tracker pose step (src/Tracker.py:83-133): 200 pixels, frozen decoders and grids, gradient to the camera 7-vector
+            from attentive_dfprior_b200 import common as CM
+            cam = scene.cam
+            tr_model = A.DF().to(dev)
+            for prm in tr_model.parameters():
+                prm.requires_grad_(False)
+            tgrids = {k: v.detach() for k, v in scene.grids.items()}
+            g = torch.Generator().manual_seed(11)
+            pi = torch.randint(100, cam["W"] - 100, (200,), generator=g).float()
+            pj = torch.randint(100, cam["H"] - 100, (200,), generator=g).float()
+            c2w0 = synth.make_pose(scene, 3)
+            with torch.no_grad():
+                ro0, rd0 = CM.get_rays_from_uv(pi, pj, c2w0, cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], "cpu")
+                tgt = synth.depth_along(scene, ro0, rd0)
+            tcol = torch.rand(200, 3, generator=g)
+            quat = torch.tensor([1.0, 0.0, 0.0, 0.0])
+            cam7 = torch.cat([quat, c2w0[:3, 3]]).to(dev).requires_grad_(True)
+            R0 = c2w0[:3, :3].to(dev)
+            tr_host = [t.pin_memory() for t in (pi, pj, tgt, tcol)]
+
+            def tracker_step(pi_, pj_, tg_, tc_):
+                cam7.grad = None
+                c2w = CM.get_camera_from_tensor(cam7)
+                c2w = torch.cat([R0 @ c2w[:3, :3], c2w[:3, 3:]], 1)
+                ro, rd = CM.get_rays_from_uv(pi_, pj_, c2w, cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], dev)
+                d, u, c, _ = renderer.render_batch_ray(tgrids, tr_model, rd, ro, dev, scene.tsdf_volume, scene.tsdf_bnds, STAGE, gt_depth=tg_)
+                u = u.detach()
+                tmp = torch.abs(tg_ - d) / torch.sqrt(u + 1e-10)
+                m = (tmp < 10 * tmp.median()) & (tg_ > 0)
+                loss = (torch.abs(tg_ - d) / torch.sqrt(u + 1e-10))[m].sum() + 0.5 * torch.abs(tc_ - c)[m].sum()
+                loss.backward()
+                return cam7.grad
+
+            tr_dev = [t.to(dev) for t in tr_host]
+            ms_tr = time_loop(lambda: tracker_step(*tr_dev))
+            ms_tr_e2e = time_loop(lambda: tracker_step(*[t.to(dev, non_blocking=True) for t in tr_host]).cpu())
+            tracker = {"rays_per_step": 200, "ms_per_step": ms_tr, "rays_per_s": 200 / (ms_tr / 1e3),
+                       "e2e": {"ms_per_step": ms_tr_e2e, "value": 200 / (ms_tr_e2e / 1e3), "unit": UNIT,
+                               "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in tr_host), "d2h_bytes_per_step": 28},
+                       "note": "pose chain and median-masked loss are torch ops (autograd carries d rays -> 7-vector); render fwd+bwd are the kernels"}
 
     out = None
     if rank == 0:
@@ -357,36 +459,51 @@ def run_ours(args):
         bytes_per_step = sum(kb.values()) * ns                       # the three decoders of stage `color`
         achieved = bytes_per_step / (op_ms[top_op] / 1e3) / 1e9 if op_ms[top_op] > 0 else 0.0
         step_gbs = value / world * BYTES_PER_RAY[STAGE] / 1e9
+        traffic, traffic_note = ncu_traffic(kernels) if (n == 65536 and world == 1) else (None, "only captured for the default 1-GPU workload")
+        # arithmetic side: >= 333 kFLOP per sample fwd+bwd (MLP MACs x 2, minimum-needed count)
+        flop_per_sample = 333e3
+        tflops = value / world * S * flop_per_sample / 1e12
         roofline = {"bound": "hbm", "kernel": top_op + " (" + " + ".join(k for k in kernels if k in kt) + ")",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ncu_traffic(kernels) if (n == 65536 and world == 1) else None,
-                    "traffic_source": NCU_SUMMARY + " (dram read+write of these kernels' launches in one step, ncu --set full)",
+                    "traffic": traffic, "traffic_source": traffic_note,
                     "peak_source": peak_src,
                     "kernel_share_of_step": op_ms[top_op] * prof_steps / total_kernel_ms if total_kernel_ms else None,
                     "algorithmic_bytes_per_step": bytes_per_step, "op_ms_per_step": op_ms[top_op],
                     "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak,
                                    "bytes_per_ray": BYTES_PER_RAY[STAGE]},
+                    "flops": {"algorithmic_flop_per_sample": flop_per_sample, "achieved_tflops": tflops,
+                              "frac_of_fp32_simt_peak": tflops / 80.0, "fp32_simt_peak_tflops": 80.0,
+                              "frac_of_tf32_tensor_peak": tflops / 1100.0, "tf32_tensor_peak_tflops": 1100.0,
+                              "note": "SURVEY 8d minimum-needed MLP flops; peaks are nominal B200 figures (no measured fp32/tf32 peak in MEASURED_PEAKS.json); the kernels spend 3 tensor-core MMAs per algorithmic one (3xTF32 / bf16 hi+mid split)"},
                     "kernels_ms_per_step": {k: round(v[1] / prof_steps, 4) for k, v in sorted(kt.items())}}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "replica_room0_mapping_iteration", "stage": STAGE, "rays_per_gpu_per_step": n,
-                       "samples_per_ray": S, "grids": "low[21,28,37] high/color[43,56,74] x32, " +
-                       ("channels_last_3d" if not args.channels_first else "channels_first (transposed per call)"),
-                       "tsdf": list(scene.tsdf_volume.shape[2:]), "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": f"ray-sharded dp{world}" + (" + NCCL all-reduce of grid/decoder grads" if world > 1 else ""),
-                       "mlp": "tcgen05 3xTF32 tensor-core path" if os.environ.get("DFP_TENSOR_CORES", "1") != "0" else "fp32 SIMT",
-                       "loss": "Mapper depth L1 + 0.2 colour L1" + (" (torch ops)" if args.torch_loss else " (mapper_ops.mapper_loss kernel)")},
+            "config": workload_config(n, world, tsdf_shape=list(scene.tsdf_volume.shape[2:])),
+            "impl_details": {
+                "grid_layout": "channels_last_3d" if not args.channels_first else "channels_first (transposed per call)",
+                "collective": "NCCL all-reduce (sum) of one flat grid+decoder gradient buffer, all-reduce (max) of gt_depth" if world > 1 else None,
+                "mlp": "tcgen05 tensor-core kernels", "kernel_source_hash": kernel_source_hash(),
+                "loss_impl": "torch ops" if args.torch_loss else "mapper_ops.mapper_loss kernel"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         }
         if small is not None:
             out["mapping_1000_rays"] = small
+        if tracker is not None:
+            out["tracker_200_rays"] = tracker
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         del flush
-        out["cpu_baseline"] = cpu_baseline(lambda: synth.make_scene("room0", seed=0, high_std=1e-2))
+        scene_cpu = synth.make_scene("room0", seed=0, high_std=1e-2)
+        if not args.no_gpu_baseline:
+            try:
+                out["torch_gpu_baseline"] = torch_gpu_baseline(scene_cpu, n)
+            except Exception as e:                      # e.g. out of memory on a smaller GPU: report, do not fail the bench
+                out["torch_gpu_baseline"] = {"unavailable": repr(e)[:200]}
+            torch.cuda.empty_cache()
+        out["cpu_baseline"] = cpu_baseline(scene_cpu, n)
     if rank == 0:
         print(json.dumps(out))
     if group is not None:
@@ -401,7 +518,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=65536, help="rays per GPU per step")
-    ap.add_argument("--ref-rays", type=int, default=1000, help="rays per step of the CPU reference arm")
+    ap.add_argument("--ref-rays", type=int, default=2048, help="reference arm: rays per step sampled from the --rays batch")
+    ap.add_argument("--device", default="cpu", help="reference arm: cpu (default) or cuda:0 (the reference's ops on the GPU)")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-on-GPU comparator of our arm")
     ap.add_argument("--channels-first", action="store_true", help="keep the grids channels-first (transposed per call)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-small", action="store_true")

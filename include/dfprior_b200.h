@@ -17,7 +17,9 @@
  *  - gradient buffers are ACCUMULATED INTO (caller zeroes them), so a caller
  *    may chunk a batch over several calls.
  *  - stateless and re-entrant: forward and backward may come from different
- *    host threads (autograd engine thread).
+ *    host threads (autograd engine thread); no environment variable or setter
+ *    changes what a call computes (the only process-wide state is the launch
+ *    counter and the opt-in event timing of the diagnostics section).
  */
 #ifndef DFPRIOR_B200_H
 #define DFPRIOR_B200_H
@@ -29,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFP_ABI_VERSION 3
+#define DFP_ABI_VERSION 4
 
 #define DFP_C_DIM 32            /* configs/df_prior.yaml:102 (model.c_dim) */
 #define DFP_HIDDEN 32           /* src/conv_onet/models/decoder.py:278 */
@@ -51,6 +53,10 @@ typedef enum DfpStage { DFP_STAGE_LOW = 0, DFP_STAGE_HIGH = 1, DFP_STAGE_COLOR =
 /* forward-call flags */
 #define DFP_FLAG_SAVE_ACT 1    /* a backward call will follow: the tensor-core forward keeps the decoders' layer
                                   activations in the (larger) workspace so that the backward need not recompute them */
+#define DFP_FLAG_SIMT 2        /* evaluate the MLPs with the fp32 SIMT kernels instead of the tcgen05 tensor-core
+                                  kernels (in-tree cross-check of the product path; several times slower).  Like
+                                  every flag it belongs to the call: pass the same value to the workspace-size
+                                  function, the forward and the backward.  The library keeps no switches. */
 
 /* One feature grid.  Logical shape is the reference's [1, C, D, H, W]
  * (src/DF_Prior.py:243-266) but memory is channels-last: element (z, y, x, c)
@@ -280,21 +286,6 @@ int dfp_mapper_loss(const DfpMapLoss* l, void* stream);
  * every launch be bracketed by CUDA events on its own stream; dfp_timing_collect waits for them
  * and writes "<kernel> <launches> <total_ms>\n" per kernel name into buf. */
 int64_t dfp_launch_count(void);
-/* 1 (default): MLP layers on the tcgen05 tensor cores (3xTF32); 0: fp32 SIMT kernels.  Env DFP_TENSOR_CORES=0 too. */
-int dfp_set_tensor_cores(int on);
-/* 2 (default): tensor-core backward; 1: tensor-core delta chain + SIMT weight gradients; 0: SIMT recompute backward */
-int dfp_set_tc_backward(int level);
-/* development probe of tcgen05 shared-memory descriptor semantics (see csrc/dfp_tc_selftest.cu) */
-int dfp_probe_tc(float* D, int32_t N, int32_t b_mn, int32_t lbo, int32_t sbo, int32_t k_hot, int32_t layout_type,
-                 int32_t start_off, void* stream);
-/* development probe of the bf16 MN-major (row-per-sample) operand layouts used by the weight-gradient kernel */
-int dfp_probe_bf16(const float* A, const float* B, float* D, int32_t N, int32_t fmt, int32_t layout_type, int32_t lbo_a, int32_t lbo_b,
-                   int32_t sbo, int32_t kstep_a, int32_t kstep_b, void* stream);
-/* development probe (not yet run on hardware): the plane layout read as a K-major bf16 A operand whose MN dimension is the sample */
-int dfp_probe_bf16_k(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b,
-                     int32_t sbo_b, void* stream);
-/* tensor-core self test: D[128,N] = A[128,K] * W[N,K]^T through the tcgen05/TMEM path (split=1: 3xTF32) */
-int dfp_selftest_tc(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t split, void* stream);
 int dfp_timing_enable(int on);
 int dfp_timing_collect(char* buf, size_t buf_bytes);
 

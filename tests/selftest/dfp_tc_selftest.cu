@@ -1,11 +1,26 @@
+// TEST INFRASTRUCTURE (built as tests/selftest/libdfp_selftest.so, not part of libdfprior_b200.so or its public header).
 // Self-test of the tcgen05 building blocks (dfp_tc.cuh): D[128 x N] = A[128 x K] * W[N x K]^T with the A operand
 // written into TMEM by its owner threads, W in the canonical shared-memory layout, the 3xTF32 split, and D read
 // back from TMEM.  tests/test_gpu_tc.py compares it with an f64 matmul.
 #include "dfp_device.cuh"
 #include "dfp_tc.cuh"
 #include <cuda_bf16.h>
+#include <stdarg.h>
+#include <stdio.h>
 
 namespace dfp {
+
+// the plumbing the shared internal header expects from its host library (the product's lives in dfp_api.cu)
+static thread_local char g_selftest_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_selftest_err, sizeof(g_selftest_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void timing_begin(const char*, cudaStream_t) {}
+void timing_end(cudaStream_t) {}
 
 __global__ void __launch_bounds__(128) k_tc_selftest(const float* __restrict__ A, const float* __restrict__ W,
                                                      float* __restrict__ D, int K, int N, int split) {
@@ -342,6 +357,11 @@ __global__ void __launch_bounds__(128) k_tc_probe_bf16(const float* __restrict__
 // layout ([8-sample group][8-feature chunk][sample][feature], dfp_planes.cuh) read as a K-major operand whose MN
 // dimension is the sample (candidate: LBO = 128 between feature chunks, SBO = 16 K between sample groups) and W in the
 // canonical K-major core-matrix layout ((k/8) * N*16 + n*16 + (k%8)*2 bytes; candidate LBO = N*16, SBO = 128).
+// BMN = true: the transposed use of the same weight image (backward chain): D[128 x N] = A[128 x K] * Wt[K x N] where
+// Wt[j][k] = weight of output j, input k, stored as the FORWARD's canonical image ((k/8) * K*16 + j*16 + (k%8)*2 bytes,
+// K = number of outputs j = contraction here) and read as an MN-major B operand (candidate: LBO = 128 between 8-j
+// groups, SBO = K*16 between 8-k chunks).
+template <bool BMN>
 __global__ void __launch_bounds__(128) k_tc_probe_bf16_k(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ D,
                                                          int K, int N, int lbo_a, int sbo_a, int lbo_b, int sbo_b) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -356,8 +376,13 @@ __global__ void __launch_bounds__(128) k_tc_probe_bf16_k(const float* __restrict
     for (int f = 0; f < K; ++f)
         *reinterpret_cast<__nv_bfloat16*>(sa + (tid >> 3) * 16 * K + (f >> 3) * 128 + (tid & 7) * 16 + (f & 7) * 2) = __float2bfloat16_rn(A[tid * K + f]);
     for (int i = tid; i < N * K; i += 128) {
-        const int n = i / K, k = i % K;
-        *reinterpret_cast<__nv_bfloat16*>(sb + (k >> 3) * N * 16 + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(W[n * K + k]);
+        if (!BMN) {
+            const int n = i / K, k = i % K;
+            *reinterpret_cast<__nv_bfloat16*>(sb + (k >> 3) * N * 16 + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(W[n * K + k]);
+        } else {
+            const int j = i / N, k = i % N;             // W given as Wt[K = J][N = KIN]
+            *reinterpret_cast<__nv_bfloat16*>(sb + (k >> 3) * K * 16 + j * 16 + (k & 7) * 2) = __float2bfloat16_rn(W[j * N + k]);
+        }
     }
     if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 128); tc::tmem_relinquish(); }
     if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
@@ -368,13 +393,13 @@ __global__ void __launch_bounds__(128) k_tc_probe_bf16_k(const float* __restrict
     const uint32_t tbase = tmem_base_s;
     const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
     if (tid == 0) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);   // both K-major
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BMN ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
         auto desc = [&](uint32_t addr, uint32_t lbo, uint32_t sbo) {
             return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
         };
         for (int ks = 0; ks < K / 16; ++ks) {                 // 16 features per MMA = two 8-feature chunks
             const uint64_t da = desc(tc::smem_u32(sa) + ks * 2 * 128, (uint32_t)lbo_a, (uint32_t)sbo_a);
-            const uint64_t db = desc(tc::smem_u32(sb) + ks * 2 * N * 16, (uint32_t)lbo_b, (uint32_t)sbo_b);
+            const uint64_t db = desc(tc::smem_u32(sb) + (BMN ? ks * 2 * 128 : ks * 2 * N * 16), (uint32_t)lbo_b, (uint32_t)sbo_b);
             tc::mma_bf16_ss(tbase, da, db, idesc, ks > 0 ? 1u : 0u);
         }
         tc::mma_commit(&bar);
@@ -393,12 +418,13 @@ __global__ void __launch_bounds__(128) k_tc_probe_bf16_k(const float* __restrict
     if (warp == 0) tc::tmem_dealloc(tbase, 128);
 }
 int launch_tc_probe_bf16_k(const float* A, const float* W, float* D, int K, int N, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool bmn = false) {
     if (K < 16 || K > 128 || K % 16 || N < 16 || N > 128 || N % 16) return fail(DFP_ERR_INVALID, "bad probe shape");
     const size_t smem = 65536 + 1024;
-    int rc = set_smem(k_tc_probe_bf16_k, smem);
+    int rc = bmn ? set_smem(k_tc_probe_bf16_k<true>, smem) : set_smem(k_tc_probe_bf16_k<false>, smem);
     if (rc) return rc;
-    DFP_TIMED("k_tc_probe_bf16_k", st, k_tc_probe_bf16_k<<<1, 128, smem, st>>>(A, W, D, K, N, lbo_a, sbo_a, lbo_b, sbo_b));
+    if (bmn) k_tc_probe_bf16_k<true><<<1, 128, smem, st>>>(A, W, D, K, N, lbo_a, sbo_a, lbo_b, sbo_b);
+    else k_tc_probe_bf16_k<false><<<1, 128, smem, st>>>(A, W, D, K, N, lbo_a, sbo_a, lbo_b, sbo_b);
     DFP_LAUNCH_CHECK("k_tc_probe_bf16_k");
     return DFP_OK;
 }
@@ -466,3 +492,35 @@ int launch_tc_selftest(const float* A, const float* W, float* D, int K, int N, i
 }
 
 }  // namespace dfp
+
+// C entry points of the self-test library (bound by tests/selftest/binding.py)
+using namespace dfp;
+extern "C" {
+const char* dfpt_last_error(void) { return g_selftest_err; }
+// D[128,N] = A[128,K] * W[N,K]^T through the tcgen05/TMEM path (split=1: 3xTF32; 11 / 12: transposed-weight / outer-product patterns)
+int dfpt_selftest_tc(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t split, void* stream) {
+    if (!A || !W || !D) return fail(DFP_ERR_INVALID, "null argument");
+    return launch_tc_selftest(A, W, D, K, N, split, (cudaStream_t)stream);
+}
+// probes of tcgen05 shared-memory descriptor semantics
+int dfpt_probe_tc(float* D, int32_t N, int32_t b_mn, int32_t lbo, int32_t sbo, int32_t k_hot, int32_t layout_type,
+                  int32_t start_off, void* stream) {
+    if (!D) return fail(DFP_ERR_INVALID, "null argument");
+    return launch_tc_probe(D, N, b_mn, lbo, sbo, k_hot, layout_type, start_off, (cudaStream_t)stream);
+}
+int dfpt_probe_bf16_k(const float* A, const float* W, float* D, int32_t K, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b,
+                      int32_t sbo_b, void* stream) {
+    if (!A || !W || !D) return fail(DFP_ERR_INVALID, "null argument");
+    return launch_tc_probe_bf16_k(A, W, D, K, N, lbo_a, sbo_a, lbo_b, sbo_b, (cudaStream_t)stream);
+}
+int dfpt_probe_bf16_kt(const float* A, const float* Wt, float* D, int32_t K, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b,
+                       int32_t sbo_b, void* stream) {
+    if (!A || !Wt || !D) return fail(DFP_ERR_INVALID, "null argument");
+    return launch_tc_probe_bf16_k(A, Wt, D, K, N, lbo_a, sbo_a, lbo_b, sbo_b, (cudaStream_t)stream, true);
+}
+int dfpt_probe_bf16(const float* A, const float* B, float* D, int32_t N, int32_t fmt, int32_t layout_type, int32_t lbo_a, int32_t lbo_b,
+                    int32_t sbo, int32_t kstep_a, int32_t kstep_b, void* stream) {
+    if (!A || !B || !D) return fail(DFP_ERR_INVALID, "null argument");
+    return launch_tc_probe_bf16(A, B, D, N, fmt, layout_type, lbo_a, lbo_b, sbo, kstep_a, kstep_b, (cudaStream_t)stream);
+}
+}  // extern "C"

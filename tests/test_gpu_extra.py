@@ -1,0 +1,304 @@
+"""GPU parity tests for the entry points, branches and process-level behaviour round 1 left unchecked:
+
+* gt_depth=None (Renderer.py:140-142,161-162) and uncertainty gradients, against reference-generated fixtures;
+* Renderer/Mesher.eval_points_tsdf + sample_grid_tsdf (Renderer.py:73-107), Mesher.eval_points / query_occupancy
+  (Mesher.py:286-326, 437-448) against the reference's own methods (fixtures);
+* two scenes with different bounds in ONE process (the stale-bounds bug of round 1), parameter writes through .data;
+* a random 2 000-ray subset of the 65 536-ray benchmark batch against the oracle, forward and grid/decoder gradients;
+* the Mapper's non-leaf channels-first grid flow (val[mask] = val_grad, Mapper.py:351-361,383-388);
+* automatic ray chunking of training calls whose saved operands exceed the workspace budget.
+"""
+import gc
+
+import pytest
+import torch
+
+from oracle import dfprior_oracle as O
+from test_gpu_parity import DEV, build, rel_err
+from test_oracle_extra import extra_loss, load_extra
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("name", ["extra_nodepth_color", "extra_unc_high"])
+def test_extra_render_fixture(name, channels_last):
+    from attentive_dfprior_b200 import functional as Fn
+    fx = load_extra(name)
+    inp, ref, stage = fx["inputs"], fx["outputs"], fx["stage"]
+    model, renderer, grids, tsdf, tb = build(inp, channels_last)
+    grids = {k: v.requires_grad_(True) for k, v in grids.items()}
+    gt = inp["gt_depth"].to(DEV) if fx["with_depth"] else None
+    rays_o, rays_d = inp["rays_o"].to(DEV), inp["rays_d"].to(DEV)
+    N = rays_o.shape[0]
+    S = 48 if fx["with_depth"] else 32
+    (_, _, _, w0), aux = Fn.render_batch_ray(grids, model, rays_d, rays_o, tsdf, tb, inp["bound"], stage, gt_depth=gt, want_aux=True)
+    assert aux["z"].shape == (N, S) and torch.equal(aux["z"].cpu(), ref["z"]), "sample depths must be bit-exact"
+    raw_ref = ref["raw"].reshape(N, S, 4)
+    assert torch.equal(aux["raw"].cpu()[..., 3] == 100, raw_ref[..., 3] == 100)
+    assert torch.equal(w0.cpu().reshape(N, S) != 1, ref["weight"].reshape(N, S) != 1)
+
+    depth, unc, color, weight = renderer.render_batch_ray(grids, model, rays_d, rays_o, DEV, tsdf, tb, stage, gt_depth=gt)
+    assert depth.dtype == torch.float64 and unc.dtype == torch.float64 and weight.shape == (N, S, 1)
+    assert rel_err(depth, ref["depth"], name + ".depth") <= 1e-4
+    assert rel_err(unc, ref["uncertainty"], name + ".uncertainty") <= 1e-4
+    if stage == "color":
+        assert rel_err(color, ref["color"], name + ".color") <= 1e-4
+    assert rel_err(weight, ref["weight"], name + ".weight") <= 1e-4
+    loss = extra_loss(fx, depth, unc, color, weight)
+    loss.backward()
+    assert abs(float(loss) - float(ref["loss"])) <= 1e-4 * abs(float(ref["loss"]))
+    for k, g in fx["grads"]["grids"].items():
+        if g is not None and float(g.abs().max()) > 0:
+            assert rel_err(grids[k].grad, g, name + ".grad." + k) <= 1e-3, k
+    named = dict(model.named_parameters())
+    for k, g in fx["grads"]["params"].items():
+        if g is not None and float(g.abs().max()) > 0:
+            assert rel_err(named[k].grad, g, name + ".grad.decoders") <= 1e-3, k
+
+
+def test_tsdf_sampling_matches_reference():
+    """Renderer / Mesher eval_points_tsdf and sample_grid_tsdf (dfp_tsdf_sample) on f64 and f32 points."""
+    import attentive_dfprior_b200 as A
+    from attentive_dfprior_b200.config import default_cfg, slam_namespace
+    fx = load_extra("extra_tsdf_points")
+    inp, ref = fx["inputs"], fx["outputs"]
+    tsdf, tb = inp["tsdf_volume"].to(DEV), inp["tsdf_bnds"].to(DEV)
+    renderer = A.Renderer(default_cfg(), None, slam_namespace(inp["bound"], tb), points_batch_size=300)
+    mesher = A.Mesher(default_cfg(), None, slam_namespace(inp["bound"], tb), points_batch_size=300)
+    for tag in ("f64", "f32"):
+        p = inp["p64" if tag == "f64" else "p32"].to(DEV)
+        for obj in (renderer, mesher):
+            v = obj.eval_points_tsdf(p, tsdf, DEV)
+            g = obj.sample_grid_tsdf(p, tsdf, DEV)
+            assert v.shape == ref["vals_" + tag].shape and g.shape == ref["grid_" + tag].shape
+            assert float((v.cpu() - ref["vals_" + tag]).abs().max()) <= 2e-6, tag
+            assert float((g.cpu() - ref["grid_" + tag]).abs().max()) <= 2e-6, tag
+            # the band classification (strictly inside (-1, 1) up to 1e-4, Mesher.py:443) must agree wherever the reference value is not on the edge
+            rv = ref["vals_" + tag]
+            clear = ((rv + 1).abs() > 1e-3) & ((rv - 1).abs() > 1e-3)
+            band = lambda t: (t > -1.0 + 1e-4) & (t < 1.0 - 1e-4)
+            assert torch.equal(band(v.cpu())[clear], band(rv)[clear])
+
+
+def test_mesher_query_matches_reference():
+    """Mesher.eval_points (f32 lattice points, all stages) and query_occupancy against the reference's Mesher methods."""
+    import attentive_dfprior_b200 as A
+    from attentive_dfprior_b200.config import default_cfg, slam_namespace
+    fx = load_extra("extra_mesher")
+    inp, ref = fx["inputs"], fx["outputs"]
+    model, _, grids, tsdf, tb = build(inp)
+    cfg = default_cfg()
+    cfg["meshing"]["resolution"] = inp["resolution"]
+    cfg["mapping"] = dict(cfg.get("mapping", {}), marching_cubes_bound=inp["marching_cubes_bound"].tolist())
+    mesher = A.Mesher(cfg, None, slam_namespace(inp["bound"], tb), points_batch_size=700)
+    pts = mesher.get_grid_uniform(inp["resolution"])["grid_points"]
+    assert torch.equal(pts, ref["grid_points"])
+    for st, r in ref["ret"].items():
+        ret = mesher.eval_points(pts.to(DEV), model, tsdf, tb, grids, st, DEV)
+        assert ret.shape == r.shape
+        assert torch.equal(ret[:, 3].cpu() == 100, r[:, 3] == 100), st
+        scale = float(r[:, 3][r[:, 3] != 100].abs().max())
+        assert float((ret.cpu() - r).abs().max()) <= 1e-4 * max(scale, 1.0), st
+    inside = torch.rand(pts.shape[0], generator=torch.Generator().manual_seed(0)) < 0.8
+    z = mesher.query_occupancy(grids, model, tsdf, DEV, inside_mask=inside.numpy())
+    zr = torch.where(inside, ref["ret"]["high"][:, -1], torch.full_like(ref["ret"]["high"][:, -1], 100.0))   # Mesher.py:448
+    assert torch.equal(z.cpu() == 100, zr == 100)
+    assert float((z.cpu() - zr).abs().max()) <= 1e-4 * max(float(zr[zr != 100].abs().max()), 1.0)
+
+
+def _render_small_vs_oracle(seed):
+    import attentive_dfprior_b200 as A
+    from attentive_dfprior_b200 import synth
+    from attentive_dfprior_b200.config import default_cfg, slam_namespace
+    scene = synth.make_scene("small", seed=seed, high_std=1e-2)
+    torch.manual_seed(seed)
+    model = A.DF()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    rays_o, rays_d, gt, _ = synth.make_rays(scene, 64, seed=seed)
+    d_ref, u_ref, c_ref, w_ref = O.render_batch_ray(sd, scene.grids, rays_d, rays_o, scene.tsdf_volume, scene.tsdf_bnds,
+                                                    scene.bound, "color", gt)
+    sc = scene.to(DEV)
+    renderer = A.Renderer(default_cfg(), None, slam_namespace(scene.bound, sc.tsdf_bnds))
+    with torch.no_grad():
+        d, u, c, w = renderer.render_batch_ray(sc.grids, model.to(DEV), rays_d.to(DEV), rays_o.to(DEV), DEV, sc.tsdf_volume,
+                                               sc.tsdf_bnds, "color", gt_depth=gt.to(DEV))
+    return max(rel_err(d, d_ref), rel_err(u, u_ref), rel_err(c, c_ref), rel_err(w, w_ref))
+
+
+def test_two_scenes_in_one_process():
+    """Regression for round 1's address-keyed bounds cache: render a room0 scene, free it, then render small scenes whose
+    freshly allocated bound tensors reuse the freed addresses -- every render must still match the oracle."""
+    import attentive_dfprior_b200 as A
+    from attentive_dfprior_b200 import synth
+    from attentive_dfprior_b200.config import default_cfg, slam_namespace
+    for rep in range(3):
+        scene = synth.make_scene("room0", seed=rep, device=DEV, high_std=1e-2, voxel=16.0 / 256)
+        model = A.DF().to(DEV)
+        renderer = A.Renderer(default_cfg(), None, slam_namespace(scene.bound, scene.tsdf_bnds))
+        rays_o, rays_d, gt, _ = synth.make_rays(scene, 256, seed=rep, device=DEV)
+        with torch.no_grad():
+            renderer.render_batch_ray(scene.grids, model, rays_d, rays_o, DEV, scene.tsdf_volume, scene.tsdf_bnds, "color", gt_depth=gt)
+        del scene, model, renderer, rays_o, rays_d, gt
+        gc.collect()
+        for seed in (20 + rep, 30 + rep):
+            assert _render_small_vs_oracle(seed) <= 1e-4
+    # and directly: fresh [3,2] tensors (CPU and CUDA) never see another tensor's values
+    from attentive_dfprior_b200.functional import _bounds
+    for i in range(100):
+        t = torch.tensor([[i, i + 1.0], [0, 1.0], [0, 1.0]], dtype=torch.float64)
+        assert _bounds.get(t)[0][0] == i
+        tc = t.to(DEV)
+        assert _bounds.get(tc)[0][0] == i
+        del t, tc
+
+
+def test_parameter_writes_through_data_are_seen():
+    """An external optimiser writing through .data / raw pointers does not bump Parameter._version: the packed
+    copy must still follow, and a pending backward must use the weights of ITS forward."""
+    fx = load_extra("extra_unc_high")
+    inp = fx["inputs"]
+    model, renderer, grids, tsdf, tb = build(inp)
+    p = torch.rand(400, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    p = (p * (inp["bound"][:, 1] - inp["bound"][:, 0]) + inp["bound"][:, 0])
+    sd = {k: v.clone() for k, v in inp["state_dict"].items()}
+    raw_ref, _ = O.eval_points(sd, p, inp["grids"], inp["tsdf_volume"], inp["tsdf_bnds"], inp["bound"], "high")
+    with torch.no_grad():
+        a, _ = renderer.eval_points(p.to(DEV), model, tsdf, tb, grids, "high", DEV)
+    assert float((a.cpu() - raw_ref).abs().max()) <= 1e-4
+    # forward that needs grad, then a .data write BEFORE its backward: the backward must not see the new weights
+    g1 = {k: v.clone().requires_grad_(True) for k, v in grids.items()}
+    raw, _ = renderer.eval_points(p.to(DEV), model, tsdf, tb, g1, "high", DEV)
+    version = model.low_decoder.output_linear.bias._version
+    model.low_decoder.output_linear.bias.data.add_(0.25)
+    model.low_decoder.pts_linears[1].weight.data.mul_(1.5)
+    assert model.low_decoder.output_linear.bias._version == version, "test premise: .data writes do not bump the version"
+    raw[:, 3].sum().backward()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    gcpu = {k: v.clone().requires_grad_(True) for k, v in inp["grids"].items()}
+    r2, _ = O.eval_points(params, p, gcpu, inp["tsdf_volume"], inp["tsdf_bnds"], inp["bound"], "high")
+    r2[:, 3].sum().backward()
+    assert rel_err(g1["grid_low"].grad, gcpu["grid_low"].grad) <= 1e-3
+    # and the next forward sees the written weights
+    sd2 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    raw_ref2, _ = O.eval_points(sd2, p, inp["grids"], inp["tsdf_volume"], inp["tsdf_bnds"], inp["bound"], "high")
+    with torch.no_grad():
+        b, _ = renderer.eval_points(p.to(DEV), model, tsdf, tb, grids, "high", DEV)
+    assert float((b.cpu() - raw_ref2).abs().max()) <= 1e-4
+    assert float((b - a).abs().max()) > 1e-2
+
+
+def test_bench_batch_subset_matches_oracle():
+    """The benchmark's own configuration (room0, full-resolution TSDF, 65 536 rays, stage colour): 2 000 random rays of
+    the batch against the oracle -- outputs, and the gradients of a loss restricted to those rays."""
+    import attentive_dfprior_b200 as A
+    from attentive_dfprior_b200 import synth
+    from attentive_dfprior_b200.config import default_cfg, slam_namespace
+    torch.manual_seed(0)
+    scene = synth.make_scene("room0", seed=0, high_std=1e-2)
+    model = A.DF()
+    with torch.no_grad():
+        for dec in (model.low_decoder, model.high_decoder):
+            dec.output_linear.weight.mul_(0.05)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    N = 65536
+    rays_o, rays_d, gt, gt_color = synth.make_rays(scene, N, seed=100)
+    sub = torch.randperm(N, generator=torch.Generator().manual_seed(1))[:2000]
+    sub[0] = int(gt.argmax())                                  # the far clamp uses the batch max (Renderer.py:159): keep it in the subset
+    sub = sub.sort()[0]
+
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    gcpu = {k: v.clone().requires_grad_(True) for k, v in scene.grids.items()}
+    torch.set_num_threads(16)
+    d_ref, u_ref, c_ref, w_ref = O.render_batch_ray(params, gcpu, rays_d[sub], rays_o[sub], scene.tsdf_volume, scene.tsdf_bnds,
+                                                    scene.bound, "color", gt[sub])
+    O.mapper_loss(d_ref, c_ref, w_ref, gt[sub], gt_color[sub], "color").backward()
+
+    sc = scene.to(DEV)
+    model = model.to(DEV)
+    grids = {k: v.contiguous(memory_format=torch.channels_last_3d).requires_grad_(True) for k, v in sc.grids.items()}
+    renderer = A.Renderer(default_cfg(), None, slam_namespace(scene.bound, sc.tsdf_bnds))
+    d, u, c, w = renderer.render_batch_ray(grids, model, rays_d.to(DEV), rays_o.to(DEV), DEV, sc.tsdf_volume, sc.tsdf_bnds, "color",
+                                           gt_depth=gt.to(DEV))
+    sd_ = sub.to(DEV)
+    assert rel_err(d[sd_], d_ref, "bench65536_subset.depth") <= 1e-4 and rel_err(u[sd_], u_ref, "bench65536_subset.uncertainty") <= 1e-4
+    assert rel_err(c[sd_], c_ref, "bench65536_subset.color") <= 1e-4 and rel_err(w[sd_], w_ref, "bench65536_subset.weight") <= 1e-4
+    g = gt.to(DEV)[sd_]
+    m = g > 0
+    (torch.abs(g[m] - d[sd_][m]).sum() + 0.2 * torch.abs(gt_color.to(DEV)[sd_] - c[sd_]).sum()).backward()
+    for k in grids:
+        assert rel_err(grids[k].grad, gcpu[k].grad, "bench65536_subset.grad." + k) <= 1e-3, k
+    named = dict(model.named_parameters())
+    for k, v in params.items():
+        if v.grad is not None and float(v.grad.abs().max()) > 0:
+            assert rel_err(named[k].grad, v.grad, "bench65536_subset.grad.decoders") <= 1e-3, k
+
+
+def test_mapper_nonleaf_channels_first_grid_flow():
+    """src/Mapper.py:351-361,383-388: the optimised tensor is val[mask] (a leaf), the grid handed to the renderer is the
+    non-leaf channels-first result of val[mask] = val_grad; gradients must arrive in val_grad."""
+    fx = load_extra("extra_nodepth_color")
+    inp = fx["inputs"]
+    model, renderer, grids, tsdf, tb = build(inp, channels_last=False)
+    gen = torch.Generator().manual_seed(4)
+    gt = inp["gt_depth"]
+    leaves_gpu, leaves_cpu, c_gpu, c_cpu, masks = {}, {}, {}, {}, {}
+    for k, v in inp["grids"].items():
+        mask = (torch.rand(v.shape[2:], generator=gen) < 0.6)[None, None].repeat(1, v.shape[1], 1, 1, 1)     # Mapper.py:347-350
+        masks[k] = mask
+        for dev, leaves, c in (("cpu", leaves_cpu, c_cpu), (DEV, leaves_gpu, c_gpu)):
+            val = v.clone().to(dev)
+            val_grad = val[mask.to(dev)].clone().requires_grad_(True)
+            val[mask.to(dev)] = val_grad
+            leaves[k], c[k] = val_grad, val
+    sd = {k: v.clone() for k, v in inp["state_dict"].items()}
+    d_ref, u_ref, c_ref, w_ref = O.render_batch_ray(sd, c_cpu, inp["rays_d"], inp["rays_o"], inp["tsdf_volume"], inp["tsdf_bnds"],
+                                                    inp["bound"], "color", gt)
+    O.mapper_loss(d_ref, c_ref, w_ref, gt, inp["gt_color"], "color", attn_term=True).backward()
+    for prm in model.parameters():
+        prm.requires_grad_(False)
+    d, u, c, w = renderer.render_batch_ray(c_gpu, model, inp["rays_d"].to(DEV), inp["rays_o"].to(DEV), DEV, tsdf, tb, "color",
+                                           gt_depth=gt.to(DEV))
+    g = gt.to(DEV)
+    m = g > 0
+    (torch.abs(g[m] - d[m]).sum() + torch.abs(w - 1).sum() + 0.2 * torch.abs(inp["gt_color"].to(DEV) - c).sum()).backward()
+    assert rel_err(d, d_ref) <= 1e-4
+    for k in leaves_cpu:
+        assert leaves_gpu[k].grad is not None and leaves_gpu[k].grad.shape == leaves_cpu[k].grad.shape
+        assert rel_err(leaves_gpu[k].grad, leaves_cpu[k].grad) <= 1e-3, k
+
+
+def test_training_call_is_chunked_when_workspace_exceeds_budget():
+    """A training call whose saved operands exceed the budget runs in ray chunks (forward keeps nothing, the backward
+    re-runs each chunk's forward): same outputs bit for bit, same gradients up to the order of the atomic sums."""
+    import attentive_dfprior_b200 as A
+    from attentive_dfprior_b200 import functional as Fn
+    from attentive_dfprior_b200 import synth
+    scene = synth.make_scene("small", seed=9, device=DEV, high_std=1e-2, channels_last=True)
+    torch.manual_seed(9)
+    model = A.DF().to(DEV)
+    with torch.no_grad():
+        for dec in (model.low_decoder, model.high_decoder):
+            dec.output_linear.weight.mul_(0.05)
+    rays_o, rays_d, gt, gc_ = synth.make_rays(scene, 3000, seed=9, device=DEV)
+    res = []
+    for budget in (None, 6 << 20):                    # 6 MiB: a few hundred rays per chunk
+        grids = {k: v.detach().clone().requires_grad_(True) for k, v in scene.grids.items()}
+        for prm in model.parameters():
+            prm.grad = None
+        ro = rays_o.clone().requires_grad_(True)
+        d, u, c, w = Fn.render_batch_ray(grids, model, rays_d, ro, scene.tsdf_volume, scene.tsdf_bnds, scene.bound, "color",
+                                         gt_depth=gt, workspace_budget=budget)
+        m = gt > 0
+        (torch.abs(gt[m] - d[m]).sum() + 0.2 * torch.abs(gc_ - c).sum() + torch.abs(w - 1).sum()).backward()
+        res.append((d.detach(), u.detach(), c.detach(), w.detach(), ro.grad.clone(), {k: v.grad.clone() for k, v in grids.items()},
+                    [q.grad.clone() for q in model.parameters()]))
+    a, b = res
+    for i in range(4):
+        assert torch.equal(a[i], b[i])
+    assert rel_err(b[4], a[4]) <= 1e-5
+    for k in a[5]:
+        assert rel_err(b[5][k], a[5][k]) <= 1e-5, k
+    for x, y in zip(b[6], a[6]):
+        if float(y.abs().max()) > 0:
+            assert rel_err(x, y) <= 1e-4

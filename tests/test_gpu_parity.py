@@ -275,19 +275,35 @@ def test_properties_at_full_size():
 
 
 def test_decoder_module_semantics():
-    """deepcopy / state_dict round trip / parameter updates are picked up (src/Tracker.py:144, Logger.py:26)."""
+    """deepcopy / state_dict round trip / in-place parameter updates (src/Tracker.py:144, Logger.py:26), each result
+    compared with the oracle evaluated on the corresponding state_dict."""
     fx = load_golden("map_high_s1")
     inp = fx["inputs"]
     model, renderer, grids, tsdf, tb = build(inp)
-    p = _random_points(inp["bound"], 500, 3, torch.float64).to(DEV)
+    p_cpu = _random_points(inp["bound"], 500, 3, torch.float64)
+    p = p_cpu.to(DEV)
+
+    def oracle(sd):
+        raw, _ = O.eval_points({k: v.detach().cpu() for k, v in sd.items()}, p_cpu, inp["grids"], inp["tsdf_volume"],
+                               inp["tsdf_bnds"], inp["bound"], "high")
+        return raw
+
+    def close(x, ref):
+        scale = float(ref[:, 3][ref[:, 3] != 100].abs().max())
+        return float((x.cpu() - ref).abs().max()) <= 1e-4 * max(scale, 1.0)
+
     with torch.no_grad():
+        ref_a = oracle(model.state_dict())
         a, _ = renderer.eval_points(p, model, tsdf, tb, grids, "high", DEV)
+        assert close(a, ref_a)
         m2 = copy.deepcopy(model)
         b, _ = renderer.eval_points(p, m2, tsdf, tb, grids, "high", DEV)
         assert torch.equal(a, b)
-        model.low_decoder.output_linear.bias.add_(0.25)          # in-place update must invalidate the packed copy
+        model.low_decoder.output_linear.bias.add_(0.25)          # an in-place update is picked up by the next call
         c, _ = renderer.eval_points(p, model, tsdf, tb, grids, "high", DEV)
         assert not torch.equal(a, c)
+        assert close(c, oracle(model.state_dict()))
+        assert not close(c, ref_a)
         m3 = type(model)().to(DEV)
         m3.load_state_dict(m2.state_dict())
         d, _ = renderer.eval_points(p, m3, tsdf, tb, grids, "high", DEV)
@@ -309,8 +325,7 @@ def test_errors_are_loud():
 
 
 def test_smoke_case_64_rays():
-    """The driver's smoke() case as a test: 64 rays of the small scene.  With so few band samples the fusion MLP's
-    parameter gradients are tiny sums, so this is the case that notices forward errors moving ReLU masks (it caught an
-    SFU-based sin in the forward kernel that every larger case tolerated)."""
+    """The driver's smoke() case as a test: 64 rays of the small scene, run here AFTER other scenes have been rendered in
+    the same process (round 1 failed exactly this: an address-keyed bounds cache handed the small scene room0's box)."""
     import __graft_entry__ as G
     G.smoke()

@@ -3,7 +3,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from attentive_dfprior_b200 import _lib as L
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "selftest"))
+import binding as L
 
 lib = L.lib()
 torch.manual_seed(0)
@@ -26,7 +27,7 @@ for N in (64, 32, 96, 128):
                   (f"sw128 type{lt} lbo=1024 sbo=16384", 2, lt, 1024, 1024, 16384, 2048, 2048)]
     for name, fmt, lt, lbo_a, lbo_b, sbo, ka, kb in cands:
         D = torch.zeros(128, N, device=dev)
-        L.check(lib.dfp_probe_bf16(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, fmt, lt, lbo_a, lbo_b, sbo, ka, kb, None))
+        L.check(lib.dfpt_probe_bf16(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, fmt, lt, lbo_a, lbo_b, sbo, ka, kb, None))
         torch.cuda.synchronize()
         rows = torch.tensor([(m // 16) * 32 + m % 16 for m in range(64)], device=dev)
         got = D[rows]

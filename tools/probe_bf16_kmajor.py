@@ -1,10 +1,11 @@
-"""Hardware probe for the planned attention chain (run on the GPU box; NOT yet run): can the plane layout be read as a
+"""Hardware probe for the attention chain (run on the GPU box): can the plane layout be read as a
 K-major bf16 A operand with the sample as the MN dimension?  Prints the max error of D = A W^T for the candidate
 descriptor readings."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from attentive_dfprior_b200 import _lib as L
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "selftest"))
+import binding as L
 
 lib = L.lib()
 torch.manual_seed(0)
@@ -19,7 +20,21 @@ for K, N in ((64, 128), (128, 128), (128, 64), (32, 32)):
              ("A: lbo=16K sbo=128 | W: lbo=128 sbo=N*16", 16 * K, 128, 128, N * 16)]
     for name, la, sa, lb, sb in cands:
         D = torch.zeros(128, N, device=dev)
-        L.check(lib.dfp_probe_bf16_k(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N, la, sa, lb, sb, None))
+        L.check(lib.dfpt_probe_bf16_k(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N, la, sa, lb, sb, None))
         torch.cuda.synchronize()
         err = (D - ref).abs().max().item()
         print(f"K={K:4d} N={N:4d} {name:44s} max_err={err:.3e} {'OK' if err < 1e-3 else ''}")
+
+print("---- transposed read of the forward weight image (backward chain): D = A[128,J] @ Wt[J,KIN]")
+for J, KIN in ((64, 128), (128, 128), (128, 64), (32, 32)):
+    A = torch.randn(128, J, device=dev).bfloat16().float()
+    Wt = torch.randn(J, KIN, device=dev).bfloat16().float()
+    ref = (A.double() @ Wt.double()).float()
+    cands = [("A: lbo=128 sbo=16J | Wt: lbo=128 sbo=J*16", 128, 16 * J, 128, J * 16),
+             ("A: lbo=128 sbo=16J | Wt: lbo=J*16 sbo=128", 128, 16 * J, J * 16, 128)]
+    for name, la, sa, lb, sb in cands:
+        D = torch.zeros(128, KIN, device=dev)
+        L.check(lib.dfpt_probe_bf16_kt(A.data_ptr(), Wt.data_ptr(), D.data_ptr(), J, KIN, la, sa, lb, sb, None))
+        torch.cuda.synchronize()
+        err = (D - ref).abs().max().item()
+        print(f"J={J:4d} KIN={KIN:4d} {name:44s} max_err={err:.3e} {'OK' if err < 1e-3 else ''}")
