@@ -145,6 +145,50 @@ def decoder_mlp(params: Params, name: str, p: torch.Tensor, grids: Dict[str, tor
     return out if name == "color" else out.squeeze(-1)
 
 
+def relu_margin(params: Params, p: torch.Tensor, grids, tsdf_volume, tsdf_bnds, bound, stage: str = "color") -> torch.Tensor:
+    """Conditioning of a point for GRADIENT comparisons: the smallest RELATIVE pre-activation |z| / (|W| |h| + |b|) over
+    every ReLU the stage evaluates at p (decoders and, inside the TSDF band, the fusion MLP), computed in f64 from f32
+    parameters.  The denominator is the magnitude of the terms the unit sums, i.e. the scale of any fp32 evaluation's
+    rounding error.  The path's gradient is discontinuous where a pre-activation crosses zero, so two correct fp32
+    implementations (relative error ~1e-6 of that scale) can differ by a whole unit's gradient at a point whose margin
+    is that small; parity tests that put equal upstream weight on every point drop such points (test infrastructure,
+    not a reference line)."""
+    p = p.reshape(-1, 3).double()
+    P64 = {k: v.detach().double() for k, v in params.items()}
+    G64 = {k: v.detach().double() for k, v in grids.items()}
+    margin = torch.full((p.shape[0],), float("inf"), dtype=torch.float64)
+    outs = {}
+    for name in {"low": ("low",), "high": ("high", "low"), "color": ("high", "color", "low")}[stage]:
+        pre = f"{name}_decoder."
+        c = trilinear_gather(G64["grid_" + name], p, bound).transpose(1, 2).squeeze(0)
+        if name == "high":
+            c = torch.cat([c, trilinear_gather(G64["grid_low"], p, bound).transpose(1, 2).squeeze(0)], dim=1)
+        emb = fourier_embed(p.float().double(), P64[pre + "embedder._B"])
+        h = emb
+        for i in range(N_BLOCKS):
+            Wm, bm = P64[pre + f"pts_linears.{i}.weight"], P64[pre + f"pts_linears.{i}.bias"]
+            z = F.linear(h, Wm, bm)
+            margin = torch.minimum(margin, (z.abs() / (F.linear(h.abs(), Wm.abs(), bm.abs()) + 1e-300)).min(dim=1)[0])
+            h = F.relu(z) + F.linear(c, P64[pre + f"fc_c.{i}.weight"], P64[pre + f"fc_c.{i}.bias"])
+            if i == SKIP_AFTER:
+                h = torch.cat([emb, h], -1)
+        outs[name] = F.linear(h, P64[pre + "output_linear.weight"], P64[pre + "output_linear.bias"])
+    if stage != "low":
+        tv = trilinear_gather(tsdf_volume.double(), p, tsdf_bnds).reshape(-1)
+        m = band_mask(tv)
+        if bool(m.any()):
+            x = torch.stack([(outs["high"].squeeze(-1) + outs["low"].squeeze(-1))[m], tsdf_to_logit(tv[m])], dim=1)
+            h = x
+            mm = torch.full((int(m.sum()),), float("inf"), dtype=torch.float64)
+            for i in range(4):
+                Wm, bm = P64[f"mlp.pts_linears.{i}.weight"], P64[f"mlp.pts_linears.{i}.bias"]
+                z = F.linear(h, Wm, bm)
+                mm = torch.minimum(mm, (z.abs() / (F.linear(h.abs(), Wm.abs(), bm.abs()) + 1e-300)).min(dim=1)[0])
+                h = F.relu(z)
+            margin = margin.index_put((m,), torch.minimum(margin[m], mm))
+    return margin
+
+
 def tsdf_to_logit(tsdf_val: torch.Tensor) -> torch.Tensor:
     """TSDF value -> occupancy logit -- decoder.py:244-248."""
     t = 1. - (tsdf_val + 1.) / 2.

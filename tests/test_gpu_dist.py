@@ -48,7 +48,28 @@ def _worker(rank, world, port, ret):
         def rel(a, b):
             return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
         worst = max([rel(gg_sh[k], gg_full[k]) for k in gg_full] + [rel(a, b) for a, b in zip(gp_sh, gp_full) if float(b.abs().max()) > 0])
-        ret[rank] = (ok, worst)
+
+        # BASELINE config 4: chunk-sharded render_img against the single-GPU frame (bit-exact: per-chunk maxima are
+        # chunk-local, no collective on the data path)
+        cam = dict(H=24, W=40, fx=30.0, fy=30.0, cx=19.5, cy=11.5)
+        r2 = A.Renderer(default_cfg(), None, slam_namespace(scene.bound, scene.tsdf_bnds, cam), ray_batch_size=96)
+        scene.cam = cam
+        c2w = synth.make_pose(scene, 2).to(dev)
+        gt_img = synth.make_depth_image(scene, c2w, device=dev, seed=3)
+        full = r2.render_img(scene.grids, model, c2w, dev, scene.tsdf_volume, scene.tsdf_bnds, "color", gt_depth=gt_img)
+        shard = D.render_img_sharded(r2, scene.grids, model, c2w, dev, scene.tsdf_volume, scene.tsdf_bnds, "color", gt_img,
+                                     group=dist.group.WORLD)
+        ok_img = all(bool(torch.equal(a, b)) for a, b in zip(full, shard))
+
+        # BASELINE config 5: voxel-block sharded Mesher query against the single-GPU query (bit-exact)
+        cfg = default_cfg()
+        cfg["meshing"]["resolution"] = 20
+        cfg["mapping"]["marching_cubes_bound"] = synth.SMALL_BOUND
+        mesher = A.Mesher(cfg, None, slam_namespace(scene.bound, scene.tsdf_bnds), points_batch_size=1500)
+        z_full = mesher.query_occupancy(scene.grids, model, scene.tsdf_volume, dev)
+        z_sh = mesher.query_occupancy(scene.grids, model, scene.tsdf_volume, dev, group=dist.group.WORLD)
+        ok_mesh = bool(torch.equal(z_full, z_sh)) and z_full.shape[0] == 20 ** 3
+        ret[rank] = (ok, worst, ok_img, ok_mesh)
     finally:
         dist.destroy_process_group()
 
@@ -60,6 +81,8 @@ def test_sharded_step_matches_single_gpu():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, 29611, ret), nprocs=2, join=True)
     for r in range(2):
-        ok, worst = ret[r]
+        ok, worst, ok_img, ok_mesh = ret[r]
         assert ok, "sharded outputs differ from the single-GPU outputs"
         assert worst <= 1e-4, worst
+        assert ok_img, "chunk-sharded render_img differs from the single-GPU frame"
+        assert ok_mesh, "voxel-block sharded Mesher query differs from the single-GPU query"

@@ -14,7 +14,7 @@ import pytest
 import torch
 
 from oracle import dfprior_oracle as O
-from test_gpu_parity import DEV, build, rel_err
+from test_gpu_parity import DEV, build, rel_err, within
 from test_oracle_extra import extra_loss, load_extra
 
 pytestmark = pytest.mark.gpu
@@ -108,22 +108,27 @@ def test_mesher_query_matches_reference():
 
 
 def _render_small_vs_oracle(seed):
+    """64 rays of a fresh small scene against the oracle; True when all four outputs are within 1e-4."""
     import attentive_dfprior_b200 as A
     from attentive_dfprior_b200 import synth
     from attentive_dfprior_b200.config import default_cfg, slam_namespace
     scene = synth.make_scene("small", seed=seed, high_std=1e-2)
     torch.manual_seed(seed)
     model = A.DF()
+    with torch.no_grad():
+        for dec in (model.low_decoder, model.high_decoder):        # un-saturate sigmoid(10*occ), as every gradient fixture does
+            dec.output_linear.weight.mul_(0.05)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     rays_o, rays_d, gt, _ = synth.make_rays(scene, 64, seed=seed)
-    d_ref, u_ref, c_ref, w_ref = O.render_batch_ray(sd, scene.grids, rays_d, rays_o, scene.tsdf_volume, scene.tsdf_bnds,
-                                                    scene.bound, "color", gt)
+    ref = O.render_batch_ray(sd, scene.grids, rays_d, rays_o, scene.tsdf_volume, scene.tsdf_bnds, scene.bound, "color", gt)
+    truth = O.render_batch_ray({k: v.double() for k, v in sd.items()}, {k: v.double() for k, v in scene.grids.items()}, rays_d,
+                               rays_o, scene.tsdf_volume.double(), scene.tsdf_bnds, scene.bound, "color", gt)
     sc = scene.to(DEV)
     renderer = A.Renderer(default_cfg(), None, slam_namespace(scene.bound, sc.tsdf_bnds))
     with torch.no_grad():
-        d, u, c, w = renderer.render_batch_ray(sc.grids, model.to(DEV), rays_d.to(DEV), rays_o.to(DEV), DEV, sc.tsdf_volume,
-                                               sc.tsdf_bnds, "color", gt_depth=gt.to(DEV))
-    return max(rel_err(d, d_ref), rel_err(u, u_ref), rel_err(c, c_ref), rel_err(w, w_ref))
+        mine = renderer.render_batch_ray(sc.grids, model.to(DEV), rays_d.to(DEV), rays_o.to(DEV), DEV, sc.tsdf_volume,
+                                         sc.tsdf_bnds, "color", gt_depth=gt.to(DEV))
+    return all(within(m, r, t, 1e-4) for m, r, t in zip(mine, ref, truth))
 
 
 def test_two_scenes_in_one_process():
@@ -142,7 +147,7 @@ def test_two_scenes_in_one_process():
         del scene, model, renderer, rays_o, rays_d, gt
         gc.collect()
         for seed in (20 + rep, 30 + rep):
-            assert _render_small_vs_oracle(seed) <= 1e-4
+            assert _render_small_vs_oracle(seed), seed
     # and directly: fresh [3,2] tensors (CPU and CUDA) never see another tensor's values
     from attentive_dfprior_b200.functional import _bounds
     for i in range(100):
@@ -159,9 +164,14 @@ def test_parameter_writes_through_data_are_seen():
     fx = load_extra("extra_unc_high")
     inp = fx["inputs"]
     model, renderer, grids, tsdf, tb = build(inp)
-    p = torch.rand(400, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    p = torch.rand(420, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
     p = (p * (inp["bound"][:, 1] - inp["bound"][:, 0]) + inp["bound"][:, 0])
     sd = {k: v.clone() for k, v in inp["state_dict"].items()}
+    # every point carries the same upstream weight here, so one point sitting on a ReLU edge (relative pre-activation
+    # ~1e-6: sample 221 of this draw, pts_linears.3 of the low decoder) changes a voxel's gradient by 20 % depending on
+    # which side an implementation's rounding puts it: such points have no meaningful gradient tolerance and are dropped
+    p = p[O.relu_margin(sd, p, inp["grids"], inp["tsdf_volume"], inp["tsdf_bnds"], inp["bound"], "high") > 2e-5]
+    assert 380 <= p.shape[0] < 420
     raw_ref, _ = O.eval_points(sd, p, inp["grids"], inp["tsdf_volume"], inp["tsdf_bnds"], inp["bound"], "high")
     with torch.no_grad():
         a, _ = renderer.eval_points(p.to(DEV), model, tsdf, tb, grids, "high", DEV)

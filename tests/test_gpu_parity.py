@@ -28,6 +28,19 @@ def rel_err(a, b, tag=None):
     return e
 
 
+def within(mine, ref, truth, tol, tag=None):
+    """``mine`` within ``tol`` of the reference value ``ref`` (relative to the tensor's max).  Where the fp32 reference is
+    itself further than that from the f64 evaluation of the same formulas on the same input (``truth``; an
+    ill-conditioned input, e.g. one sample sitting on a ReLU edge: SURVEY.md appendix A.5 asks for exactly this
+    comparison), the gate is widened by the reference's own distance to the truth and ``mine`` must be within ``tol``
+    of the truth."""
+    e = rel_err(mine, ref, tag)
+    if e <= tol:
+        return True
+    e_ref = rel_err(ref, truth)
+    return e <= tol + e_ref and rel_err(mine, truth) <= tol
+
+
 @pytest.fixture(scope="module", autouse=True)
 def _dump_margins():
     """With DFP_PARITY_LOG=<file> the measured errors of the tagged comparisons are written out (profiles/ evidence)."""
@@ -156,17 +169,23 @@ def test_points_query_matches_oracle(stage, dtype):
     inp = fx["inputs"]
     model, renderer, grids, tsdf, tb = build(inp)
     p_cpu = _random_points(inp["bound"], 3000, 11, dtype)
-    params = {k: v.clone().requires_grad_(True) for k, v in inp["state_dict"].items()}
-    grids_cpu = {k: v.clone().requires_grad_(True) for k, v in inp["grids"].items()}
-    p_ref = p_cpu.clone().requires_grad_(True)
     torch.set_num_threads(8)
-    raw_ref, w_ref = O.eval_points(params, p_ref, grids_cpu, inp["tsdf_volume"], inp["tsdf_bnds"], inp["bound"], stage)
-    gr = torch.randn(raw_ref.shape, generator=torch.Generator().manual_seed(5))
-    gw = torch.randn(w_ref.shape, generator=torch.Generator().manual_seed(6))
-    ((raw_ref * gr).sum() + (w_ref * gw).sum()).backward()
+    gr = torch.randn(3000, 4, generator=torch.Generator().manual_seed(5))
+    gw = torch.randn(3000, generator=torch.Generator().manual_seed(6))
+
+    def oracle(prec):              # the reference's arithmetic (prec = f32) or the same formulas in f64 on the same points
+        params = {k: v.clone().to(prec).requires_grad_(True) for k, v in inp["state_dict"].items()}
+        grids_cpu = {k: v.clone().to(prec).requires_grad_(True) for k, v in inp["grids"].items()}
+        p_ref = (p_cpu.clone() if prec == torch.float32 else p_cpu.double().clone()).requires_grad_(True)
+        raw_ref, w_ref = O.eval_points(params, p_ref, grids_cpu, inp["tsdf_volume"].to(prec), inp["tsdf_bnds"], inp["bound"], stage)
+        ((raw_ref * gr.to(prec)).sum() + (w_ref * gw.to(prec)).sum()).backward()
+        return raw_ref.detach(), w_ref.detach(), params, grids_cpu, p_ref
+
+    raw_ref, w_ref, params, grids_cpu, p_ref = oracle(torch.float32)
+    _, _, params_t, grids_t, p_t = oracle(torch.float64)
 
     grids = {k: v.requires_grad_(True) for k, v in grids.items()}
-    p = p_cpu.to(DEV).requires_grad_(True)
+    p = p_cpu.detach().to(DEV).requires_grad_(True)
     raw, w = renderer.eval_points(p, model, tsdf, tb, grids, stage, DEV)
     assert torch.equal(raw[:, 3].cpu() == 100, raw_ref[:, 3] == 100)
     assert torch.equal(w.cpu() != 1, w_ref != 1)
@@ -176,12 +195,12 @@ def test_points_query_matches_oracle(stage, dtype):
     ((raw * gr.to(DEV)).sum() + (w * gw.to(DEV)).sum()).backward()
     for k, v in grids_cpu.items():
         if v.grad is not None and float(v.grad.abs().max()) > 0:
-            assert rel_err(grids[k].grad, v.grad) <= 1e-3, k
+            assert within(grids[k].grad, v.grad, grids_t[k].grad, 1e-3), k
     named = dict(model.named_parameters())
     for k, v in params.items():
         if v.grad is not None and float(v.grad.abs().max()) > 0:
-            assert rel_err(named[k].grad, v.grad) <= 1e-3, k
-    assert rel_err(p.grad, p_ref.grad) <= 1e-3
+            assert within(named[k].grad, v.grad, params_t[k].grad, 1e-3), k
+    assert within(p.grad, p_ref.grad, p_t.grad, 1e-3)
 
     # bare DF.forward: no out-of-bound override
     raw2, w2 = model(p.detach().unsqueeze(0), c_grid=grids, tsdf_volume=tsdf, tsdf_bnds=tb, stage=stage)
