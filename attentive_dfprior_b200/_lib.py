@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfprior_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 FLAG_SAVE_ACT = 1
 FLAG_SIMT = 2
 MAX_RAY_SAMPLES = 64
@@ -112,6 +112,7 @@ SYMBOLS = {
     "dfp_abi_version": (C.c_int, []),
     "dfp_last_error": (C.c_char_p, []),
     "dfp_packed_param_floats": (C.c_int64, []),
+    "dfp_packed_grad_floats": (C.c_int64, []),
     "dfp_pack_params": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "dfp_unpack_param_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfp_grid_to_ndhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

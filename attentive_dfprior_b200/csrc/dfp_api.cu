@@ -28,6 +28,7 @@
 
 #include "dfp_device.cuh"
 #include "dfp_planes.cuh"
+#include "dfp_attn_tc.cuh"
 
 namespace dfp {
 
@@ -125,8 +126,17 @@ static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with
     w.sc_dh = (float*)take(act ? pl::array_bytes(nsp, pl::F_DH) : 0);
     w.sc_darg = (float*)take(act ? pl::array_bytes(nsp, pl::F_DL0) : 0);
     w.sc_dl1 = (float*)take(act ? pl::array_bytes(nsp, pl::F_DL1) : 0);
-    w.att_act = (float*)take(act && stage >= DFP_STAGE_HIGH ? (size_t)nsp * ATT_ACT * 4 : 0);
-    if (!(act && stage >= DFP_STAGE_HIGH)) w.att_act = nullptr;
+    // fusion MLP (tensor-core path): activations, ReLU masks, softmax outputs kept by the forward and the delta planes of
+    // the backward, per 128-sample tile of the band list (which can be as long as the sample list)
+    const bool att = act && stage >= DFP_STAGE_HIGH;
+    const size_t ntile = (size_t)(nsp / 128);
+    w.att_act = nullptr;
+    w.att_planes = (unsigned char*)take(att ? ntile * att::G_TILE : 0);
+    w.att_masks = (uint32_t*)take(att ? ntile * att::MASK_WORDS * 128 * 4 : 0);
+    w.att_soft = (float*)take(att ? ntile * 256 * 4 : 0);
+    w.att_dplanes = (unsigned char*)take(att ? ntile * att::G_DTILE : 0);
+    w.att_tileflag = (int*)take(att ? ntile * 4 : 0);
+    if (!att) { w.att_planes = nullptr; w.att_masks = nullptr; w.att_soft = nullptr; w.att_dplanes = nullptr; w.att_tileflag = nullptr; }
     return off;
 }
 
@@ -378,7 +388,36 @@ __global__ void k_tsdf_sample(PointSrc ps, int64_t n, Bounds tb, DfpTsdf vol, fl
 // ------------------------------------------------------------------------------------------
 struct PtrTable { const float* p[N_TENSORS]; };
 
+constexpr int ATT_IMG_BLOCKS = 16;      // 4096 (row, 8-input chunk) tasks of the three wide fusion layers, 256 per block
+
 __global__ void k_pack_params(const PtrTable tab, float* __restrict__ packed) {
+    if (blockIdx.x >= N_TENSORS) {
+        // tensor-core image of the fusion MLP (dfp_layout.h, AttImg): 8 consecutive inputs of one output row are 32
+        // contiguous source bytes (torch keeps [out][in]) and one 16-byte core-matrix row of each plane
+        int task = (blockIdx.x - N_TENSORS) * blockDim.x + threadIdx.x;
+        unsigned char* img = reinterpret_cast<unsigned char*>(packed + OFF_ATT_IMG);
+        unsigned char* img16 = reinterpret_cast<unsigned char*>(packed + OFF_ATT_IMG_F16);
+        const float* src; int nin, nout, hi_off, mid_off;
+        if (task < 1024) { src = tab.p[71]; nin = 64; nout = 128; hi_off = AttImg::W2H; mid_off = AttImg::W2M; }
+        else if (task < 3072) { task -= 1024; src = tab.p[73]; nin = 128; nout = 128; hi_off = AttImg::W3H; mid_off = AttImg::W3M; }
+        else { task -= 3072; src = tab.p[75]; nin = 128; nout = 64; hi_off = AttImg::W4H; mid_off = AttImg::W4M; }
+        const int nchunk = nin / 8, j = task / nchunk, c = task % nchunk;
+        if (j < nout) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = src[j * nin + c * 8 + i];
+            uint4 hi, mid;
+            pl::split8<false>(v, hi, mid);
+            *reinterpret_cast<uint4*>(img + hi_off + c * (nout * 16) + j * 16) = hi;
+            *reinterpret_cast<uint4*>(img + mid_off + c * (nout * 16) + j * 16) = mid;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= ATT_IMG_F16_SCALE;
+            pl::split8<true>(v, hi, mid);
+            *reinterpret_cast<uint4*>(img16 + hi_off + c * (nout * 16) + j * 16) = hi;
+            *reinterpret_cast<uint4*>(img16 + mid_off + c * (nout * 16) + j * 16) = mid;
+        }
+        return;
+    }
     const int t = blockIdx.x;
     int rows, cols;
     tensor_shape(t, rows, cols);
@@ -480,8 +519,10 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
         memset(&aa, 0, sizeof(aa));
         aa.params = params; aa.band_list = w.band_list; aa.band_count = w.band_count;
         aa.low = w.low; aa.high = w.high; aa.tsdf = w.tsdf; aa.fused = w.fused; aa.w_attn = w.w_attn;
-        aa.act = (flags & DFP_FLAG_SAVE_ACT) ? w.att_act : nullptr;
-        if ((rc = launch_attn_fwd(aa, n, st))) return rc;
+        if (tcp) {
+            aa.tc_planes = save ? w.att_planes : nullptr; aa.tc_masks = save ? w.att_masks : nullptr; aa.tc_soft = save ? w.att_soft : nullptr;
+            if ((rc = launch_attn_fwd_tc(aa, n, st))) return rc;
+        } else if ((rc = launch_attn_fwd(aa, n, st))) return rc;
     }
     return DFP_OK;
 }
@@ -500,8 +541,11 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
         aa.ps = ps; aa.tsdf_bnds = to_bounds(sc->tsdf_bnds); aa.vol = sc->tsdf;
         aa.d_fused = w.d_fused; aa.g_w = g_w; aa.d_low = w.d_low; aa.d_high = w.d_high;
         aa.dp = want_dp ? w.dp : nullptr; aa.gparams = g->params_packed;
-        aa.act = (flags & DFP_FLAG_SAVE_ACT) ? w.att_act : nullptr;
-        if ((rc = launch_attn_bwd<MODE>(aa, n, st))) return rc;
+        if (flags_tc(flags) && (flags & DFP_FLAG_SAVE_ACT) && w.att_planes != nullptr) {
+            aa.tc_planes = w.att_planes; aa.tc_masks = w.att_masks; aa.tc_soft = w.att_soft; aa.tc_dplanes = w.att_dplanes;
+            aa.tc_tileflag = w.att_tileflag;
+            if ((rc = launch_attn_bwd_tc<MODE>(aa, n, st))) return rc;
+        } else if ((rc = launch_attn_bwd<MODE>(aa, n, st))) return rc;
     }
     DecArgs da;
     memset(&da, 0, sizeof(da));
@@ -554,7 +598,8 @@ extern "C" {
 
 int dfp_abi_version(void) { return DFP_ABI_VERSION; }
 const char* dfp_last_error(void) { return g_err; }
-int64_t dfp_packed_param_floats(void) { return PACKED_FLOATS; }
+int64_t dfp_packed_param_floats(void) { return PACKED_TOTAL_FLOATS; }
+int64_t dfp_packed_grad_floats(void) { return PACKED_FLOATS; }
 
 int64_t dfp_launch_count(void) { return (int64_t)g_launches.load(); }
 
@@ -600,7 +645,7 @@ int dfp_pack_params(const float* const* tensors79, float* packed, void* stream) 
         if (!tensors79[t]) return fail(DFP_ERR_INVALID, "parameter tensor %d is null", t);
         tab.p[t] = tensors79[t];
     }
-    DFP_TIMED("k_pack_params", (cudaStream_t)stream, k_pack_params<<<N_TENSORS, 256, 0, (cudaStream_t)stream>>>(tab, packed));
+    DFP_TIMED("k_pack_params", (cudaStream_t)stream, k_pack_params<<<N_TENSORS + ATT_IMG_BLOCKS, 256, 0, (cudaStream_t)stream>>>(tab, packed));
     DFP_LAUNCH_CHECK("k_pack_params");
     return DFP_OK;
 }

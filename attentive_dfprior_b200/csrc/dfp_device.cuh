@@ -101,7 +101,8 @@ struct Ws {                        // per-sample workspace arrays (NS samples)
     float* sc_dh;                  // DH:  gradient of each block's output (before the ReLU mask)
     float* sc_darg;                // DL0: upstream gradient and masked deltas of blocks 4, 2, 1, 3
     float* sc_dl1;                 // DL1: masked deltas of blocks 3, 0 and the gradient of the embedding arguments
-    float* att_act;                // fusion MLP activations per band-list position (AttArgs::act)
+    float* att_act;                // SIMT path: fusion MLP activations per band-list position (AttArgs::act)
+    unsigned char* att_planes; uint32_t* att_masks; float* att_soft; unsigned char* att_dplanes; int* att_tileflag;   // tensor-core path (AttArgs::tc_*)
 };
 
 
@@ -309,7 +310,13 @@ struct AttArgs {
     // backward
     PointSrc ps; Bounds tsdf_bnds; DfpTsdf vol;
     const float* d_fused; const float* g_w; float* d_low; float* d_high; float* dp; float* gparams;
-    float* act;                    // saved activations of the fusion MLP (ATT_ACT floats per band-list position), or null
+    float* act;                    // SIMT path: saved activations of the fusion MLP (ATT_ACT floats per band-list position), or null
+    // tensor-core path (dfp_attn_tc.cu), indexed by 128-sample tile of the band list; null = nothing kept
+    unsigned char* tc_planes;      // activations h1..h4 as bf16 planes (att::G_TILE bytes per tile)
+    uint32_t* tc_masks;            // ReLU masks (att::MASK_WORDS x 128 words per tile)
+    float* tc_soft;                // softmax outputs a0, a1 ([2][128] per tile)
+    unsigned char* tc_dplanes;     // backward: deltas d2, d3, d4, dl as planes (att::G_DTILE bytes per tile)
+    int* tc_tileflag;              // backward: 1 if the tile carries any upstream gradient
 };
 // h1 (64) | h2 (128) | h3 (128) | h4 (64) | a0 a1 | pad: index ((pos/32)*ATT_ACT + f)*32 + pos%32, so a warp's 32 positions coalesce
 constexpr int ATT_ACT = 388;
@@ -409,6 +416,8 @@ template <int DEC, int MODE> int launch_decoder_fwd_tc(const DecArgs& a, cudaStr
 template <int DEC, int MODE> int launch_decoder_dh_tc(const DecArgs& a, cudaStream_t st);      // backward K1: delta chain
 template <int DEC> int launch_decoder_dw_tc(const DecArgs& a, cudaStream_t st);                // backward K2: weight gradients
 int launch_attn_fwd(const AttArgs& a, int64_t n, cudaStream_t st);
+int launch_attn_fwd_tc(const AttArgs& a, int64_t n, cudaStream_t st);                            // tcgen05 path
+template <int MODE> int launch_attn_bwd_tc(const AttArgs& a, int64_t n, cudaStream_t st);        // delta chain + weight gradients
 template <int MODE> int launch_attn_bwd(const AttArgs& a, int64_t n, cudaStream_t st);
 
 }  // namespace dfp

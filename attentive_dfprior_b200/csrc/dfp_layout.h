@@ -57,7 +57,31 @@ constexpr int OFF_LOW = 0;
 constexpr int OFF_HIGH = OFF_LOW + DecOff<32>::SIZE;
 constexpr int OFF_COLOR = OFF_HIGH + DecOff<64>::SIZE;
 constexpr int OFF_ATT = OFF_COLOR + DecOff<32>::SIZE;
-constexpr int PACKED_FLOATS = OFF_ATT + AttOff::SIZE;
+constexpr int PACKED_FLOATS = OFF_ATT + AttOff::SIZE;      // fp32 parameters (and the size of a packed gradient)
+
+// ---- tensor-core operand images appended to the packed PARAMETER buffer by the pack kernel (not part of gradients) ----
+// Fusion MLP: the three wide layers as bf16 hi + mid planes (w ~= hi + mid, |w - hi - mid| <= 2^-18 |w|) in the
+// canonical K-major core-matrix order of a B operand with N = outputs:  byte(n = out j, k = in) =
+// (k/8) * (N*16) + n*16 + (k%8)*2.  The forward reads it K-major (LBO = N*16, SBO = 128); the backward chain reads the
+// very same bytes transposed as an MN-major operand (LBO = 128, SBO = N*16) -- both readings probed on B200
+// (tools/probe_bf16_kmajor.py).  One bulk copy brings the 128 KB into shared memory.
+struct AttImg {
+    static constexpr int W2H = 0;                          // pts_linears.1: in 64,  out 128   (bytes)
+    static constexpr int W2M = W2H + 64 * 128 * 2;
+    static constexpr int W3H = W2M + 64 * 128 * 2;         // pts_linears.2: in 128, out 128
+    static constexpr int W3M = W3H + 128 * 128 * 2;
+    static constexpr int W4H = W3M + 128 * 128 * 2;        // pts_linears.3: in 128, out 64
+    static constexpr int W4M = W4H + 128 * 64 * 2;
+    static constexpr int BYTES = W4M + 128 * 64 * 2;       // 131072
+};
+// Two copies: bf16 planes (fp32's exponent range: the backward chain multiplies them with gradients of arbitrary
+// scale) and fp16 planes for the forward (hi + mid = 22 mantissa bits, the accuracy of the decoders' 3xTF32 scheme:
+// the forward decides ReLU masks, and with bf16's 2^-17 about one band sample in 300 lands on the other side of an
+// edge than the fp32 reference does, which small gradient parity cases notice).
+constexpr float ATT_IMG_F16_SCALE = 64.f;          // the fp16 image holds 64 w: a weight of 0.1 keeps its "mid" part a normal fp16 number
+constexpr int OFF_ATT_IMG = (PACKED_FLOATS + 31) / 32 * 32;             // 128-byte aligned (bulk-copy source)
+constexpr int OFF_ATT_IMG_F16 = OFF_ATT_IMG + AttImg::BYTES / 4;
+constexpr int PACKED_TOTAL_FLOATS = OFF_ATT_IMG_F16 + AttImg::BYTES / 4;
 
 static_assert(DecOff<32>::SIZE % 4 == 0 && DecOff<64>::SIZE % 4 == 0 && AttOff::SIZE % 4 == 0, "float4 copies");
 

@@ -44,6 +44,29 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {        // 
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// fp16 variant of the split (11-bit mantissas: hi + mid carries 22 bits, for operands of bounded range)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {         // lo -> bits 0..15
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t v, float& lo, float& hi) {
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(v));
+}
+template <bool F16>
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& mid) {
+    uint32_t h[4], m[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float f0, f1;
+        if (F16) { h[i] = pack_f16x2(v[2 * i], v[2 * i + 1]); unpack_f16x2(h[i], f0, f1); }
+        else { h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]); f0 = __uint_as_float(h[i] << 16); f1 = __uint_as_float(h[i] & 0xffff0000u); }
+        m[i] = F16 ? pack_f16x2(v[2 * i] - f0, v[2 * i + 1] - f1) : pack_bf16x2(v[2 * i] - f0, v[2 * i + 1] - f1);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    mid = make_uint4(m[0], m[1], m[2], m[3]);
+}
+
 // 8 consecutive features [f0, f0+8) of sample s (list position): hi and mid planes, one 16-byte store each
 __device__ __forceinline__ void store8(unsigned char* base, int F, int64_t s, int f0, const float* v) {
     uint32_t h[4], m[4];

@@ -162,7 +162,7 @@ def _grads_struct(ctx, needs_grid, need_params, dev):
     g = L.DfpGrads()
     want = [k for k in GRID_KEYS if needs_grid.get(k) and ctx.grids_cl.get(k) is not None]
     sizes = [ctx.grids_cl[k].numel() for k in want]
-    npk = int(L.lib().dfp_packed_param_floats()) if need_params else 0
+    npk = int(L.lib().dfp_packed_grad_floats()) if need_params else 0
     pad = lambda n: (n + 63) // 64 * 64                              # keep every slice 256-byte aligned
     total = sum(pad(n) for n in sizes) + npk
     flat = torch.zeros(total, device=dev, dtype=torch.float32) if total else None

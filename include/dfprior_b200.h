@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFP_ABI_VERSION 4
+#define DFP_ABI_VERSION 5
 
 #define DFP_C_DIM 32            /* configs/df_prior.yaml:102 (model.c_dim) */
 #define DFP_HIDDEN 32           /* src/conv_onet/models/decoder.py:278 */
@@ -135,7 +135,7 @@ typedef struct DfpGrads {
     float* grid_low;           /* NDHWC, same shape as the grid, accumulated */
     float* grid_high;
     float* grid_color;
-    float* params_packed;      /* packed layout (dfp_packed_param_floats() floats), accumulated */
+    float* params_packed;      /* packed layout (dfp_packed_grad_floats() floats), accumulated */
     float* rays_o;             /* [n_rays,3] f32, overwritten */
     float* rays_d;             /* [n_rays,3] f32, overwritten */
     void* points;              /* dfp_points_bwd only: [n,3] in the points' dtype, overwritten */
@@ -160,7 +160,8 @@ const char* dfp_last_error(void);
  * are gathered into one kernel-friendly packed buffer (k-major weights, padded rows);
  * dfp_unpack_param_grads scatters a packed gradient back into a flat buffer holding
  * the 79 gradients back to back in native [out,in] layout (DFP_N_PARAMS floats). */
-int64_t dfp_packed_param_floats(void);
+int64_t dfp_packed_param_floats(void);   /* size of the packed PARAMETER buffer (fp32 parameters + tensor-core operand images) */
+int64_t dfp_packed_grad_floats(void);    /* size of a packed GRADIENT buffer (DfpGrads.params_packed): the fp32 part only */
 int dfp_pack_params(const float* const* tensors79, float* packed, void* stream);
 int dfp_unpack_param_grads(const float* packed_grad, float* native_flat, void* stream);
 
