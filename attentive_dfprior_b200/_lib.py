@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfprior_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 FLAG_SAVE_ACT = 1
 FLAG_SIMT = 2
 MAX_RAY_SAMPLES = 64
@@ -62,7 +62,8 @@ class DfpRenderOutGrad(C.Structure):
 
 class DfpGrads(C.Structure):
     _fields_ = [("grid_low", C.c_void_p), ("grid_high", C.c_void_p), ("grid_color", C.c_void_p),
-                ("params_packed", C.c_void_p), ("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("points", C.c_void_p)]
+                ("params_packed", C.c_void_p), ("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("points", C.c_void_p),
+                ("ev_high", C.c_void_p), ("ev_color", C.c_void_p)]
 
 
 class DfpPoints(C.Structure):

@@ -567,10 +567,12 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
         da.grid = sc->high; da.grid_low = sc->low; da.dout = w.d_high; da.ggrid = g->grid_high;
         if ((rc = run(std::integral_constant<int, 1>{}))) return rc;
     }
+    if (g->ev_high) DFP_CUDA(cudaEventRecord((cudaEvent_t)g->ev_high, st));        // grid_high's gradient is final
     if (stage == DFP_STAGE_COLOR) {
         da.grid = sc->color; da.dout = w.d_rgb; da.ggrid = g->grid_color;
         if ((rc = run(std::integral_constant<int, 2>{}))) return rc;
     }
+    if (g->ev_color) DFP_CUDA(cudaEventRecord((cudaEvent_t)g->ev_color, st));      // grid_color's gradient is final
     da.grid = sc->low; da.dout = w.d_low; da.ggrid = g->grid_low;
     if ((rc = run(std::integral_constant<int, 0>{}))) return rc;
     return DFP_OK;

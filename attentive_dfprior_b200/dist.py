@@ -49,18 +49,33 @@ def global_depth_max(gt_depth: torch.Tensor, group) -> torch.Tensor:
 
 
 def render_batch_ray_sharded(renderer, c, decoders, rays_d, rays_o, tsdf_volume, tsdf_bnds, stage, gt_depth=None,
-                             group=None):
+                             group=None, depth_max=None, overlap_allreduce=True):
     """``renderer.render_batch_ray`` on this rank's shard of a batch that is spread over ``group``.
 
     Outputs are the shard's; gradients of grids and decoders come back already summed over the ranks
-    (identical on every rank, so identical optimiser steps keep the replicas in sync)."""
+    (identical on every rank, so identical optimiser steps keep the replicas in sync).
+
+    ``depth_max``: max(gt_depth) of the WHOLE batch (the far clamp and the depth==0 sampling use it,
+    src/utils/Renderer.py:159,195).  A Mapper whose ranks all hold the keyframes computes it locally before dealing the
+    rays out and passes it here; without it the ranks agree on it with an all-reduce(max) -- one more collective and one
+    more synchronisation point per step.  The gradient all-reduce runs in three buckets on a side stream, each bucket as
+    soon as the backward has finished it (``overlap_allreduce=False``: one blocking all-reduce after the backward)."""
     if group is None:
         return renderer.render_batch_ray(c, decoders, rays_d, rays_o, rays_o.device, tsdf_volume, tsdf_bnds, stage,
                                          gt_depth=gt_depth)
-    dmax = global_depth_max(gt_depth, group) if gt_depth is not None else None
+    if gt_depth is None:
+        dmax = None
+    elif depth_max is not None:
+        dmax = torch.as_tensor(depth_max, dtype=torch.float32, device=rays_o.device).reshape(1)
+    else:
+        dmax = global_depth_max(gt_depth, group)
+    if rays_o.shape[0] == 0:
+        raise ValueError("this rank's shard is empty: deal at least one ray to every rank (interleaved_shard / shard_range "
+                         "of a batch with n >= world size), the other ranks would wait forever in the gradient all-reduce")
     return Fn.render_batch_ray(c, decoders, rays_d, rays_o, tsdf_volume, tsdf_bnds, renderer.bound, stage,
                                gt_depth=gt_depth, n_samples=renderer.N_samples, n_surface=renderer.N_surface,
-                               n_importance=renderer.N_importance, depth_max=dmax, group=group)
+                               n_importance=renderer.N_importance, depth_max=dmax, group=group,
+                               overlap_allreduce=overlap_allreduce)
 
 
 def gather_concat(x: torch.Tensor, sizes, group, dst: Optional[int] = None):

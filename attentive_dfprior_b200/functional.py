@@ -160,19 +160,23 @@ def _grads_struct(ctx, needs_grid, need_params, dev):
     All sinks are views of ONE flat zero-filled buffer (one memset; one all-reduce when the batch is sharded over
     ranks).  Grid gradients are channels-last views ([1,C,D,H,W] logical shape over an NDHWC slice)."""
     g = L.DfpGrads()
-    want = [k for k in GRID_KEYS if needs_grid.get(k) and ctx.grids_cl.get(k) is not None]
+    # bucket order of the sharded all-reduce: the big grids first (final early in the backward), then grid_low + parameters
+    order = ("grid_high", "grid_color", "grid_low")
+    want = [k for k in order if needs_grid.get(k) and ctx.grids_cl.get(k) is not None]
     sizes = [ctx.grids_cl[k].numel() for k in want]
     npk = int(L.lib().dfp_packed_grad_floats()) if need_params else 0
     pad = lambda n: (n + 63) // 64 * 64                              # keep every slice 256-byte aligned
     total = sum(pad(n) for n in sizes) + npk
     flat = torch.zeros(total, device=dev, dtype=torch.float32) if total else None
-    ggrids, off = {}, 0
+    ggrids, off, spans = {}, 0, {}
     for k, n in zip(want, sizes):
         _, C_, D_, H_, W_ = ctx.grids_cl[k].shape
         t = flat[off:off + n].view(1, D_, H_, W_, C_).permute(0, 4, 1, 2, 3)
         ggrids[k] = t
         setattr(g, k, t.data_ptr())
+        spans[k] = (off, off + pad(n))
         off += pad(n)
+    g._spans = spans
     gp = None
     if need_params:
         gp = flat[off:off + npk]
@@ -189,6 +193,44 @@ def _param_grads(gp, params, needs):
     # one C++ call makes the 79 shaped views (a Python slice/view/to per tensor cost 0.4 ms per step, measured)
     views = torch._C._nn.unflatten_dense_tensors(flat, list(params))
     return [(v if v.dtype == p.dtype else v.to(p.dtype)) if need else None for v, p, need in zip(views, params, needs)]
+
+
+_comm_streams = {}
+
+
+def _comm_stream(dev):
+    s = _comm_streams.get(dev)
+    if s is None:
+        s = _comm_streams[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def _reduce_buckets(flat, spans, overlap, group):
+    """All-reduce ``flat`` in three buckets on the side stream: grid_high as soon as the library has recorded its event,
+    grid_color likewise, then the rest (grid_low + packed parameter gradients) when the whole backward is enqueued.
+    Every rank issues the same collectives in the same order; the compute stream waits for the side stream at the end."""
+    import torch.distributed as dist
+    ev_high, ev_color, main, comm = overlap
+    flat.record_stream(comm)
+    done = 0
+    with torch.cuda.stream(comm):
+        for key, ev in (("grid_high", ev_high), ("grid_color", ev_color)):
+            if key in spans:
+                lo, hi = spans[key]
+                if lo != done:                                           # buckets are laid out in this order; be safe
+                    continue
+                comm.wait_event(ev)
+                dist.all_reduce(flat[lo:hi], group=group)
+                done = hi
+    tail = torch.cuda.Event()
+    tail.record(main)
+    with torch.cuda.stream(comm):
+        comm.wait_event(tail)
+        if done < flat.numel():
+            dist.all_reduce(flat[done:], group=group)
+    fin = torch.cuda.Event()
+    fin.record(comm)
+    main.wait_event(fin)
 
 
 # ----------------------------------------------------------------------------------------
@@ -285,6 +327,13 @@ class _RenderBatchRay(torch.autograd.Function):
                               prep(g_weight, torch.float32))
             gt = aux.gt_depth
             sl = lambda t, lo, hi: None if t is None else t[lo:hi].data_ptr()
+            # sharded + single-chunk: the library records an event when each big grid's gradient is final, so that its
+            # all-reduce runs on a side stream under the remaining decoders' backward
+            overlap = None
+            if aux.group is not None and flat is not None and k.step >= k.N and aux.overlap:
+                overlap = (torch.cuda.Event(), torch.cuda.Event(), torch.cuda.current_stream(), _comm_stream(dev))
+                overlap[0].record(); overlap[1].record()                  # create the CUDA events (lazily created otherwise)
+                g.ev_high, g.ev_color = overlap[0].cuda_event, overlap[1].cuda_event
             for lo in range(0, k.N, k.step):
                 hi = min(k.N, lo + k.step)
                 if k.ws is not None:
@@ -301,10 +350,12 @@ class _RenderBatchRay(torch.autograd.Function):
                 og = L.DfpRenderOutGrad(sl(gd, lo, hi), sl(gu, lo, hi), sl(gc, lo, hi), sl(gw, lo, hi))
                 L.check(lib.dfp_render_bwd(C.byref(k.scene), k.packed.data_ptr(), C.byref(rays), C.byref(cfg), C.byref(og),
                                            C.byref(g), ws.data_ptr(), ws_bytes, _stream()))
-            if aux.group is not None:
+            if aux.group is not None and flat is not None:
                 # ray-sharded data parallelism: sum the replicated state's gradients over the ranks (NCCL)
-                import torch.distributed as dist
-                if flat is not None:
+                if overlap is not None:
+                    _reduce_buckets(flat, g._spans, overlap, aux.group)
+                else:
+                    import torch.distributed as dist
                     dist.all_reduce(flat, group=aux.group)           # grids + packed parameters in one collective
             pgrads = _param_grads(gp, k.params, need[6:])
         return (None, d_o if need[1] else None, d_d if need[2] else None,
@@ -313,7 +364,7 @@ class _RenderBatchRay(torch.autograd.Function):
 
 def render_batch_ray(c, decoders, rays_d, rays_o, tsdf_volume, tsdf_bnds, bound, stage, gt_depth=None,
                      n_samples=32, n_surface=16, n_importance=0, chunk=0, want_aux=False, depth_max=None, group=None,
-                     simt=False, workspace_budget=None):
+                     simt=False, workspace_budget=None, overlap_allreduce=True):
     """Functional form of Renderer.render_batch_ray (src/utils/Renderer.py:110-255).
 
     Returns ``(depth [N] f64, uncertainty [N] f64, color [N,3] f32, weight [N,S,1] f32)``; with
@@ -331,7 +382,7 @@ def render_batch_ray(c, decoders, rays_d, rays_o, tsdf_volume, tsdf_bnds, bound,
                chunk=int(chunk), gt_depth=gt, tsdf_volume=tsdf_volume.detach() if tsdf_volume is not None else None,
                tsdf_bnds=tsdf_bnds, bound=bound, pack=param_pack_of(decoders), want_aux=want_aux,
                depth_max=None if depth_max is None else depth_max.detach().reshape(-1)[:1].float().contiguous(),
-               group=group, simt=bool(simt),
+               group=group, simt=bool(simt), overlap=bool(overlap_allreduce),
                ws_budget=WORKSPACE_BUDGET_BYTES if workspace_budget is None else int(workspace_budget))
     dummy = rays_o.new_zeros(())
     gl = c.get("grid_low")

@@ -288,7 +288,7 @@ def run_ours(args):
             group = None
     L.lib()
 
-    n = args.rays                                   # rays per GPU per step (weak scaling)
+    n = args.rays if args.scaling == "weak" else max(1, args.rays // world)   # rays per GPU per step
     torch.manual_seed(0)
     scene = synth.make_scene("room0", seed=0, device=dev, high_std=1e-2, channels_last=not args.channels_first)
     model = A.DF().to(dev)
@@ -301,6 +301,9 @@ def run_ours(args):
     parts = [synth.make_rays(scene, n, seed=100 + k, device=dev) for k in range(world)]
     mine = D.interleaved_shard(n * world, rank, world).to(dev)
     rays_o, rays_d, gt, gt_color = (torch.cat([p[i] for p in parts])[mine].contiguous() for i in range(4))
+    # every rank holds the keyframes, so the batch-global max(gt_depth) (Renderer.py:159,195) is computed locally before
+    # the rays are dealt out: no all-reduce(max), the gradient all-reduce is the step's only collective
+    gmax = torch.cat([p[2] for p in parts]).max().reshape(1) if world > 1 else None
     del parts
     host = [t.cpu().pin_memory() for t in (rays_o, rays_d, gt, gt_color)]
     h2d = sum(t.numel() * t.element_size() for t in host)
@@ -312,10 +315,11 @@ def run_ours(args):
         for t in grids.values():
             t.grad = None
 
-    def step(ro, rd, g, gc):
+    def step(ro, rd, g, gc, dm=None):
         zero_grads()
         d, u, c, w = D.render_batch_ray_sharded(renderer, grids, model, rd, ro, scene.tsdf_volume, scene.tsdf_bnds,
-                                                STAGE, g, group=group)
+                                                STAGE, g, group=group, depth_max=dm,
+                                                overlap_allreduce=not args.no_overlap)
         if args.torch_loss:
             m = g > 0
             loss = torch.abs(g[m] - d[m]).sum() + 0.2 * torch.abs(gc - c).sum()      # src/Mapper.py:457-469 as torch ops
@@ -325,11 +329,11 @@ def run_ours(args):
         return loss
 
     def step_dev():
-        return step(rays_o, rays_d, gt, gt_color)
+        return step(rays_o, rays_d, gt, gt_color, gmax)
 
     def step_e2e():
         dv = [t.to(dev, non_blocking=True) for t in host]
-        return float(step(*dv))                                        # D2H of the loss closes the step
+        return float(step(*dv, gmax))                                  # D2H of the loss closes the step
 
     def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
@@ -478,12 +482,13 @@ def run_ours(args):
                     "kernels_ms_per_step": {k: round(v[1] / prof_steps, 4) for k, v in sorted(kt.items())}}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(n, world, tsdf_shape=list(scene.tsdf_volume.shape[2:])),
             "impl_details": {
                 "grid_layout": "channels_last_3d" if not args.channels_first else "channels_first (transposed per call)",
-                "collective": "NCCL all-reduce (sum) of one flat grid+decoder gradient buffer, all-reduce (max) of gt_depth" if world > 1 else None,
+                "collective": ("NCCL all-reduce (sum) of the grid + decoder gradients in 3 buckets on a side stream, each issued when the "
+                               "backward has finished it" if not args.no_overlap else "one blocking NCCL all-reduce after the backward") if world > 1 else None,
                 "mlp": "tcgen05 tensor-core kernels", "kernel_source_hash": kernel_source_hash(),
                 "loss_impl": "torch ops" if args.torch_loss else "mapper_ops.mapper_loss kernel"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
@@ -524,6 +529,9 @@ def main():
     ap.add_argument("--channels-first", action="store_true", help="keep the grids channels-first (transposed per call)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-small", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one blocking gradient all-reduce instead of the bucketed overlap")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = --rays per GPU (default, the driver's contract); strong = --rays in total, split over the ranks")
     ap.add_argument("--torch-loss", action="store_true", help="Mapper loss as torch ops (boolean indexing, host sync) instead of the loss kernel")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

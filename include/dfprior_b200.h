@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFP_ABI_VERSION 5
+#define DFP_ABI_VERSION 6
 
 #define DFP_C_DIM 32            /* configs/df_prior.yaml:102 (model.c_dim) */
 #define DFP_HIDDEN 32           /* src/conv_onet/models/decoder.py:278 */
@@ -139,6 +139,12 @@ typedef struct DfpGrads {
     float* rays_o;             /* [n_rays,3] f32, overwritten */
     float* rays_d;             /* [n_rays,3] f32, overwritten */
     void* points;              /* dfp_points_bwd only: [n,3] in the points' dtype, overwritten */
+    /* optional cudaEvent_t handles (NULL = none), recorded on the call's stream by dfp_render_bwd / dfp_points_bwd:
+     * ev_high once grid_high's gradient is final (the fusion MLP's and the high decoder's backward are enqueued),
+     * ev_color once grid_color's is.  A multi-GPU caller starts the all-reduce of those buckets on a side stream
+     * while the remaining decoders' backward still runs (grid_low and params_packed are final when the call's work is). */
+    void* ev_high;
+    void* ev_color;
 } DfpGrads;
 
 /* A batch of query points (Renderer.eval_points / Mesher.eval_points / DF.forward). */

@@ -30,24 +30,29 @@ def _worker(rank, world, port, ret):
         n = 512
         rays_o, rays_d, gt, gc = synth.make_rays(scene, n, seed=5, device=dev)      # identical on every rank
 
-        def run(lo, hi, group):
+        def run(lo, hi, group, **kw):
             grids = {k: v.clone().requires_grad_(True) for k, v in scene.grids.items()}
             for p in model.parameters():
                 p.grad = None
             d, u, c, w = D.render_batch_ray_sharded(renderer, grids, model, rays_d[lo:hi], rays_o[lo:hi], scene.tsdf_volume,
-                                                    scene.tsdf_bnds, "color", gt[lo:hi], group=group)
+                                                    scene.tsdf_bnds, "color", gt[lo:hi], group=group, **kw)
             g = gt[lo:hi]
             m = g > 0
             (torch.abs(g[m] - d[m]).sum() + 0.2 * torch.abs(gc[lo:hi] - c).sum()).backward()
             return d.detach(), {k: v.grad.clone() for k, v in grids.items()}, [p.grad.clone() for p in model.parameters()]
 
         lo, hi = D.shard_range(n, rank, world)
-        d_sh, gg_sh, gp_sh = run(lo, hi, dist.group.WORLD)
         d_full, gg_full, gp_full = run(0, n, None)
-        ok = bool(torch.equal(d_sh, d_full[lo:hi]))            # per-ray outputs do not depend on the sharding (global depth max)
         def rel(a, b):
             return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
-        worst = max([rel(gg_sh[k], gg_full[k]) for k in gg_full] + [rel(a, b) for a, b in zip(gp_sh, gp_full) if float(b.abs().max()) > 0])
+        ok, worst = True, 0.0
+        # bucketed all-reduce on the side stream (default), one blocking all-reduce, and the caller-supplied global depth
+        # maximum (no all-reduce(max)): all three must reproduce the single-GPU step
+        for kw in ({}, {"overlap_allreduce": False}, {"depth_max": gt.max()}):
+            d_sh, gg_sh, gp_sh = run(lo, hi, dist.group.WORLD, **kw)
+            ok = ok and bool(torch.equal(d_sh, d_full[lo:hi]))     # per-ray outputs do not depend on the sharding (global depth max)
+            worst = max([worst] + [rel(gg_sh[k], gg_full[k]) for k in gg_full] +
+                        [rel(a, b) for a, b in zip(gp_sh, gp_full) if float(b.abs().max()) > 0])
 
         # BASELINE config 4: chunk-sharded render_img against the single-GPU frame (bit-exact: per-chunk maxima are
         # chunk-local, no collective on the data path)
