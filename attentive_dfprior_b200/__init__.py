@@ -21,7 +21,8 @@ from .renderer import Renderer  # noqa: F401
 from . import dist  # noqa: F401
 from . import mapper_ops  # noqa: F401
 from . import io  # noqa: F401
+from . import graphs  # noqa: F401
 from .mapper_ops import MaskedGridAdam  # noqa: F401
 
-__all__ = ["Renderer", "Mesher", "dist", "mapper_ops", "MaskedGridAdam", "DF", "MLP", "mlp_tsdf", "DenseLayer", "GaussianFourierFeatureTransform", "get_model",
+__all__ = ["Renderer", "Mesher", "dist", "graphs", "mapper_ops", "MaskedGridAdam", "DF", "MLP", "mlp_tsdf", "DenseLayer", "GaussianFourierFeatureTransform", "get_model",
            "functional", "common"]

@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfprior_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 FLAG_SAVE_ACT = 1
 FLAG_SIMT = 2
 MAX_RAY_SAMPLES = 64
@@ -129,6 +129,8 @@ SYMBOLS = {
     "dfp_points_bwd": (C.c_int, [C.POINTER(DfpScene), C.c_void_p, C.POINTER(DfpPoints), C.c_int32, C.c_void_p,
                                  C.c_void_p, C.POINTER(DfpGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
     "dfp_tsdf_sample": (C.c_int, [C.POINTER(DfpScene), C.POINTER(DfpPoints), C.c_void_p, C.c_void_p]),
+    "dfp_gen_rays": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                               C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfp_masked_adam_step": (C.c_int, [C.POINTER(DfpAdam), C.c_void_p]),
     "dfp_frustum_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "dfp_frustum_mask": (C.c_int, [C.POINTER(DfpFrustum), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -1,7 +1,9 @@
-"""Ray generation and pose utilities around the hot path (src/common.py), kept in PyTorch:
-they are trivial element-wise work, and the Tracker's pose gradient enters through them
-(camera 7-vector -> c2w -> rays_o/rays_d), so autograd must see them.  The kernels return
-d rays_o / d rays_d and autograd carries those into the quaternion and translation.
+"""Ray generation and pose utilities around the hot path (src/common.py).
+
+Where the Tracker's pose gradient enters (camera 7-vector -> c2w -> rays_o/rays_d) they are PyTorch ops, so autograd
+sees them: the kernels return d rays_o / d rays_d and autograd carries those into the quaternion and translation.
+Without gradient (render_img's full frames, a Mapper's fixed poses) and with the pose on the GPU, ``get_rays`` and
+``get_rays_from_uv`` run as one kernel (dfp_gen_rays) that reproduces the torch ops' f32 arithmetic bit for bit.
 """
 from __future__ import annotations
 
@@ -9,10 +11,35 @@ import numpy as np
 import torch
 
 
+def _kernel_rays(n, W, pix_i, pix_j, fx, fy, cx, cy, c2w):
+    import ctypes as C  # noqa: F401
+    from . import _lib as L
+    pose = c2w.detach()
+    if pose.dtype != torch.float32 or pose.stride(-1) != 1:
+        pose = pose.float().contiguous()
+    rays_o = torch.empty((n, 3), dtype=torch.float32, device=pose.device)
+    rays_d = torch.empty((n, 3), dtype=torch.float32, device=pose.device)
+    with torch.cuda.device(pose.device):
+        L.check(L.lib().dfp_gen_rays(n, W, None if pix_i is None else pix_i.data_ptr(), None if pix_j is None else pix_j.data_ptr(),
+                                     float(fx), float(fy), float(cx), float(cy), pose.data_ptr(), pose.stride(0),
+                                     rays_o.data_ptr(), rays_d.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return rays_o, rays_d
+
+
+def _kernel_ok(c2w, *more):
+    return (torch.is_tensor(c2w) and c2w.is_cuda and not (torch.is_grad_enabled() and c2w.requires_grad)
+            and c2w.dim() == 2 and c2w.shape[0] >= 3 and c2w.shape[1] == 4
+            and all(torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and not t.requires_grad for t in more))
+
+
 def get_rays_from_uv(i, j, c2w, H, W, fx, fy, cx, cy, device):
     """Rays of chosen pixels -- src/common.py:76-91."""
     if isinstance(c2w, np.ndarray):
         c2w = torch.from_numpy(c2w).to(device)
+    if _kernel_ok(c2w, i, j):
+        n = i.numel()
+        rays_o, rays_d = _kernel_rays(n, W, i.reshape(-1).contiguous(), j.reshape(-1).contiguous(), fx, fy, cx, cy, c2w)
+        return rays_o.reshape(*i.shape, 3), rays_d.reshape(*i.shape, 3)
     dirs = torch.stack([(i - cx) / fx, -(j - cy) / fy, -torch.ones_like(i)], -1).to(device).reshape(-1, 1, 3)
     rays_d = torch.sum(dirs * c2w[:3, :3], -1)
     rays_o = c2w[:3, -1].expand(rays_d.shape)
@@ -46,6 +73,9 @@ def get_rays(H, W, fx, fy, cx, cy, c2w, device):
     """All rays of a frame -- src/common.py:254-272."""
     if isinstance(c2w, np.ndarray):
         c2w = torch.from_numpy(c2w)
+    if _kernel_ok(c2w):
+        rays_o, rays_d = _kernel_rays(H * W, W, None, None, fx, fy, cx, cy, c2w)
+        return rays_o.reshape(H, W, 3), rays_d.reshape(H, W, 3)
     i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing="ij")
     i, j = i.t(), j.t()
     dirs = torch.stack([(i - cx) / fx, -(j - cy) / fy, -torch.ones_like(i)], -1).to(device).reshape(H, W, 1, 3)

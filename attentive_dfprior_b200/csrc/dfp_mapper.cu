@@ -299,7 +299,51 @@ __global__ void __launch_bounds__(256) k_mapper_loss(const LossArgs a) {
 
 using namespace dfp;
 
+// ------------------------------------------------------------------------------------------
+// ray generation without gradient: get_rays (src/common.py:254-272) and get_rays_from_uv (:76-91)
+// ------------------------------------------------------------------------------------------
+struct RayGenArgs {
+    int64_t n; int W;                      // full frame: pixel r = (r % W, r / W)
+    const float* pix_i; const float* pix_j; // or explicit pixel coordinates (null = full frame)
+    float fx, fy, cx, cy;
+    const float* c2w; int row_stride;      // device pose, rows 0..2 x columns 0..3
+    float* rays_o; float* rays_d;
+};
+__global__ void k_gen_rays(const RayGenArgs a) {
+    __shared__ float m[12];
+    if (threadIdx.x < 12) m[threadIdx.x] = a.c2w[(threadIdx.x >> 2) * a.row_stride + (threadIdx.x & 3)];
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (int64_t)gridDim.x * blockDim.x) {
+        // i, j of the full frame come from torch.linspace(0, W-1, W): integers, exact in f32
+        const float fi = a.pix_i ? a.pix_i[r] : (float)(r % a.W), fj = a.pix_j ? a.pix_j[r] : (float)(r / a.W);
+        const float d0 = __fdiv_rn(__fsub_rn(fi, a.cx), a.fx), d1 = -__fdiv_rn(__fsub_rn(fj, a.cy), a.fy), d2 = -1.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {      // rays_d = sum(dirs * c2w[:3,:3], -1): a sequential 3-term f32 sum per row
+            float acc = __fmul_rn(d0, m[4 * k]);
+            acc = __fadd_rn(acc, __fmul_rn(d1, m[4 * k + 1]));
+            acc = __fadd_rn(acc, __fmul_rn(d2, m[4 * k + 2]));
+            a.rays_d[3 * r + k] = acc;
+            a.rays_o[3 * r + k] = m[4 * k + 3];
+        }
+    }
+}
+
 extern "C" {
+
+int dfp_gen_rays(int64_t n, int32_t W, const float* pix_i, const float* pix_j, double fx, double fy, double cx, double cy,
+                 const float* c2w_dev, int32_t row_stride, float* rays_o, float* rays_d, void* stream) {
+    if (!c2w_dev || !rays_o || !rays_d) return fail(DFP_ERR_INVALID, "null argument");
+    if (n < 1 || (!pix_i && W < 1) || ((pix_i == nullptr) != (pix_j == nullptr))) return fail(DFP_ERR_INVALID, "bad ray generation request");
+    RayGenArgs a;
+    a.n = n; a.W = W; a.pix_i = pix_i; a.pix_j = pix_j;
+    a.fx = (float)fx; a.fy = (float)fy; a.cx = (float)cx; a.cy = (float)cy;
+    a.c2w = c2w_dev; a.row_stride = row_stride; a.rays_o = rays_o; a.rays_d = rays_d;
+    const int64_t want = (n + 255) / 256;
+    const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+    DFP_TIMED("k_gen_rays", (cudaStream_t)stream, k_gen_rays<<<blocks, 256, 0, (cudaStream_t)stream>>>(a));
+    DFP_LAUNCH_CHECK("k_gen_rays");
+    return DFP_OK;
+}
 
 int dfp_masked_adam_step(const DfpAdam* a, void* stream) {
     if (!a || !a->param || !a->grad || !a->exp_avg || !a->exp_avg_sq) return fail(DFP_ERR_INVALID, "null argument");

@@ -402,6 +402,19 @@ def run_ours(args):
                  "e2e": {"ms_per_step": ms_e2e_small, "value": n_small * world / (ms_e2e_small / 1e3), "unit": UNIT,
                          "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in sm_host), "d2h_bytes_per_step": 8}}
         if world == 1:
+            # the same iteration captured once into a CUDA graph (attentive_dfprior_b200.graphs) and replayed
+            try:
+                from attentive_dfprior_b200.graphs import GraphedStep
+                zero_grads()
+                gs = GraphedStep(lambda ro, rd, g, gc: step(ro, rd, g, gc), static_inputs=[t.clone() for t in sm_dev])
+                ms_g = time_loop(lambda: gs(*sm_dev))
+                ms_g_e2e = time_loop(lambda: float(gs(*[t.to(dev, non_blocking=True) for t in sm_host])))
+                small["cuda_graph"] = {"ms_per_step": ms_g, "rays_per_s": n_small / (ms_g / 1e3),
+                                       "e2e": {"ms_per_step": ms_g_e2e, "value": n_small / (ms_g_e2e / 1e3), "unit": UNIT}}
+                del gs
+            except Exception as e:
+                small["cuda_graph"] = {"unavailable": repr(e)[:300]}
+        if world == 1:
             # Tracker pose step (src/Tracker.py:83-133): 200 pixels, frozen decoders and grids, gradient to the camera 7-vector
             from attentive_dfprior_b200 import common as CM
             cam = scene.cam
@@ -430,8 +443,9 @@ def run_ours(args):
                 d, u, c, _ = renderer.render_batch_ray(tgrids, tr_model, rd, ro, dev, scene.tsdf_volume, scene.tsdf_bnds, STAGE, gt_depth=tg_)
                 u = u.detach()
                 tmp = torch.abs(tg_ - d) / torch.sqrt(u + 1e-10)
-                m = (tmp < 10 * tmp.median()) & (tg_ > 0)
-                loss = (torch.abs(tg_ - d) / torch.sqrt(u + 1e-10))[m].sum() + 0.5 * torch.abs(tc_ - c)[m].sum()
+                m = ((tmp < 10 * tmp.median()) & (tg_ > 0)).to(tmp.dtype)
+                # src/Tracker.py:116-129; the sums over the selected rays written as masked sums (same values, no host sync)
+                loss = (tmp * m).sum() + 0.5 * (torch.abs(tc_ - c) * m[:, None]).sum()
                 loss.backward()
                 return cam7.grad
 
@@ -442,6 +456,16 @@ def run_ours(args):
                        "e2e": {"ms_per_step": ms_tr_e2e, "value": 200 / (ms_tr_e2e / 1e3), "unit": UNIT,
                                "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in tr_host), "d2h_bytes_per_step": 28},
                        "note": "pose chain and median-masked loss are torch ops (autograd carries d rays -> 7-vector); render fwd+bwd are the kernels"}
+            try:
+                from attentive_dfprior_b200.graphs import GraphedStep
+                gs = GraphedStep(tracker_step, static_inputs=[t.clone() for t in tr_dev])
+                ms_g = time_loop(lambda: gs(*tr_dev))
+                ms_g_e2e = time_loop(lambda: gs(*[t.to(dev, non_blocking=True) for t in tr_host]).cpu())
+                tracker["cuda_graph"] = {"ms_per_step": ms_g, "rays_per_s": 200 / (ms_g / 1e3),
+                                         "e2e": {"ms_per_step": ms_g_e2e, "value": 200 / (ms_g_e2e / 1e3), "unit": UNIT}}
+                del gs
+            except Exception as e:
+                tracker["cuda_graph"] = {"unavailable": repr(e)[:300]}
 
     out = None
     if rank == 0:

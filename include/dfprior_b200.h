@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFP_ABI_VERSION 6
+#define DFP_ABI_VERSION 7
 
 #define DFP_C_DIM 32            /* configs/df_prior.yaml:102 (model.c_dim) */
 #define DFP_HIDDEN 32           /* src/conv_onet/models/decoder.py:278 */
@@ -197,6 +197,13 @@ int dfp_points_bwd(const DfpScene* scene, const float* params_packed, const DfpP
 
 /* ---- Renderer.eval_points_tsdf / sample_grid_tsdf (Renderer.py:73-107) ---------------- */
 int dfp_tsdf_sample(const DfpScene* scene, const DfpPoints* pts, float* tsdf_out, void* stream);
+
+/* ---- ray generation without gradient: get_rays (src/common.py:254-272, every pixel of an H x W frame in row-major
+ * order; pix_i = pix_j = NULL) and get_rays_from_uv (src/common.py:76-91, explicit pixel coordinates as f32 device
+ * arrays).  The pose is read from device memory (rows 0..2 of a row-major c2w with `row_stride` floats per row), so a
+ * render_img call makes no host round trip.  The Tracker's differentiable use of get_rays_from_uv stays with autograd. */
+int dfp_gen_rays(int64_t n_rays, int32_t W, const float* pix_i, const float* pix_j, double fx, double fy, double cx, double cy,
+                 const float* c2w_dev, int32_t row_stride, float* rays_o, float* rays_d, void* stream);
 
 /* ---- Mapper-side rows --------------------------------------------
  *

@@ -312,3 +312,29 @@ def test_training_call_is_chunked_when_workspace_exceeds_budget():
     for x, y in zip(b[6], a[6]):
         if float(y.abs().max()) > 0:
             assert rel_err(x, y) <= 1e-4
+
+
+def test_ray_generation_kernel_matches_torch_ops():
+    """get_rays / get_rays_from_uv without gradient run as one kernel (dfp_gen_rays); same values as the torch ops of
+    src/common.py:76-91, 254-272 evaluated by the oracle on the CPU."""
+    from attentive_dfprior_b200 import common as CM
+    from attentive_dfprior_b200 import synth
+    scene = synth.make_scene("small", seed=1)
+    cam = scene.cam
+    c2w = synth.make_pose(scene, 5)
+    ro_ref, rd_ref = O.get_rays(cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], c2w)
+    ro, rd = CM.get_rays(cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], c2w.to(DEV), DEV)
+    assert ro.shape == ro_ref.shape and rd.shape == rd_ref.shape
+    assert torch.equal(ro.cpu(), ro_ref)
+    assert float((rd.cpu() - rd_ref).abs().max()) <= 2e-7 * float(rd_ref.abs().max())
+    g = torch.Generator().manual_seed(3)
+    i = torch.randint(0, cam["W"], (777,), generator=g).float()
+    j = torch.randint(0, cam["H"], (777,), generator=g).float()
+    ro_ref, rd_ref = O.get_rays_from_uv(i, j, c2w, cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+    ro, rd = CM.get_rays_from_uv(i.to(DEV), j.to(DEV), c2w.to(DEV), cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], DEV)
+    assert torch.equal(ro.cpu(), ro_ref.expand_as(rd_ref).contiguous())
+    assert float((rd.cpu() - rd_ref).abs().max()) <= 2e-7 * float(rd_ref.abs().max())
+    # with a pose that requires grad the torch ops stay in charge (the Tracker's pose gradient flows through them)
+    pose = c2w.to(DEV).requires_grad_(True)
+    ro2, rd2 = CM.get_rays_from_uv(i.to(DEV), j.to(DEV), pose, cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], DEV)
+    assert rd2.requires_grad and float((rd2.detach() - rd).abs().max()) <= 2e-7 * float(rd_ref.abs().max())
