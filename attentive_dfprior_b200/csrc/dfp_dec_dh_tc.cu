@@ -156,7 +156,6 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) dacc[j] = ((m >> j) & 1u) ? dh[j] : 0.f;
             if (planes) {                                     // operands of kernel 2 (rows past the end carry zero deltas)
-                pl::store16(reinterpret_cast<unsigned char*>(a.sc_dh), pl::F_DH, i_raw, i * 32 + c0, dh);
                 pl::store16(reinterpret_cast<unsigned char*>(a.sc_darg), pl::F_DL0, i_raw, 8 + pl::dl0_pos(i) * 32 + c0, dacc);
                 if (i == 3) pl::store16(reinterpret_cast<unsigned char*>(a.sc_dl1), pl::F_DL1, i_raw, c0, dacc);
             }
@@ -184,7 +183,6 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
         }
         // block 0: fc_c[0] path, then the embedding
         {
-            if (planes) pl::store16(reinterpret_cast<unsigned char*>(a.sc_dh), pl::F_DH, i_raw, c0, dh);
             tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 32, dh);
             tc::wait_st();
             tc::fence_before_sync();

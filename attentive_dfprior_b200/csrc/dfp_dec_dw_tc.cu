@@ -13,7 +13,7 @@
 //   pass 0   P : H[0:128)   x DL0[8:136)   M=128 N=128  diagonal 32x32 blocks = pts_linears.4/.2/.1/.3 (hidden part)
 //            O : H[128:192) x DL0[0:104)   M=64  N=104  rows 0..31 x dout = output_linear; the constant-1 row gives
 //                                                       output_linear.bias and pts_linears.4/.2/.1 biases
-//            C : CX[0:..)   x DH[0:160)    M=64/128 N=160  fc_c.0..4 weights; constant-1 row = their biases
+//            C : CX[0:..)   x DL0[0:136)   M=64/128 N=136/144  -> scratch; k_fcc_finish forms fc_c.0..4 weights and biases from it
 //   pass 1   E : EX[0:128)  x DL1[0:160)   M=128 N=160  rows 0..92 x dacc3|dacc0 = pts_linears.3 (embedding part) / .0,
 //                                                       row 93 (constant 1) = their biases, rows 96..98 x darg = embedder._B
 // Feature ranges that run past an array (H[168:192), CX beyond CD+8, EX[104:128)) read whatever finite plane data
@@ -29,9 +29,10 @@ constexpr int NST = 3;                        // ring depth
 constexpr int QS = 32;                        // samples per stage (4 groups of 8)
 constexpr int MAX_TILES = 1024;               // active tiles of one CTA
 constexpr int THREADS = 192;                  // warp 0: tile list + producer, warp 1: MMA issuer, warps 2..5: flush
+constexpr int FCC_N = 144;                    // row length of the [c | 1]^T [dout8 | dacc4 | dacc2 | dacc1 | dacc3] scratch (136 used)
 __host__ __device__ constexpr uint32_t piece(int F) { return 64u * (uint32_t)F; }          // one plane, 32 samples
 template <int CD, int PASS> __host__ __device__ constexpr uint32_t stage_bytes() {
-    return PASS == 0 ? 2u * (piece(pl::F_H) + piece(pl::f_cx(CD)) + piece(pl::F_DH) + piece(pl::F_DL0)) : 2u * (piece(pl::F_EX) + piece(pl::F_DL1));
+    return PASS == 0 ? 2u * (piece(pl::F_H) + piece(pl::f_cx(CD)) + piece(pl::F_DL0)) : 2u * (piece(pl::F_EX) + piece(pl::F_DL1));
 }
 }  // namespace dw
 
@@ -44,7 +45,8 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
     using L = DecOff<CD>;
     constexpr uint32_t STAGE = dw::stage_bytes<CD, PASS>();
     // byte offsets of the pieces inside a stage
-    constexpr uint32_t O_H = 0, O_CX = O_H + 2 * dw::piece(pl::F_H), O_DH = O_CX + 2 * dw::piece(FCX), O_DL0 = O_DH + 2 * dw::piece(pl::F_DH);
+    constexpr uint32_t O_H = 0, O_CX = O_H + 2 * dw::piece(pl::F_H), O_DL0 = O_CX + 2 * dw::piece(FCX);
+    constexpr int NC = (MC == 64) ? dw::FCC_N - 8 : dw::FCC_N;       // columns of the CX^T DL0 product (M = 128 needs N % 16 == 0)
     constexpr uint32_t O_EX = 0, O_DL1 = O_EX + 2 * dw::piece(pl::F_EX);
     // TMEM columns
     constexpr uint32_t T_P = 0, T_O = 128, T_C = 232, T_E = 0;
@@ -100,7 +102,6 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
             if (lane == 0) {
                 const unsigned char* gH = reinterpret_cast<const unsigned char*>(a.act_h);
                 const unsigned char* gCX = reinterpret_cast<const unsigned char*>(a.act_c);
-                const unsigned char* gDH = reinterpret_cast<const unsigned char*>(a.sc_dh);
                 const unsigned char* gDL0 = reinterpret_cast<const unsigned char*>(a.sc_darg);
                 const unsigned char* gEX = reinterpret_cast<const unsigned char*>(a.sc_e);
                 const unsigned char* gDL1 = reinterpret_cast<const unsigned char*>(a.sc_dl1);
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
                             tc::bulk_copy_g2s(dst + off + plane * dw::piece(F), g + (tile * 2 + plane) * (int64_t)(256 * F) + quarter * dw::piece(F),
                                               dw::piece(F), &full_bar[st]);
                     };
-                    if (PASS == 0) { copy(gH, pl::F_H, O_H); copy(gCX, FCX, O_CX); copy(gDH, pl::F_DH, O_DH); copy(gDL0, pl::F_DL0, O_DL0); }
+                    if (PASS == 0) { copy(gH, pl::F_H, O_H); copy(gCX, FCX, O_CX); copy(gDL0, pl::F_DL0, O_DL0); }
                     else { copy(gEX, pl::F_EX, O_EX); copy(gDL1, pl::F_DL1, O_DL1); }
                 }
             }
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
                     if (PASS == 0) {
                         prod(T_P, 128, 128, O_H, pl::F_H, 0, O_DL0, pl::F_DL0, 8);
                         prod(T_O, 64, 104, O_H, pl::F_H, 128, O_DL0, pl::F_DL0, 0);
-                        prod(T_C, MC, 160, O_CX, FCX, 0, O_DH, pl::F_DH, 0);
+                        prod(T_C, MC, NC, O_CX, FCX, 0, O_DL0, pl::F_DL0, 0);
                     } else {
                         prod(T_E, 128, 160, O_EX, pl::F_EX, 0, O_DL1, pl::F_DL1, 0);
                     }
@@ -192,17 +193,27 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
                         }
                     }
                 }
-#pragma unroll 1
-                for (int i = 0; i < 5; ++i) {   // C: fc_c.i
-                    tc::tmem_ld32(tl + T_C + i * 32, d);
-                    tc::wait_ld();
+                // C: [c | 1]^T [dout8 | dacc4 | dacc2 | dacc1 | dacc3] goes to the scratch; k_fcc_finish turns it into the
+                // fc_c.i gradients (c^T dh_i = (c^T dacc_{i+1}) W_{i+1}: the dh planes are never materialised)
+                {
                     const int row = (MC == 64) ? row64 : row128;
-                    if (row >= 0 && row < CD) {
+#pragma unroll 1
+                    for (int b = 0; b < 5; ++b) {
+                        float d8[8];
+                        if (b < 4) { tc::tmem_ld32(tl + T_C + b * 32, d); }
+                        else { uint32_t v[8]; tc::tmem_ld8(tl + T_C + 128, v);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) atomicAdd(g + L::WC + i * CD * 32 + row * 32 + j, d[j]);
-                    } else if (row == CD) {
+                               for (int j = 0; j < 8; ++j) d8[j] = __uint_as_float(v[j]); }
+                        tc::wait_ld();
+                        if (row >= 0 && row <= CD) {
+                            if (b < 4) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) atomicAdd(g + L::BC + i * 32 + j, d[j]);
+                                for (int j = 0; j < 32; ++j) atomicAdd(a.fcc + row * dw::FCC_N + b * 32 + j, d[j]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) atomicAdd(a.fcc + row * dw::FCC_N + 128 + j, d8[j]);
+                            }
+                        }
                     }
                 }
             } else {
@@ -233,10 +244,34 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
     if (warp == 1) tc::tmem_dealloc(tb, 512);
 }
 
+// fc_c.i gradients from the accumulated G = [c | 1]^T [dout8 | dacc4 | dacc2 | dacc1 | dacc3]  (rows: feature c, last row the
+// constant 1):  dh_4 = dout W_o and dh_{i-1} = dacc_i W_i (hidden part of W_3 for i = 3), hence
+//   d fc_c.4[c][k] = sum_o G[c][o] W_o[o][k],   d fc_c.(i-1)[c][k] = sum_j G[c][col_i + j] W_i[j][k],   biases from the last row.
+// grid (5 layers, CD + 1 rows), 32 threads = output units k.
+template <int CD, int NOUT>
+__global__ void k_fcc_finish(const float* __restrict__ fcc, const float* __restrict__ P /* packed decoder params */, float* __restrict__ g) {
+    using L = DecOff<CD>;
+    const int layer = blockIdx.x, row = blockIdx.y, k = threadIdx.x;
+    const float* G = fcc + row * dw::FCC_N;
+    float acc = 0.f;
+    if (layer == 4) {
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) acc = fmaf(G[o], P[L::WO + o * 32 + k], acc);
+    } else {
+        const int i = layer + 1;                                  // the block whose masked delta produced dh_layer
+        const int col0 = i == 4 ? 8 : i == 2 ? 40 : i == 1 ? 72 : 104;
+        const float* W = P + L::WH + (i - 1) * 1024 + k * 32;     // packed k-major: WH[slot][kin = k][j]
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) acc = fmaf(G[col0 + j], W[j], acc);
+    }
+    if (row < CD) g[L::WC + layer * CD * 32 + row * 32 + k] += acc;
+    else g[L::BC + layer * 32 + k] += acc;
+}
+
 template <int DEC>
 int launch_decoder_dw_tc(const DecArgs& a, cudaStream_t st) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
-    const size_t smem0 = dw::NST * dw::stage_bytes<CD, 0>() + 1024, smem1 = dw::NST * dw::stage_bytes<CD, 1>() + 1024;
+    const size_t smem0 = dw::NST * dw::stage_bytes<CD, 0>() + 1024 + 256, smem1 = dw::NST * dw::stage_bytes<CD, 1>() + 1024 + 256;   // + alignment + over-read slack
     int rc = set_smem(k_decoder_dw_tc<DEC, 0>, smem0);
     if (rc) return rc;
     if ((rc = set_smem(k_decoder_dw_tc<DEC, 1>, smem1))) return rc;
@@ -248,6 +283,10 @@ int launch_decoder_dw_tc(const DecArgs& a, cudaStream_t st) {
     DFP_LAUNCH_CHECK("k_decoder_dw_tc");
     DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC, 1><<<blocks, dw::THREADS, smem1, st>>>(a));
     DFP_LAUNCH_CHECK("k_decoder_dw_tc");
+    constexpr int NOUT = (DEC == 2) ? 4 : 1;
+    const int off = DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR);
+    DFP_TIMED("k_fcc_finish", st, k_fcc_finish<CD, NOUT><<<dim3(5, CD + 1), 32, 0, st>>>(a.fcc, a.params + off, a.gparams + off));
+    DFP_LAUNCH_CHECK("k_fcc_finish");
     return DFP_OK;
 }
 template int launch_decoder_dw_tc<0>(const DecArgs&, cudaStream_t);

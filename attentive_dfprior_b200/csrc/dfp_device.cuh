@@ -98,7 +98,7 @@ struct Ws {                        // per-sample workspace arrays (NS samples)
     float* act_c[3];               // CX: gathered grid features + constant 1
     // scratch shared by the decoders during the tensor-core backward
     float* sc_e;                   // EX:  sin(embedding argument), point
-    float* sc_dh;                  // DH:  gradient of each block's output (before the ReLU mask)
+    float* fcc[3];                 // per decoder: accumulated [c | 1]^T [dout8 | dacc..] ((CD + 1) x 144 floats, zeroed before the backward)
     float* sc_darg;                // DL0: upstream gradient and masked deltas of blocks 4, 2, 1, 3
     float* sc_dl1;                 // DL1: masked deltas of blocks 3, 0 and the gradient of the embedding arguments
     float* att_act;                // SIMT path: fusion MLP activations per band-list position (AttArgs::act)
@@ -289,7 +289,7 @@ struct DecArgs {
     float* gparams;          // packed parameter gradient or null
     float* dp;               // [n][3] accumulated, or null
     // tensor-core training path (DFP_FLAG_SAVE_ACT): saved activations / backward scratch, feature-major with stride n
-    float* act_h; uint32_t* act_m; float* act_c; float* sc_e; float* sc_dh; float* sc_darg; float* sc_dl1;   // see Ws
+    float* act_h; uint32_t* act_m; float* act_c; float* sc_e; float* sc_darg; float* sc_dl1; float* fcc;   // see Ws
     // optional compacted sample list (device): the kernel then processes samples list[0..*count) only and indexes the
     // saved activations / scratch by list position.  Used for the high decoder, whose output and gradient only matter
     // on TSDF-band samples (decoder.py:326-333: f_add_m_occ is read under the band mask only).

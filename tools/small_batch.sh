@@ -1,7 +1,7 @@
 #!/bin/bash
 # per-kernel breakdown at the reference's own mapping batch sizes
 for n in 1000 5000; do
-timeout 200 python bench.py --rays $n --steps 20 --warmup 5 --no-cpu-baseline --no-small 2>/dev/null | tail -1 | python -c '
+timeout 200 python bench.py --rays $n --steps 20 --warmup 5 --no-cpu-baseline --no-gpu-baseline --no-small 2>/dev/null | tail -1 | python -c '
 import sys, json
 d = json.loads(sys.stdin.read())
 k = d["roofline"]["kernels_ms_per_step"]
