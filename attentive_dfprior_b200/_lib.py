@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfprior_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 FLAG_SAVE_ACT = 1
 FLAG_SIMT = 2
 MAX_RAY_SAMPLES = 64
@@ -108,6 +108,13 @@ class DfpMapLoss(C.Structure):
                 ("loss", C.c_void_p)]
 
 
+class DfpTsdfFuse(C.Structure):
+    _fields_ = [("tsdf_vol", C.c_void_p), ("weight_vol", C.c_void_p), ("color_vol", C.c_void_p), ("dim", C.c_int32 * 3),
+                ("origin", C.c_float * 3), ("voxel_size", C.c_float), ("trunc_margin", C.c_float), ("depth_im", C.c_void_p),
+                ("color_im", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32), ("intr", C.c_float * 9), ("pose", C.c_float * 16),
+                ("obs_weight", C.c_float)]
+
+
 # every symbol include/dfprior_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "dfp_abi_version": (C.c_int, []),
@@ -136,6 +143,9 @@ SYMBOLS = {
     "dfp_frustum_mask": (C.c_int, [C.POINTER(DfpFrustum), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dfp_assemble_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "dfp_assemble_rays": (C.c_int, [C.POINTER(DfpRayBatch), C.POINTER(DfpRayBatchOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dfp_tsdf_integrate": (C.c_int, [C.POINTER(DfpTsdfFuse), C.c_void_p]),
+    "dfp_point_masks": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                  C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfp_mapper_loss": (C.c_int, [C.POINTER(DfpMapLoss), C.c_void_p]),
     "dfp_launch_count": (C.c_int64, []),
     "dfp_timing_enable": (C.c_int, [C.c_int]),

@@ -274,49 +274,159 @@ struct CompArgs {
     float* d_low; float* d_high; float* d_fused; float* d_rgb4; float* dp;
 };
 
-__global__ void __launch_bounds__(128) k_composite_fwd(const CompArgs a) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n_rays) return;
-    const int S = a.S;
-    float occ[DFP_MAX_RAY_SAMPLES], rgb[3 * DFP_MAX_RAY_SAMPLES];
-    const bool col = a.stage == DFP_STAGE_COLOR;
-    for (int s = 0; s < S; ++s) {
-        const int64_t i = r * S + s;
-        occ[s] = final_occ(a.stage, a.flags[i], a.low[i], a.fused[i]);
-        if (col) { const float4 v = *reinterpret_cast<const float4*>(a.rgb4 + 4 * i); rgb[3 * s] = v.x; rgb[3 * s + 1] = v.y; rgb[3 * s + 2] = v.z; }
-        a.weight[i] = a.w_attn[i];
-        if (a.raw) *reinterpret_cast<float4*>(a.raw + 4 * i) = make_float4(col ? rgb[3 * s] : 0.f, col ? rgb[3 * s + 1] : 0.f, col ? rgb[3 * s + 2] : 0.f, occ[s]);
+// Compositing along the ray with warp scans: 16 lanes per ray (two rays per warp), each lane owns PER = ceil(S/16)
+// consecutive samples.  Transmittance T_s = prod_{k<s} (1 - alpha_k + 1e-10) (common.py:244-245) is a lane-local running
+// product seeded by a multiplicative exclusive scan over the 16 lanes; the ray sums (depth and variance in f64, colour
+// in f32) are butterfly reductions; the backward's suffix sums are the mirrored scan.
+constexpr int COMP_LANES = 16;
+constexpr int COMP_MAXPER = DFP_MAX_RAY_SAMPLES / COMP_LANES;          // 4
+__device__ __forceinline__ double red16(double v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, COMP_LANES);
+    return v;
+}
+__device__ __forceinline__ float red16(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, COMP_LANES);
+    return v;
+}
+// product of the factors of all lanes before this one (1 for lane 0)
+__device__ __forceinline__ float excl_prod16(float p, int lane16) {
+    float incl = p;
+#pragma unroll
+    for (int d = 1; d < COMP_LANES; d <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, incl, d, COMP_LANES);
+        if (lane16 >= d) incl *= t;
     }
-    double depth, var;
-    float c3[3];
-    composite_ray(S, occ, col ? rgb : nullptr, a.z + r * S, depth, var, c3, nullptr);
-    a.depth[r] = depth; a.unc[r] = var;
-    a.color[3 * r] = c3[0]; a.color[3 * r + 1] = c3[1]; a.color[3 * r + 2] = c3[2];
+    const float e = __shfl_up_sync(0xffffffffu, incl, 1, COMP_LANES);
+    return lane16 == 0 ? 1.f : e;
+}
+// sum of the values of all lanes after this one (0 for lane 15)
+__device__ __forceinline__ double excl_suffix16(double v, int lane16) {
+    double incl = v;
+#pragma unroll
+    for (int d = 1; d < COMP_LANES; d <<= 1) {
+        const double t = __shfl_down_sync(0xffffffffu, incl, d, COMP_LANES);
+        if (lane16 + d < COMP_LANES) incl += t;
+    }
+    const double e = __shfl_down_sync(0xffffffffu, incl, 1, COMP_LANES);
+    return lane16 == COMP_LANES - 1 ? 0.0 : e;
 }
 
-__global__ void __launch_bounds__(128) k_composite_bwd(const CompArgs a) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n_rays) return;
-    const int S = a.S;
-    float occ[DFP_MAX_RAY_SAMPLES], rgb[3 * DFP_MAX_RAY_SAMPLES], d_occ[DFP_MAX_RAY_SAMPLES], d_rgb[3 * DFP_MAX_RAY_SAMPLES];
+__global__ void __launch_bounds__(256) k_composite_fwd(const CompArgs a) {
+    const int lane16 = threadIdx.x & (COMP_LANES - 1);
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / COMP_LANES;
+    const bool live = r < a.n_rays;
+    const int S = a.S, per = (S + COMP_LANES - 1) / COMP_LANES;
     const bool col = a.stage == DFP_STAGE_COLOR;
-    for (int s = 0; s < S; ++s) {
-        const int64_t i = r * S + s;
-        occ[s] = final_occ(a.stage, a.flags[i], a.low[i], a.fused[i]);
-        if (col) { const float4 v = *reinterpret_cast<const float4*>(a.rgb4 + 4 * i); rgb[3 * s] = v.x; rgb[3 * s + 1] = v.y; rgb[3 * s + 2] = v.z; }
+    float alpha[COMP_MAXPER], rgb[COMP_MAXPER][3];
+    double z[COMP_MAXPER];
+    float prod = 1.f;
+#pragma unroll
+    for (int k = 0; k < COMP_MAXPER; ++k) {
+        const int s = lane16 * per + k;
+        alpha[k] = 0.f; z[k] = 0.0; rgb[k][0] = rgb[k][1] = rgb[k][2] = 0.f;
+        if (k < per && s < S && live) {
+            const int64_t i = r * S + s;
+            const float occ = final_occ(a.stage, a.flags[i], a.low[i], a.fused[i]);
+            if (col) { const float4 v = *reinterpret_cast<const float4*>(a.rgb4 + 4 * i); rgb[k][0] = v.x; rgb[k][1] = v.y; rgb[k][2] = v.z; }
+            a.weight[i] = a.w_attn[i];
+            if (a.raw) *reinterpret_cast<float4*>(a.raw + 4 * i) = make_float4(rgb[k][0], rgb[k][1], rgb[k][2], occ);
+            alpha[k] = sigmoid10(occ);                                   // common.py:236
+            z[k] = a.z[i];
+            prod *= (1.f - alpha[k]) + 1e-10f;
+        }
     }
-    const float gc[3] = {a.g_color ? a.g_color[3 * r] : 0.f, a.g_color ? a.g_color[3 * r + 1] : 0.f, a.g_color ? a.g_color[3 * r + 2] : 0.f};
-    composite_ray_bwd(S, occ, col ? rgb : nullptr, a.z + r * S, a.g_depth ? a.g_depth[r] : 0.0, a.g_unc ? a.g_unc[r] : 0.0,
-                      gc, d_occ, col ? d_rgb : nullptr);
-    for (int s = 0; s < S; ++s) {
+    float T = excl_prod16(prod, lane16);
+    float w[COMP_MAXPER];
+    double dsum = 0.0;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < COMP_MAXPER; ++k) {
+        const bool on = k < per && lane16 * per + k < S && live;
+        w[k] = on ? alpha[k] * T : 0.f;                                  // common.py:244-245
+        if (on) T = T * ((1.f - alpha[k]) + 1e-10f);
+        dsum += (double)w[k] * z[k];                                     // common.py:248 (f64)
+        c0 += w[k] * rgb[k][0]; c1 += w[k] * rgb[k][1]; c2 += w[k] * rgb[k][2];
+    }
+    const double depth = red16(dsum);
+    c0 = red16(c0); c1 = red16(c1); c2 = red16(c2);
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < COMP_MAXPER; ++k) { const double t = z[k] - depth; v += ((double)w[k] * t) * t; }      // common.py:249-250
+    v = red16(v);
+    if (live && lane16 == 0) {
+        a.depth[r] = depth; a.unc[r] = v;
+        a.color[3 * r] = c0; a.color[3 * r + 1] = c1; a.color[3 * r + 2] = c2;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_composite_bwd(const CompArgs a) {
+    const int lane16 = threadIdx.x & (COMP_LANES - 1);
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / COMP_LANES;
+    const bool live = r < a.n_rays;
+    const int S = a.S, per = (S + COMP_LANES - 1) / COMP_LANES;
+    const bool col = a.stage == DFP_STAGE_COLOR;
+    float alpha[COMP_MAXPER], rgb[COMP_MAXPER][3], Ts[COMP_MAXPER], w[COMP_MAXPER];
+    double z[COMP_MAXPER];
+    int fl[COMP_MAXPER];
+    float prod = 1.f;
+#pragma unroll
+    for (int k = 0; k < COMP_MAXPER; ++k) {
+        const int s = lane16 * per + k;
+        alpha[k] = 0.f; z[k] = 0.0; fl[k] = 0; rgb[k][0] = rgb[k][1] = rgb[k][2] = 0.f;
+        if (k < per && s < S && live) {
+            const int64_t i = r * S + s;
+            fl[k] = a.flags[i];
+            alpha[k] = sigmoid10(final_occ(a.stage, fl[k], a.low[i], a.fused[i]));
+            if (col) { const float4 v = *reinterpret_cast<const float4*>(a.rgb4 + 4 * i); rgb[k][0] = v.x; rgb[k][1] = v.y; rgb[k][2] = v.z; }
+            z[k] = a.z[i];
+            prod *= (1.f - alpha[k]) + 1e-10f;
+        }
+    }
+    float T = excl_prod16(prod, lane16);
+    double dsum = 0.0;
+#pragma unroll
+    for (int k = 0; k < COMP_MAXPER; ++k) {
+        const bool on = k < per && lane16 * per + k < S && live;
+        Ts[k] = T;
+        w[k] = on ? alpha[k] * T : 0.f;
+        if (on) T = T * ((1.f - alpha[k]) + 1e-10f);
+        dsum += (double)w[k] * z[k];
+    }
+    const double depth = red16(dsum);
+    double dv = 0.0;                                 // var = sum w (z - D)^2  ->  d var/d D = -2 sum w (z - D)
+#pragma unroll
+    for (int k = 0; k < COMP_MAXPER; ++k) dv += -2.0 * (double)w[k] * (z[k] - depth);
+    dv = red16(dv);
+    const double g_depth = (live && a.g_depth) ? a.g_depth[r] : 0.0, g_var = (live && a.g_unc) ? a.g_unc[r] : 0.0;
+    float gc[3] = {0.f, 0.f, 0.f};
+    if (live && a.g_color) { gc[0] = a.g_color[3 * r]; gc[1] = a.g_color[3 * r + 1]; gc[2] = a.g_color[3 * r + 2]; }
+    const double gd = g_depth + g_var * dv;
+    double G[COMP_MAXPER], local = 0.0;
+#pragma unroll
+    for (int k = 0; k < COMP_MAXPER; ++k) {
+        const double dz = z[k] - depth;
+        G[k] = gd * z[k] + g_var * dz * dz;
+        if (col) G[k] += (double)gc[0] * rgb[k][0] + (double)gc[1] * rgb[k][1] + (double)gc[2] * rgb[k][2];
+        local += G[k] * (double)w[k];
+    }
+    double suffix = excl_suffix16(local, lane16);    // sum_{k > s} G_k w_k over the lanes after this one
+#pragma unroll
+    for (int k = COMP_MAXPER - 1; k >= 0; --k) {
+        const int s = lane16 * per + k;
+        if (!(k < per && s < S && live)) continue;
         const int64_t i = r * S + s;
-        const int f = a.flags[i];
-        const float g = (f & 1) ? d_occ[s] : 0.f;                        // occ overwritten by 100 outside the bound
-        const bool band = a.stage != DFP_STAGE_LOW && (f & 2);
+        const double one_minus = (double)((1.f - alpha[k]) + 1e-10f);
+        const double dalpha = G[k] * (double)Ts[k] - suffix / one_minus;
+        suffix += G[k] * (double)w[k];
+        const float d_occ = (float)(dalpha * 10.0 * (double)alpha[k] * (1.0 - (double)alpha[k]));
+        const float g = (fl[k] & 1) ? d_occ : 0.f;                       // occ overwritten by 100 outside the bound
+        const bool band = a.stage != DFP_STAGE_LOW && (fl[k] & 2);
         a.d_low[i] = band ? 0.f : g;
         a.d_high[i] = 0.f;
         a.d_fused[i] = band ? g : 0.f;
-        if (col) *reinterpret_cast<float4*>(a.d_rgb4 + 4 * i) = make_float4(d_rgb[3 * s], d_rgb[3 * s + 1], d_rgb[3 * s + 2], 0.f);
+        if (col) *reinterpret_cast<float4*>(a.d_rgb4 + 4 * i) = make_float4(w[k] * gc[0], w[k] * gc[1], w[k] * gc[2], 0.f);
         if (a.dp) { a.dp[3 * i] = 0.f; a.dp[3 * i + 1] = 0.f; a.dp[3 * i + 2] = 0.f; }
     }
 }
@@ -736,7 +846,7 @@ int dfp_render_fwd(const DfpScene* sc, const float* params, const DfpRays* rays,
     ca.n_rays = N; ca.S = S; ca.stage = cfg->stage; ca.z = w.z; ca.low = w.low; ca.fused = w.fused; ca.rgb4 = w.rgb;
     ca.flags = w.flags; ca.w_attn = w.w_attn;
     ca.depth = out->depth; ca.unc = out->uncertainty; ca.color = out->color; ca.weight = out->weight; ca.raw = out->raw;
-    DFP_TIMED("k_composite_fwd", st, k_composite_fwd<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(ca));
+    DFP_TIMED("k_composite_fwd", st, k_composite_fwd<<<(unsigned)((N * COMP_LANES + 255) / 256), 256, 0, st>>>(ca));
     DFP_LAUNCH_CHECK("k_composite_fwd");
     if (out->z_vals) DFP_CUDA(cudaMemcpyAsync(out->z_vals, w.z, NS * sizeof(double), cudaMemcpyDeviceToDevice, st));
     return DFP_OK;
@@ -767,7 +877,7 @@ int dfp_render_bwd(const DfpScene* sc, const float* params, const DfpRays* rays,
     ca.flags = w.flags; ca.w_attn = w.w_attn;
     ca.g_depth = og->depth; ca.g_unc = og->uncertainty; ca.g_color = og->color; ca.g_weight = og->weight;
     ca.d_low = w.d_low; ca.d_high = w.d_high; ca.d_fused = w.d_fused; ca.d_rgb4 = w.d_rgb; ca.dp = want_dp ? w.dp : nullptr;
-    DFP_TIMED("k_composite_bwd", st, k_composite_bwd<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(ca));
+    DFP_TIMED("k_composite_bwd", st, k_composite_bwd<<<(unsigned)((N * COMP_LANES + 255) / 256), 256, 0, st>>>(ca));
     DFP_LAUNCH_CHECK("k_composite_bwd");
 
     PointSrc ps;

@@ -87,10 +87,11 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float part[2][6][128];                                  // d(point) partial sums of the upper halves
-    // feature gradients of a tile (rows padded against bank conflicts) and each sample's cell / continuous index, for the
-    // cooperative scatter: carved from the dynamic allocation behind the weights
+    // feature gradients of a tile (rows padded against bank conflicts) and, per (sample, corner), the voxel offset (in
+    // float4 units, -1 = nothing to add) and trilinear weight, for the cooperative scatter: carved from the dynamic
+    // allocation behind the weights
     float (*s_dc)[128][36] = reinterpret_cast<float (*)[128][36]>(sm + T::FLOATS);
-    int (*s_tri)[128][6] = reinterpret_cast<int (*)[128][6]>(sm + T::FLOATS + 2 * 128 * 36);
+    int2 (*s_cw)[1024] = reinterpret_cast<int2 (*)[1024]>(sm + T::FLOATS + 2 * 128 * 36);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int grp = tid >> 8, gt = tid & 255;
@@ -290,30 +291,26 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                 float* row = &s_dc[grp][r][16 * hf];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(row + 4 * q) = make_float4(d_c[4 * q], d_c[4 * q + 1], d_c[4 * q + 2], d_c[4 * q + 3]);
-                if (hf == 0) {
-                    int* tr = &s_tri[grp][r][0];
-                    tr[0] = (valid && any) ? tri.x0 : -1;     // -1: no gradient for this sample
-                    tr[1] = tri.y0; tr[2] = tri.z0;
-                    tr[3] = __float_as_int(tri.ix); tr[4] = __float_as_int(tri.iy); tr[5] = __float_as_int(tri.iz);
+                // each owner thread fills four of its sample's eight (offset, weight) pairs once
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    int x, y, z;
+                    const bool ok = tri_corner(tri, 4 * hf + cc, a.grid.W, a.grid.H, a.grid.D, x, y, z) && valid && any;
+                    s_cw[grp][r * 8 + 4 * hf + cc] = make_int2(ok ? ((z * a.grid.H + y) * a.grid.W + x) * (CDIM / 4) : -1,
+                                                               __float_as_int(tri_weight(tri, 4 * hf + cc)));
                 }
             }
             tc::named_bar_sync(3 + grp, 256);
             const int sub = gt >> 3, q = gt & 7;
-#pragma unroll 1
+            float4* gg4 = reinterpret_cast<float4*>(a.ggrid);
+#pragma unroll 4
             for (int it = 0; it < 32; ++it) {
                 const int pair = it * 32 + sub;               // (sample, corner): the 4 sub-groups of a warp share the sample
-                const int smp = pair >> 3, cn = pair & 7;
-                const int* tr = &s_tri[grp][smp][0];
-                Tri t;
-                t.x0 = tr[0];
-                if (t.x0 < 0) continue;
-                t.y0 = tr[1]; t.z0 = tr[2];
-                t.ix = __int_as_float(tr[3]); t.iy = __int_as_float(tr[4]); t.iz = __int_as_float(tr[5]);
-                int x, y, z;
-                if (!tri_corner(t, cn, a.grid.W, a.grid.H, a.grid.D, x, y, z)) continue;
-                const float wgt = tri_weight(t, cn);
-                const float4 v = *reinterpret_cast<const float4*>(&s_dc[grp][smp][4 * q]);
-                red_add_v4(a.ggrid + (((int64_t)z * a.grid.H + y) * a.grid.W + x) * CDIM + 4 * q, v.x * wgt, v.y * wgt, v.z * wgt, v.w * wgt);
+                const int2 ent = s_cw[grp][pair];
+                if (ent.x < 0) continue;
+                const float wgt = __int_as_float(ent.y);
+                const float4 v = *reinterpret_cast<const float4*>(&s_dc[grp][pair >> 3][4 * q]);
+                red_add_v4(reinterpret_cast<float*>(gg4 + ent.x + q), v.x * wgt, v.y * wgt, v.z * wgt, v.w * wgt);
             }
         } else if (valid && any && (a.ggrid || want_coord)) {
             scatter_features16(a.grid, a.ggrid, tri, hf, d_c, want_coord, gn);
@@ -340,7 +337,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
 
 template <int DEC, int MODE>
 int launch_decoder_dh_tc(const DecArgs& a, cudaStream_t st) {
-    const size_t smem = (DhLayout::FLOATS + 2 * 128 * 36 + 2 * 128 * 6) * sizeof(float) + 1024;
+    const size_t smem = (DhLayout::FLOATS + 2 * 128 * 36 + 2 * 1024 * 2) * sizeof(float) + 1024;
     int rc = set_smem(k_decoder_dh_tc<DEC, MODE>, smem);
     if (rc) return rc;
     const int64_t tiles = (a.n + 127) / 128;

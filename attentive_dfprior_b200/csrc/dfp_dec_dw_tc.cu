@@ -25,7 +25,8 @@
 namespace dfp {
 
 namespace dw {
-constexpr int NST = 3;                        // ring depth
+constexpr int RING_BYTES = 216 * 1024;        // shared memory given to the ring: as many stages as fit (bytes in flight per SM bound the HBM rate)
+template <int CD, int PASS> __host__ __device__ constexpr int nst();
 constexpr int QS = 32;                        // samples per stage (4 groups of 8)
 constexpr int MAX_TILES = 1024;               // active tiles of one CTA
 constexpr int THREADS = 192;                  // warp 0: tile list + producer, warp 1: MMA issuer, warps 2..5: flush
@@ -34,6 +35,7 @@ __host__ __device__ constexpr uint32_t piece(int F) { return 64u * (uint32_t)F; 
 template <int CD, int PASS> __host__ __device__ constexpr uint32_t stage_bytes() {
     return PASS == 0 ? 2u * (piece(pl::F_H) + piece(pl::f_cx(CD)) + piece(pl::F_DL0)) : 2u * (piece(pl::F_EX) + piece(pl::F_DL1));
 }
+template <int CD, int PASS> __host__ __device__ constexpr int nst() { return RING_BYTES / (int)stage_bytes<CD, PASS>(); }
 }  // namespace dw
 
 template <int DEC, int PASS>
@@ -44,6 +46,7 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
     constexpr int MC = (CD == 32) ? 64 : 128;                        // M of the fc_c product
     using L = DecOff<CD>;
     constexpr uint32_t STAGE = dw::stage_bytes<CD, PASS>();
+    constexpr int NST = dw::nst<CD, PASS>();
     // byte offsets of the pieces inside a stage
     constexpr uint32_t O_H = 0, O_CX = O_H + 2 * dw::piece(pl::F_H), O_DL0 = O_CX + 2 * dw::piece(FCX);
     constexpr int NC = (MC == 64) ? dw::FCC_N - 8 : dw::FCC_N;       // columns of the CX^T DL0 product (M = 128 needs N % 16 == 0)
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
     constexpr uint32_t T_P = 0, T_O = 128, T_C = 232, T_E = 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    __shared__ __align__(8) uint64_t full_bar[dw::NST], empty_bar[dw::NST], done_bar;
+    __shared__ __align__(8) uint64_t full_bar[NST], empty_bar[NST], done_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ int tile_list[dw::MAX_TILES];
     __shared__ int n_active_s;
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
     const int64_t tiles = (n + 127) / 128;
 
     // the stage ring must never hold NaN bit patterns where the over-long feature ranges read: clear it once
-    for (uint32_t i = tid; i < dw::NST * STAGE / 16; i += dw::THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = tid; i < NST * STAGE / 16; i += dw::THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) n_active_s = 0;
     __syncthreads();
     // the CTA's tiles that carry any upstream gradient (kernel 1 wrote its planes only for those), in order
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
     }
     if (warp == 1) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
     if (tid == 0) {
-        for (int i = 0; i < dw::NST; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < NST; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
         tc::mbar_init(&done_bar, 1);
         tc::fence_mbar_init();
     }
@@ -106,8 +109,8 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
                 const unsigned char* gEX = reinterpret_cast<const unsigned char*>(a.sc_e);
                 const unsigned char* gDL1 = reinterpret_cast<const unsigned char*>(a.sc_dl1);
                 for (uint32_t q = 0; q < total; ++q) {
-                    const int st = q % dw::NST;
-                    if (q >= dw::NST) tc::mbar_wait(&empty_bar[st], ((q / dw::NST) - 1) & 1);     // MMAs of the previous use are done
+                    const int st = q % NST;
+                    if (q >= NST) tc::mbar_wait(&empty_bar[st], ((q / NST) - 1) & 1);     // MMAs of the previous use are done
                     const int64_t tile = tile_list[q >> 2];
                     const uint32_t quarter = q & 3;
                     const uint32_t dst = sm_base + st * STAGE;
@@ -125,8 +128,8 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
             // ===================== MMA issuer =====================
             if (lane == 0) {
                 for (uint32_t q = 0; q < total; ++q) {
-                    const int st = q % dw::NST;
-                    tc::mbar_wait(&full_bar[st], (q / dw::NST) & 1);
+                    const int st = q % NST;
+                    tc::mbar_wait(&full_bar[st], (q / NST) & 1);
                     tc::fence_after_sync();
                     const uint32_t s0 = sm_base + st * STAGE;
                     auto prod = [&](uint32_t d_col, int M, int N, uint32_t a_off, int FA, int fa0, uint32_t b_off, int FB, int fb0) {
@@ -271,7 +274,7 @@ __global__ void k_fcc_finish(const float* __restrict__ fcc, const float* __restr
 template <int DEC>
 int launch_decoder_dw_tc(const DecArgs& a, cudaStream_t st) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
-    const size_t smem0 = dw::NST * dw::stage_bytes<CD, 0>() + 1024 + 256, smem1 = dw::NST * dw::stage_bytes<CD, 1>() + 1024 + 256;   // + alignment + over-read slack
+    const size_t smem0 = dw::nst<CD, 0>() * dw::stage_bytes<CD, 0>() + 1024 + 256, smem1 = dw::nst<CD, 1>() * dw::stage_bytes<CD, 1>() + 1024 + 256;   // + alignment + over-read slack
     int rc = set_smem(k_decoder_dw_tc<DEC, 0>, smem0);
     if (rc) return rc;
     if ((rc = set_smem(k_decoder_dw_tc<DEC, 1>, smem1))) return rc;

@@ -29,7 +29,8 @@ struct TcLayout {                                   // shared memory, in floats
     static constexpr int FLOATS = S_BO + 4;
     static constexpr int GROUPS = (CD == 32) ? 2 : 1;
     static constexpr int GATHER = (FLOATS + 3) / 4 * 4;                                   // staging of the cooperative gather
-    static constexpr int TOTAL = GATHER + GROUPS * 128 * (CD + 4) + GROUPS * 128 * (CD == 64 ? 12 : 6);
+    static constexpr int NGRID = (CD == 64) ? 2 : 1;                                      // grids a sample gathers from
+    static constexpr int TOTAL = GATHER + GROUPS * 128 * (CD + 4) + GROUPS * NGRID * 128 * 8 * 2;   // + corner table (int2 per sample and corner)
     // TMEM columns of one group
     static constexpr int T_C_HI = 0, T_C_LO = CD, T_X_HI = 2 * CD, T_X_LO = 2 * CD + 32;
     static constexpr int T_D03 = 2 * CD + 64, T_DH = 2 * CD + 128, T_DC = 2 * CD + 160;
@@ -85,10 +86,10 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
     __shared__ uint32_t tmem_base_s;
     __shared__ float part[2][4][128];                                  // output-layer partial sums of the upper halves
     // cooperative gather staging behind the weights: interpolated features [group][128][CD + 4] (padded rows) and the
-    // samples' cell / continuous index per grid
-    constexpr int C_W = CD + 4, TRI_W = (DEC == 1) ? 12 : 6;
+    // corner table [group][grid][128 samples][8 corners] of (voxel offset in float4 units or -1, trilinear weight)
+    constexpr int C_W = CD + 4, NGRID = T::NGRID;
     float* s_c = sm + T::GATHER;
-    int* s_tri = reinterpret_cast<int*>(s_c + T::GROUPS * 128 * C_W);
+    int2* s_cw = reinterpret_cast<int2*>(s_c + T::GROUPS * 128 * C_W);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int grp = tid >> 8, gt = tid & 255;                         // group, thread within the group
@@ -126,15 +127,18 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
         {   // trilinear features -> A_C.  Cooperative gather: a thread fetching its own 16 channels touches 32 different
             // lines per warp instruction (one 16-byte piece per lane); instead eight lanes fetch one corner's whole
             // 128-byte line and the interpolated features go to their owners through shared memory.
-            if (hf == 0) {
-                const Tri t0 = tri_setup(xn, a.grid.W, a.grid.H, a.grid.D);
-                int* tr = &s_tri[grp * 128 * TRI_W + r * TRI_W];
-                tr[0] = t0.x0; tr[1] = t0.y0; tr[2] = t0.z0;
-                tr[3] = __float_as_int(t0.ix); tr[4] = __float_as_int(t0.iy); tr[5] = __float_as_int(t0.iz);
-                if (DEC == 1) {
-                    const Tri t1 = tri_setup(xn, a.grid_low.W, a.grid_low.H, a.grid_low.D);
-                    tr[6] = t1.x0; tr[7] = t1.y0; tr[8] = t1.z0;
-                    tr[9] = __float_as_int(t1.ix); tr[10] = __float_as_int(t1.iy); tr[11] = __float_as_int(t1.iz);
+            // Every (sample, corner) pair's voxel offset and weight are computed ONCE by the sample's two owner threads
+            // (four corners each); the eight lanes that then fetch a corner's 128-byte line only read the pair.
+#pragma unroll
+            for (int gsel = 0; gsel < NGRID; ++gsel) {
+                const DfpGrid& g = gsel == 0 ? a.grid : a.grid_low;
+                const Tri t0 = tri_setup(xn, g.W, g.H, g.D);
+                int2* e = &s_cw[((grp * NGRID + gsel) * 128 + r) * 8 + 4 * hf];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    int x, y, z;
+                    const bool ok = tri_corner(t0, 4 * hf + cc, g.W, g.H, g.D, x, y, z);
+                    e[cc] = make_int2(ok ? ((z * g.H + y) * g.W + x) * (CDIM / 4) : -1, __float_as_int(tri_weight(t0, 4 * hf + cc)));
                 }
             }
             tc::named_bar_sync(3 + grp, 256);
@@ -143,22 +147,18 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
 #pragma unroll 1
                 for (int j = 0; j < 4; ++j) {
                     const int smp = j * 32 + sub;
-                    const int* tr = &s_tri[grp * 128 * TRI_W + smp * TRI_W];
 #pragma unroll
-                    for (int gsel = 0; gsel < (DEC == 1 ? 2 : 1); ++gsel) {
-                        const DfpGrid& g = gsel == 0 ? a.grid : a.grid_low;
-                        Tri t;
-                        t.x0 = tr[6 * gsel]; t.y0 = tr[6 * gsel + 1]; t.z0 = tr[6 * gsel + 2];
-                        t.ix = __int_as_float(tr[6 * gsel + 3]); t.iy = __int_as_float(tr[6 * gsel + 4]); t.iz = __int_as_float(tr[6 * gsel + 5]);
+                    for (int gsel = 0; gsel < NGRID; ++gsel) {
+                        const float4* gdata = reinterpret_cast<const float4*>((gsel == 0 ? a.grid : a.grid_low).data);
+                        const int4* e4 = reinterpret_cast<const int4*>(&s_cw[((grp * NGRID + gsel) * 128 + smp) * 8]);
                         float4 v[8];
                         float wgt[8];
 #pragma unroll
-                        for (int cn = 0; cn < 8; ++cn) {
-                            int x, y, z;
-                            const bool ok = tri_corner(t, cn, g.W, g.H, g.D, x, y, z);
-                            wgt[cn] = tri_weight(t, cn);
-                            v[cn] = ok ? __ldg(reinterpret_cast<const float4*>(g.data + (((int64_t)z * g.H + y) * g.W + x) * CDIM) + q)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int c2 = 0; c2 < 4; ++c2) {
+                            const int4 ent = e4[c2];                       // two (offset, weight) pairs
+                            wgt[2 * c2] = __int_as_float(ent.y); wgt[2 * c2 + 1] = __int_as_float(ent.w);
+                            v[2 * c2] = ent.x >= 0 ? __ldg(gdata + ent.x + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            v[2 * c2 + 1] = ent.z >= 0 ? __ldg(gdata + ent.z + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll

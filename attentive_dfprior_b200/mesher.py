@@ -29,6 +29,8 @@ class Mesher(object):
         self.tsdf_bnds = getattr(slam, "tsdf_bnds", None)
         if self.tsdf_bnds is None:
             self.tsdf_bnds = slam.vol_bnds
+        self.depth_test = cfg["meshing"].get("depth_test", False)
+        self.H, self.W, self.fx, self.fy, self.cx, self.cy = (getattr(slam, k, None) for k in ("H", "W", "fx", "fy", "cx", "cy"))
         mcb = cfg.get("mapping", {}).get("marching_cubes_bound")
         self.marching_cubes_bound = (torch.from_numpy(np.array(mcb) * self.scale) if mcb is not None
                                      else slam.bound.clone())
@@ -58,6 +60,46 @@ class Mesher(object):
         vals = [Fn.sample_tsdf(pi, tsdf_volume, self.tsdf_bnds).reshape(1, -1)
                 for pi in torch.split(p, self.points_batch_size)]
         return torch.cat(vals, dim=1)
+
+    # -- Mesher.py:58-204
+    def point_masks(self, input_points, keyframe_dict, estimate_c2w_list, idx, device, get_mask_use_all_frames=False):
+        """Seen / forecast / unseen classification of points (mesh vertices) against the keyframes' frusta, as numpy bool
+        arrays like upstream.  One kernel over points x frames; ``depth_test`` (off in every shipped config,
+        configs/df_prior.yaml:18) is not implemented."""
+        import ctypes as C  # noqa: F401
+        from . import _lib as L
+        if self.depth_test:
+            raise NotImplementedError("meshing.depth_test is off in every shipped config (configs/df_prior.yaml:18)")
+        if not isinstance(input_points, torch.Tensor):
+            input_points = torch.from_numpy(np.asarray(input_points))
+        pts = input_points.detach().to(device).float().contiguous()
+        if get_mask_use_all_frames:
+            poses = [estimate_c2w_list[i] for i in range(0, idx + 1)]
+            # upstream's all-frames branch applies no depth bound (Mesher.py:93-128)
+            maxd = [float("inf")] * len(poses)
+        else:
+            poses = [kf["est_c2w"] for kf in keyframe_dict]
+            maxd = [float(torch.max(kf["depth"])) * 1.1 for kf in keyframe_dict]              # Mesher.py:186
+        if len(poses) == 0 or pts.shape[0] == 0:
+            z = np.zeros(pts.shape[0], dtype=bool)
+            return z, z.copy(), ~z
+        w2c = np.stack([np.linalg.inv(p.cpu().numpy()).astype(np.float32) for p in poses])   # Mesher.py:133-135
+        seen = torch.empty(pts.shape[0], dtype=torch.uint8, device=pts.device)
+        fore = torch.empty_like(seen)
+        lib = L.lib()
+        with torch.cuda.device(pts.device):
+            for f0 in range(0, len(poses), 64):                       # frames in groups; masks are OR-ed across groups
+                w = torch.from_numpy(w2c[f0:f0 + 64].reshape(-1, 16).copy()).to(pts.device)
+                md = torch.tensor(maxd[f0:f0 + 64], dtype=torch.float32, device=pts.device)
+                s_k, f_k = (seen, fore) if f0 == 0 else (torch.empty_like(seen), torch.empty_like(seen))
+                L.check(lib.dfp_point_masks(pts.data_ptr(), pts.shape[0], w.data_ptr(), md.data_ptr(), w.shape[0], float(self.fx), float(self.fy),
+                                            float(self.cx), float(self.cy), int(self.H), int(self.W), s_k.data_ptr(), f_k.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
+                if f0 > 0:
+                    fore = ((fore | f_k | seen) & ~(seen | s_k)).to(torch.uint8)      # forecast = in some extended frustum, not seen
+                    seen = seen | s_k
+        seen_b, fore_b = seen.bool(), fore.bool()
+        return seen_b.cpu().numpy(), fore_b.cpu().numpy(), (~(seen_b | fore_b)).cpu().numpy()
 
     # -- the query loop of get_mesh, Mesher.py:437-447
     def query_occupancy(self, c, decoders, tsdf_volume, device="cuda:0", points=None, inside_mask=None, group=None,

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFP_ABI_VERSION 7
+#define DFP_ABI_VERSION 8
 
 #define DFP_C_DIM 32            /* configs/df_prior.yaml:102 (model.c_dim) */
 #define DFP_HIDDEN 32           /* src/conv_onet/models/decoder.py:278 */
@@ -294,6 +294,31 @@ typedef struct {
     double* loss;
 } DfpMapLoss;
 int dfp_mapper_loss(const DfpMapLoss* l, void* stream);
+
+/* (f4) Offline TSDF fusion, the `integrate` kernel of src/fusion.py:69-142 (pycuda upstream): one RGB-D frame into the
+ * [X][Y][Z] f32 volumes (tsdf initialised to -1, weight and colour to 0 by the caller, fusion.py:52-56), truncation
+ * 5 voxels, running averages weighted by obs_weight, colour packed b*65536 + g*256 + r.  Same f32 arithmetic as the
+ * upstream kernel (including its float voxel-index decomposition), without fused multiply-adds. */
+typedef struct {
+    float* tsdf_vol; float* weight_vol; float* color_vol;
+    int32_t dim[3];            /* X, Y, Z */
+    float origin[3];           /* vol_bnds[:, 0] as f32 (fusion.py:44) */
+    float voxel_size, trunc_margin;
+    const float* depth_im;     /* [H, W] f32 (device) */
+    const float* color_im;     /* [H, W] f32, folded floor(b*65536 + g*256 + r) (fusion.py:207-208) */
+    int32_t H, W;
+    float intr[9];             /* row-major 3x3 */
+    float pose[16];            /* row-major 4x4 camera-to-world */
+    float obs_weight;
+} DfpTsdfFuse;
+int dfp_tsdf_integrate(const DfpTsdfFuse* f, void* stream);
+
+/* (f4) Mesher.point_masks without depth test (src/utils/Mesher.py:58-204, cfg meshing.depth_test = False): points [n,3]
+ * f32 are classified against n_frames keyframes given as world-to-camera matrices (np.linalg.inv of the estimated pose,
+ * f32, row-major [n_frames][16]) and max_depth[f] = max(depth_f) * 1.1; seen = inside some frame's image with -z <
+ * max_depth, forecast = inside some frame's image extended by 1000 px and not seen.  unseen = neither. */
+int dfp_point_masks(const float* points, int64_t n, const float* w2c, const float* max_depth, int32_t n_frames, double fx, double fy,
+                    double cx, double cy, int32_t H, int32_t W, uint8_t* seen, uint8_t* forecast, void* stream);
 
 /* ---- diagnostics (used by bench.py; not part of the reference seam) ---------------------
  * dfp_launch_count: kernels launched by this library since load.  dfp_timing_enable(1) makes
