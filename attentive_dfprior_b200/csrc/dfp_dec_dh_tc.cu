@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
         const bool valid = i_raw < n;
         const int64_t ia = valid ? i_raw : n - 1;                    // list position: index of saved activations and scratch
         const int64_t s = dec_sample(a, ia);                         // sample id: index of points, dout, dp
+        const pl::Row r_dl0 = pl::row_of(a.sc_darg, pl::F_DL0, i_raw), r_dl1 = pl::row_of(a.sc_dl1, pl::F_DL1, i_raw),
+                      r_ex = pl::row_of(a.sc_e, pl::F_EX, i_raw);
         float dout[NOUT];
         if (NOUT == 1) dout[0] = valid ? a.dout[s] : 0.f;
         else {
@@ -157,8 +159,8 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) dacc[j] = ((m >> j) & 1u) ? dh[j] : 0.f;
             if (planes) {                                     // operands of kernel 2 (rows past the end carry zero deltas)
-                pl::store16(reinterpret_cast<unsigned char*>(a.sc_darg), pl::F_DL0, i_raw, 8 + pl::dl0_pos(i) * 32 + c0, dacc);
-                if (i == 3) pl::store16(reinterpret_cast<unsigned char*>(a.sc_dl1), pl::F_DL1, i_raw, c0, dacc);
+                pl::store16(r_dl0, 8 + pl::dl0_pos(i) * 32 + c0, dacc);
+                if (i == 3) pl::store16(r_dl1, c0, dacc);
             }
             tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 32, dh);            // for d_c += dh_i * Wc_i
             tc::tmem_store_split16(tl + T::T_A + 64, tl + T::T_A + 96, dacc);     // for dh_{i-1} = dacc_i * W_i
@@ -197,14 +199,14 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) dh[j] = ((m0 >> j) & 1u) ? dh[j] : 0.f;      // dacc_0
             if (planes) {
-                pl::store16(reinterpret_cast<unsigned char*>(a.sc_dl1), pl::F_DL1, i_raw, 32 + c0, dh);
+                pl::store16(r_dl1, 32 + c0, dh);
                 if (hf == 0) {                                // upstream gradient, padded to 8 columns
                     float d8[8];
 #pragma unroll
                     for (int o = 0; o < 8; ++o) d8[o] = 0.f;
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o) d8[o] = dout[o];
-                    pl::store8(reinterpret_cast<unsigned char*>(a.sc_darg), pl::F_DL0, i_raw, 0, d8);
+                    pl::store8(r_dl0, 0, d8);
                 }
             }
             tc::mbar_wait(bar, parity); parity ^= 1;
@@ -269,13 +271,13 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             }
             }
             if (planes) {
-                pl::store16(reinterpret_cast<unsigned char*>(a.sc_e), pl::F_EX, i_raw, ch * 32 + c0, sn);
-                pl::store16(reinterpret_cast<unsigned char*>(a.sc_dl1), pl::F_DL1, i_raw, 64 + ch * 32 + c0, da);
+                pl::store16(r_ex, ch * 32 + c0, sn);
+                pl::store16(r_dl1, 64 + ch * 32 + c0, da);
             }
         }
         if (planes && hf == 0) {                              // the point itself (A operand of embedder._B's gradient)
             const float p8[8] = {pf[0], pf[1], pf[2], 0.f, 0.f, 0.f, 0.f, 0.f};
-            pl::store8(reinterpret_cast<unsigned char*>(a.sc_e), pl::F_EX, i_raw, 96, p8);
+            pl::store8(r_ex, 96, p8);
         }
         float d_c[16];
         tc::tmem_ld16(tl + T::T_DC, d_c);

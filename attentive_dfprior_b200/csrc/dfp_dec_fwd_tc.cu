@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
         normalize(p, box, xn);
         const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
         const bool fast = embed_fast_ok(pf, bmax);
+        pl::Row r_c, r_h;
+        if (a.act_c) { r_c = pl::row_of(a.act_c, pl::f_cx(CD), i_raw); r_h = pl::row_of(a.act_h, pl::F_H, i_raw); }
         {   // trilinear features -> A_C.  Cooperative gather: a thread fetching its own 16 channels touches 32 different
             // lines per warp instruction (one 16-byte piece per lane); instead eight lanes fetch one corner's whole
             // 128-byte line and the interpolated features go to their owners through shared memory.
@@ -181,8 +183,8 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             // saved operands go out as bf16 planes at the row's own position (every row of a tile is written: rows past
             // the end repeat the last sample, their deltas are zero in the backward)
             if (a.act_c) {
-                pl::store16(reinterpret_cast<unsigned char*>(a.act_c), pl::f_cx(CD), i_raw, 16 * hf, c);
-                if (hf == 0) pl::store_ones8(reinterpret_cast<unsigned char*>(a.act_c), pl::f_cx(CD), i_raw, CD);
+                pl::store16(r_c, 16 * hf, c);
+                if (hf == 0) pl::store_ones8(r_c, CD);
             }
             if (DEC == 1) {
 #pragma unroll
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                     c[4 * q4] = v.x; c[4 * q4 + 1] = v.y; c[4 * q4 + 2] = v.z; c[4 * q4 + 3] = v.w;
                 }
                 tc::tmem_store_split16(tl + T::T_C_HI + 32, tl + T::T_C_LO + 32, c);
-                if (a.act_c) pl::store16(reinterpret_cast<unsigned char*>(a.act_c), pl::f_cx(CD), i_raw, 32 + 16 * hf, c);
+                if (a.act_c) pl::store16(r_c, 32 + 16 * hf, c);
             }
         }
         // Fourier embedding in three 32-wide K chunks (16 per thread), each accumulated into D03 = [z0 | skip part of z3]
@@ -245,8 +247,8 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             }
             if (a.act_h) {                                            // kept for the backward (DFP_FLAG_SAVE_ACT)
                 if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, 0, 5))[hf] = (uint16_t)m;
-                pl::store16(reinterpret_cast<unsigned char*>(a.act_h), pl::F_H, i_raw, pl::h_pos(0) * 32 + 16 * hf, h);
-                if (hf == 0) pl::store_ones8(reinterpret_cast<unsigned char*>(a.act_h), pl::F_H, i_raw, 160);
+                pl::store16(r_h, pl::h_pos(0) * 32 + 16 * hf, h);
+                if (hf == 0) pl::store_ones8(r_h, 160);
             }
         }
 #pragma unroll 1
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             }
             if (a.act_h) {
                 if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, i, 5))[hf] = (uint16_t)m;
-                pl::store16(reinterpret_cast<unsigned char*>(a.act_h), pl::F_H, i_raw, pl::h_pos(i) * 32 + 16 * hf, h);
+                pl::store16(r_h, pl::h_pos(i) * 32 + 16 * hf, h);
             }
         }
         // output layer: each half sums its 16 inputs, the lower half adds the upper half's partial and the bias

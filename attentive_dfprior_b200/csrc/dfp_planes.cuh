@@ -90,5 +90,34 @@ __device__ __forceinline__ void store_ones8(unsigned char* base, int F, int64_t 
     *reinterpret_cast<uint4*>(chunk_ptr(base, F, s, 1, f0)) = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// A producer thread's row of one array: the two plane addresses of its sample are computed once per tile, every store is
+// then `row + chunk * 128` (the 64-bit address arithmetic of chunk_ptr otherwise repeats for each of ~40 stores).
+struct Row {
+    unsigned char* hi;          // chunk 0 of the hi plane
+    uint32_t plane;             // distance to the mid plane
+};
+__device__ __forceinline__ Row row_of(void* base, int F, int64_t s) {
+    Row r;
+    r.hi = chunk_ptr(reinterpret_cast<unsigned char*>(base), F, s, 0, 0);
+    r.plane = 256u * (uint32_t)F;
+    return r;
+}
+__device__ __forceinline__ void store8(const Row& r, int f0, const float* v) {
+    uint4 hi, mid;
+    split8<false>(v, hi, mid);
+    unsigned char* p = r.hi + (f0 >> 3) * 128;
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + r.plane) = mid;
+}
+__device__ __forceinline__ void store16(const Row& r, int f0, const float (&v)[16]) {
+    store8(r, f0, v);
+    store8(r, f0 + 8, v + 8);
+}
+__device__ __forceinline__ void store_ones8(const Row& r, int f0) {
+    unsigned char* p = r.hi + (f0 >> 3) * 128;
+    *reinterpret_cast<uint4*>(p) = make_uint4(0x00003f80u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(p + r.plane) = make_uint4(0u, 0u, 0u, 0u);
+}
+
 }  // namespace pl
 }  // namespace dfp

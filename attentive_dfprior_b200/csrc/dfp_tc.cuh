@@ -149,10 +149,13 @@ __device__ __forceinline__ float tf32_rna(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// x = hi + lo with both parts TF32 numbers.  cvt.rna.tf32.f32 is not a native instruction on sm_100a (it expands to
+// add / compare-with-infinity / select / mask, ~4 instructions), and this split runs for every activation and delta of
+// every layer; for the finite values that reach it the rounding is an integer add of half a TF32 ulp and a mask.
+// The tensor core reads only the upper 19 bits of a TF32 operand, so the residual needs the add but not the mask.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    const float h = tf32_rna(x);
-    hi = __float_as_uint(h);
-    lo = __float_as_uint(tf32_rna(x - h));
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
 }
 
 // ---- TMEM <-> registers, 32x32b shape: thread t of warp w touches lane 32*(w%4)+t ----
