@@ -500,8 +500,11 @@ struct PtrTable { const float* p[N_TENSORS]; };
 
 constexpr int ATT_IMG_BLOCKS = 16;      // 4096 (row, 8-input chunk) tasks of the three wide fusion layers, 256 per block
 
+constexpr int PACK_SPLIT = 8;           // blocks per tensor (the largest tensor has 16 384 elements: one block per tensor is latency-bound)
+
 __global__ void k_pack_params(const PtrTable tab, float* __restrict__ packed) {
     if (blockIdx.x >= N_TENSORS) {
+        if (blockIdx.y != 0) return;
         // tensor-core image of the fusion MLP (dfp_layout.h, AttImg): 8 consecutive inputs of one output row are 32
         // contiguous source bytes (torch keeps [out][in]) and one 16-byte core-matrix row of each plane
         int task = (blockIdx.x - N_TENSORS) * blockDim.x + threadIdx.x;
@@ -532,7 +535,7 @@ __global__ void k_pack_params(const PtrTable tab, float* __restrict__ packed) {
     int rows, cols;
     tensor_shape(t, rows, cols);
     const float* src = tab.p[t];
-    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) packed[packed_index(t, i / cols, i % cols)] = src[i];
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < rows * cols; i += PACK_SPLIT * blockDim.x) packed[packed_index(t, i / cols, i % cols)] = src[i];
 }
 struct OffTable { int off[N_TENSORS]; };
 __global__ void k_unpack_grads(const float* __restrict__ packed, float* __restrict__ flat, const OffTable offs) {
@@ -540,7 +543,7 @@ __global__ void k_unpack_grads(const float* __restrict__ packed, float* __restri
     int rows, cols;
     tensor_shape(t, rows, cols);
     float* dst = flat + offs.off[t];
-    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) dst[i] = packed[packed_index(t, i / cols, i % cols)];
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < rows * cols; i += PACK_SPLIT * blockDim.x) dst[i] = packed[packed_index(t, i / cols, i % cols)];
 }
 
 // [C][V] <-> [V][C] with V = D*H*W, C = 32: a 32x32 shared-memory tile per block
@@ -758,7 +761,7 @@ int dfp_pack_params(const float* const* tensors79, float* packed, void* stream) 
         if (!tensors79[t]) return fail(DFP_ERR_INVALID, "parameter tensor %d is null", t);
         tab.p[t] = tensors79[t];
     }
-    DFP_TIMED("k_pack_params", (cudaStream_t)stream, k_pack_params<<<N_TENSORS + ATT_IMG_BLOCKS, 256, 0, (cudaStream_t)stream>>>(tab, packed));
+    DFP_TIMED("k_pack_params", (cudaStream_t)stream, k_pack_params<<<dim3(N_TENSORS + ATT_IMG_BLOCKS, PACK_SPLIT), 256, 0, (cudaStream_t)stream>>>(tab, packed));
     DFP_LAUNCH_CHECK("k_pack_params");
     return DFP_OK;
 }
@@ -773,7 +776,7 @@ int dfp_unpack_param_grads(const float* packed_grad, float* native_flat, void* s
         offs.off[t] = off;
         off += r * c;
     }
-    DFP_TIMED("k_unpack_grads", (cudaStream_t)stream, k_unpack_grads<<<N_TENSORS, 256, 0, (cudaStream_t)stream>>>(packed_grad, native_flat, offs));
+    DFP_TIMED("k_unpack_grads", (cudaStream_t)stream, k_unpack_grads<<<dim3(N_TENSORS, PACK_SPLIT), 256, 0, (cudaStream_t)stream>>>(packed_grad, native_flat, offs));
     DFP_LAUNCH_CHECK("k_unpack_grads");
     return DFP_OK;
 }

@@ -38,8 +38,19 @@ template <int CD, int PASS> __host__ __device__ constexpr uint32_t stage_bytes()
 template <int CD, int PASS> __host__ __device__ constexpr int nst() { return RING_BYTES / (int)stage_bytes<CD, PASS>(); }
 }  // namespace dw
 
+// state shared by the two passes' code (one CTA runs exactly one pass)
+struct DwShared {
+    uint64_t full_bar[8], empty_bar[8], done_bar;
+    uint32_t tmem_base;
+    int n_active;
+    int tile_list[dw::MAX_TILES];
+};
+
+// One pass for CTA `cta` of `nctas` CTAs working on it (the kernel gives the first n0 CTAs of the grid to pass 0 and the
+// rest to pass 1, so that both passes of a decoder run in ONE launch: at the reference's batch sizes a launch is mostly
+// fixed cost, and on large batches the two HBM streams share the machine in proportion to their bytes).
 template <int DEC, int PASS>
-__global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs a) {
+__device__ __forceinline__ void dw_body(const DecArgs& a, const int cta, const int nctas, DwShared& S) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
     constexpr int NOUT = (DEC == 2) ? 4 : 1;
     constexpr int FCX = pl::f_cx(CD);
@@ -55,10 +66,11 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
     constexpr uint32_t T_P = 0, T_O = 128, T_C = 232, T_E = 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    __shared__ __align__(8) uint64_t full_bar[NST], empty_bar[NST], done_bar;
-    __shared__ uint32_t tmem_base_s;
-    __shared__ int tile_list[dw::MAX_TILES];
-    __shared__ int n_active_s;
+    uint64_t* full_bar = S.full_bar; uint64_t* empty_bar = S.empty_bar; uint64_t& done_bar = S.done_bar;
+    uint32_t& tmem_base_s = S.tmem_base;
+    int* tile_list = S.tile_list;
+    int& n_active_s = S.n_active;
+    static_assert(NST <= 8, "ring deeper than the barrier arrays");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n = dec_items(a);
     const int64_t tiles = (n + 127) / 128;
@@ -70,7 +82,7 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
     // the CTA's tiles that carry any upstream gradient (kernel 1 wrote its planes only for those), in order
     if (warp == 0) {
         int cnt = 0;
-        for (int64_t tile = blockIdx.x; tile < tiles && cnt < dw::MAX_TILES; tile += gridDim.x) {
+        for (int64_t tile = cta; tile < tiles && cnt < dw::MAX_TILES; tile += nctas) {
             bool any = false;
             for (int r = lane; r < 128; r += 32) {
                 const int64_t ii = tile * 128 + r;
@@ -272,19 +284,32 @@ __global__ void k_fcc_finish(const float* __restrict__ fcc, const float* __restr
 }
 
 template <int DEC>
+__global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs a, const int n0) {
+    __shared__ __align__(8) DwShared S;
+    if ((int)blockIdx.x < n0) dw_body<DEC, 0>(a, blockIdx.x, n0, S);
+    else dw_body<DEC, 1>(a, blockIdx.x - n0, gridDim.x - n0, S);
+}
+
+template <int DEC>
 int launch_decoder_dw_tc(const DecArgs& a, cudaStream_t st) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
-    const size_t smem0 = dw::nst<CD, 0>() * dw::stage_bytes<CD, 0>() + 1024 + 256, smem1 = dw::nst<CD, 1>() * dw::stage_bytes<CD, 1>() + 1024 + 256;   // + alignment + over-read slack
-    int rc = set_smem(k_decoder_dw_tc<DEC, 0>, smem0);
+    constexpr size_t smem0 = dw::nst<CD, 0>() * dw::stage_bytes<CD, 0>() + 1024 + 256, smem1 = dw::nst<CD, 1>() * dw::stage_bytes<CD, 1>() + 1024 + 256;   // + alignment + over-read slack
+    constexpr size_t smem = smem0 > smem1 ? smem0 : smem1;
+    int rc = set_smem(k_decoder_dw_tc<DEC>, smem);
     if (rc) return rc;
-    if ((rc = set_smem(k_decoder_dw_tc<DEC, 1>, smem1))) return rc;
     const int64_t tiles = (a.n + 127) / 128;
-    int blocks = grid_for(tiles, 1, num_sms());
-    const int64_t min_blocks = (tiles + dw::MAX_TILES - 1) / dw::MAX_TILES;      // a CTA lists at most MAX_TILES tiles
-    if (blocks < min_blocks) blocks = (int)min_blocks;
-    DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC, 0><<<blocks, dw::THREADS, smem0, st>>>(a));
-    DFP_LAUNCH_CHECK("k_decoder_dw_tc");
-    DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC, 1><<<blocks, dw::THREADS, smem1, st>>>(a));
+    // CTAs per pass in proportion to the bytes a tile costs in it (pass 0: H + CX + DL0, pass 1: EX + DL1)
+    constexpr double share0 = (double)dw::stage_bytes<CD, 0>() / (double)(dw::stage_bytes<CD, 0>() + dw::stage_bytes<CD, 1>());
+    int blocks = grid_for(2 * tiles, 1, num_sms());
+    if (blocks < 2) blocks = 2;
+    int n0 = (int)(blocks * share0 + 0.5);
+    if (n0 < 1) n0 = 1;
+    if (n0 > blocks - 1) n0 = blocks - 1;
+    int n1 = blocks - n0;
+    const int min_blocks = (int)((tiles + dw::MAX_TILES - 1) / dw::MAX_TILES);   // a CTA lists at most MAX_TILES tiles
+    if (n0 < min_blocks) n0 = min_blocks;
+    if (n1 < min_blocks) n1 = min_blocks;
+    DFP_TIMED("k_decoder_dw_tc", st, k_decoder_dw_tc<DEC><<<n0 + n1, dw::THREADS, smem, st>>>(a, n0));
     DFP_LAUNCH_CHECK("k_decoder_dw_tc");
     constexpr int NOUT = (DEC == 2) ? 4 : 1;
     const int off = DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR);

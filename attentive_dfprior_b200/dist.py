@@ -94,30 +94,47 @@ def gather_concat(x: torch.Tensor, sizes, group, dst: Optional[int] = None):
 
 def render_img_sharded(renderer, c, decoders, c2w, device, tsdf_volume, tsdf_bnds, stage, gt_depth, group=None,
                        gather=True):
-    """Full-frame render with the reference's ray_batch_size chunks dealt out to the ranks (chunk-exact)."""
+    """Full-frame render with the rays dealt evenly to the ranks, identical to the single-GPU frame bit for bit.
+
+    The reference renders ``ray_batch_size`` chunks, each with its own max(gt_depth) (src/utils/Renderer.py:294-306, 159,
+    195).  Whole chunks per rank would leave the frame's 9 chunks (816 000 rays / 100 000) on 8 ranks with one rank doing
+    two of them; instead every rank takes n / world consecutive rays, cut at the chunk boundaries it straddles, and each
+    piece is rendered with ITS chunk's maximum (computed once over the whole frame, on the device) passed in."""
     from .common import get_rays
     if group is None:
         return renderer.render_img(c, decoders, c2w, device, tsdf_volume, tsdf_bnds, stage, gt_depth=gt_depth)
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     H, W = renderer.H, renderer.W
+    rb = renderer.ray_batch_size
     with torch.no_grad():
         rays_o, rays_d = get_rays(H, W, renderer.fx, renderer.fy, renderer.cx, renderer.cy, c2w, device)
-        rays_o, rays_d, gt = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), gt_depth.reshape(-1)
+        rays_o, rays_d, gt = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), gt_depth.reshape(-1).float()
         n = rays_d.shape[0]
-        lo, hi = chunk_aligned_range(n, renderer.ray_batch_size, rank, world)
-        if hi > lo:
-            d, u, col, _ = Fn.render_batch_ray(c, decoders, rays_d[lo:hi], rays_o[lo:hi], tsdf_volume, tsdf_bnds,
-                                               renderer.bound, stage, gt_depth=gt[lo:hi], n_samples=renderer.N_samples,
-                                               n_surface=renderer.N_surface, chunk=renderer.ray_batch_size)
+        nchunks = (n + rb - 1) // rb
+        pad = nchunks * rb - n
+        gtp = torch.cat([gt, gt.new_full((pad,), float("-inf"))]) if pad else gt
+        chunk_max = gtp.reshape(nchunks, rb).max(dim=1)[0]                       # per-chunk max(gt_depth), device, no sync
+        lo, hi = shard_range(n, rank, world)
+        ds, us, cs = [], [], []
+        a = lo
+        while a < hi:
+            ck = a // rb
+            b = min(hi, (ck + 1) * rb)
+            d, u, col, _ = Fn.render_batch_ray(c, decoders, rays_d[a:b], rays_o[a:b], tsdf_volume, tsdf_bnds, renderer.bound, stage,
+                                               gt_depth=gt[a:b], n_samples=renderer.N_samples, n_surface=renderer.N_surface,
+                                               depth_max=chunk_max[ck:ck + 1])
+            ds.append(d); us.append(u); cs.append(col)
+            a = b
+        if ds:
+            d, u, col = torch.cat(ds), torch.cat(us), torch.cat(cs)
         else:
             d = torch.empty(0, device=device, dtype=torch.float64)
             u = torch.empty(0, device=device, dtype=torch.float64)
             col = torch.empty(0, 3, device=device)
         if not gather:
             return (lo, hi), d, u, col
-        sizes = [chunk_aligned_range(n, renderer.ray_batch_size, r, world) for r in range(world)]
-        sizes = [b - a for a, b in sizes]
+        sizes = [b_ - a_ for a_, b_ in (shard_range(n, r, world) for r in range(world))]
         d = gather_concat(d, sizes, group)
         u = gather_concat(u, sizes, group)
         col = gather_concat(col, sizes, group)

@@ -99,7 +99,7 @@ def main():
         torch.cuda.synchronize()
         ms_mask = timeit(lambda: [M.frustum_mask(frames[0][2], scene.bound, scene.grids[k].shape[2:], frames[0][0], H, W, *intr) for k in keys], 2, 5)
         frac = {k: float(masks[k].float().mean()) for k in keys}
-        lrs = {"grid_low": 0.1, "grid_high": 0.005, "grid_color": 0.005}
+        lrs = {"grid_low": 0.1, "grid_high": 0.005, "grid_color": 0.0}     # upstream never sets the colour-grid group's lr: it stays 0 (Mapper.py:372-376, 392-398)
 
         grids_f = {k: scene.grids[k].detach().clone(memory_format=torch.preserve_format).requires_grad_(True) for k in keys}
         opt_g = M.MaskedGridAdam(grids_f, masks)
