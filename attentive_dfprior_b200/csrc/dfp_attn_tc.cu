@@ -116,7 +116,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_attn_fwd_tc(const AttArgs a) {
     tc::fence_after_sync();
     const uint32_t tb = tmem_base_s;
     const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16);
-    const bool issuer = tid == 0;
     const bool save = a.tc_planes != nullptr;
     uint32_t parity = 0;
     bool weights_ready = false;
@@ -158,9 +157,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_attn_fwd_tc(const AttArgs a) {
             tc::fence_proxy_async();                                   // plane writes -> visible to the tensor core
             tc::fence_before_sync();
             tc::named_bar_sync(1, THREADS);
-            if (issuer) {
+            if (warp == 0 && !weights_ready) { tc::mbar_wait(&bar_w, 0); weights_ready = true; }
+            if (warp == 0 && tc::elect_one()) {
                 tc::fence_after_sync();
-                if (!weights_ready) { tc::mbar_wait(&bar_w, 0); weights_ready = true; }
                 const int K = layer == 0 ? 64 : 128, N = layer == 2 ? 64 : 128;
                 const uint32_t wh = img_s + (layer == 0 ? AttImg::W2H : layer == 1 ? AttImg::W3H : AttImg::W4H);
                 const uint32_t wm = img_s + (layer == 0 ? AttImg::W2M : layer == 1 ? AttImg::W3M : AttImg::W4M);
@@ -341,18 +340,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_attn_dh_tc(const AttArgs a) {
             tc::fence_before_sync();
             tc::named_bar_sync(1, THREADS);
             const int J = step == 0 ? 64 : 128, NIN = step == 2 ? 64 : 128;
-            if (issuer) {
+            if (WP && issuer) {                                        // bulk groups are per-thread state: always thread 0
+                const uint32_t goff = step == 0 ? G_D4 : step == 1 ? G_D3 : G_D2, pbytes = 256u * J;
+                bulk_store_s2g(gsave + goff, act_s, pbytes);
+                bulk_store_s2g(gsave + goff + pbytes, act_s + ACT_PLANE, pbytes);
+                if (step == 0) { bulk_store_s2g(gsave + G_DL, dl8_s, 2048u); bulk_store_s2g(gsave + G_DL + 2048u, dl8_s + 2048u, 2048u); }
+                bulk_commit();
+            }
+            if (warp == 0 && !weights_ready) { tc::mbar_wait(&bar_w, 0); weights_ready = true; }
+            if (warp == 0 && tc::elect_one()) {
                 tc::fence_after_sync();
-                if (!weights_ready) { tc::mbar_wait(&bar_w, 0); weights_ready = true; }
                 const uint32_t wh = img_s + (step == 0 ? AttImg::W4H : step == 1 ? AttImg::W3H : AttImg::W2H);
                 const uint32_t wm = img_s + (step == 0 ? AttImg::W4M : step == 1 ? AttImg::W3M : AttImg::W2M);
-                if (WP) {
-                    const uint32_t goff = step == 0 ? G_D4 : step == 1 ? G_D3 : G_D2, pbytes = 256u * J;
-                    bulk_store_s2g(gsave + goff, act_s, pbytes);
-                    bulk_store_s2g(gsave + goff + pbytes, act_s + ACT_PLANE, pbytes);
-                    if (step == 0) { bulk_store_s2g(gsave + G_DL, dl8_s, 2048u); bulk_store_s2g(gsave + G_DL + 2048u, dl8_s + 2048u, 2048u); }
-                    bulk_commit();
-                }
                 mma_layer_bwd(tb + T_D, act_s, J, wh, wm, NIN);
                 if (WP) {                                              // [1 x0 x1]^T d over the tile's 128 samples
                     const uint32_t xcol = step == 0 ? T_X4 : step == 1 ? T_X3 : T_X2;
@@ -377,7 +376,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_attn_dh_tc(const AttArgs a) {
             tc::fence_proxy_async();
             tc::fence_before_sync();
             tc::named_bar_sync(1, THREADS);
-            if (issuer) {
+            if (warp == 0 && tc::elect_one()) {
                 tc::fence_after_sync();
                 const uint32_t idesc = tc::idesc_bf16_mn(64, 64);
                 for (uint32_t ks = 0; ks < 8; ++ks)
@@ -525,7 +524,7 @@ __global__ void __launch_bounds__(adw::THREADS, 1) k_attn_dw_tc(const AttArgs a)
                 }
             }
         } else if (warp == 1) {
-            if (lane == 0) {                                           // MMA issuer
+            if (tc::elect_one()) {                                     // MMA issuer
                 for (uint32_t q = 0; q < total; ++q) {
                     const int st = q % adw::NST;
                     tc::mbar_wait(&full_bar[st], (q / adw::NST) & 1);

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
     const BoxT<PT> box = make_box<PT>(a.bound.b);
     const int64_t n = dec_items(a);
     const int64_t tiles = (n + 127) / 128;
-    const bool issuer = (gt == 0);
+    const bool issuer_warp = __shfl_sync(0xffffffffu, gt >> 5, 0) == 0;   // warp-uniform by construction
     const bool planes = a.gparams != nullptr;
     const float bmax = embed_bmax(sm + T::S_B);
     const int c0 = 16 * hf;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             tc::wait_st();
             tc::fence_before_sync();
             tc::named_bar_sync(3 + grp, 256);
-            if (issuer) {
+            if (issuer_warp && tc::elect_one()) {
                 tc::fence_after_sync();
                 tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + (T::WC + i * 1024) * 4, wlo + (T::WC + i * 1024) * 4,
                                   32, 32, 4096u, i != 4);
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             tc::wait_st();
             tc::fence_before_sync();
             tc::named_bar_sync(3 + grp, 256);
-            if (issuer) {
+            if (issuer_warp && tc::elect_one()) {
                 tc::fence_after_sync();
                 tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + T::WC * 4, wlo + T::WC * 4, 32, 32, 4096u, true);
                 tc::mma_commit(bar);
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             tc::wait_st();
             tc::fence_before_sync();
             tc::named_bar_sync(3 + grp, 256);
-            if (issuer) {
+            if (issuer_warp && tc::elect_one()) {
                 tc::fence_after_sync();
                 tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A, tb + T::T_A + 64, whi + T::W03 * 4, wlo + T::W03 * 4, 64, 96, 8192u, false);
                 tc::mma_commit(bar);

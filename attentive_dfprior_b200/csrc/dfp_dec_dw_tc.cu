@@ -138,7 +138,7 @@ __device__ __forceinline__ void dw_body(const DecArgs& a, const int cta, const i
             }
         } else if (warp == 1) {
             // ===================== MMA issuer =====================
-            if (lane == 0) {
+            if (tc::elect_one()) {
                 for (uint32_t q = 0; q < total; ++q) {
                     const int st = q % NST;
                     tc::mbar_wait(&full_bar[st], (q / NST) & 1);

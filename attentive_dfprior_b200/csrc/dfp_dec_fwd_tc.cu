@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
     const BoxT<PT> box = make_box<PT>(a.bound.b);
     const int64_t nitems = dec_items(a);
     const int64_t tiles = (nitems + 127) / 128;
-    const bool issuer = (gt == 0);
+    const bool issuer_warp = __shfl_sync(0xffffffffu, gt >> 5, 0) == 0;   // warp-uniform by construction
     const float bmax = embed_bmax(sm + T::S_B);
 
     for (int64_t tile = (int64_t)blockIdx.x * T::GROUPS + grp; tile < tiles; tile += (int64_t)gridDim.x * T::GROUPS) {
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             tc::wait_st();
             tc::fence_before_sync();
             tc::named_bar_sync(1 + grp, 256);
-            if (issuer) {
+            if (issuer_warp && tc::elect_one()) {
                 tc::fence_after_sync();
                 const uint32_t koff = (uint32_t)ch * 8u * (64u * 16u);             // 8 K-chunks of 16 B per 32 k, LBO = N*16
                 tc::mma_3xtf32(tb + T::T_D03, tb + T::T_X_HI, tb + T::T_X_LO, bhi + T::W03 * 4 + koff, blo + T::W03 * 4 + koff,
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             tc::wait_st();
             tc::fence_before_sync();
             tc::named_bar_sync(1 + grp, 256);
-            if (issuer) {
+            if (issuer_warp && tc::elect_one()) {
                 tc::fence_after_sync();
                 tc::mma_3xtf32(tb + T::T_DH, tb + T::T_X_HI, tb + T::T_X_LO, bhi + (T::WH + (i - 1) * 1024) * 4,
                                blo + (T::WH + (i - 1) * 1024) * 4, 32, 32, false);

@@ -39,6 +39,18 @@ __device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// one lane of a converged warp (elect.sync): the compiler then knows that a single thread runs the guarded code and
+// keeps descriptors in uniform registers instead of looping over the lanes' values for every tcgen05.mma
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
