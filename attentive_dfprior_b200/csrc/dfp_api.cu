@@ -606,6 +606,9 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
     DecArgs da;
     memset(&da, 0, sizeof(da));
     da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params;
+#ifdef DFP_EXPERIMENTS
+    { const char* e = getenv("DFP_EXP"); da.dbg = e ? atoi(e) : 0; }
+#endif
     int rc;
     const bool tcp = flags_tc(flags);
     const bool save = tcp && (flags & DFP_FLAG_SAVE_ACT);
@@ -663,6 +666,9 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
     DecArgs da;
     memset(&da, 0, sizeof(da));
     da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params;
+#ifdef DFP_EXPERIMENTS
+    { const char* e = getenv("DFP_EXP"); da.dbg = e ? atoi(e) : 0; }
+#endif
     da.gparams = g->params_packed; da.dp = want_dp ? w.dp : nullptr;
     // tensor-core backward (needs the activations saved by the tensor-core forward): K1 = delta chain, K2 = weight grads
     const bool tcb = flags_tc(flags) && (flags & DFP_FLAG_SAVE_ACT) && w.act_h[0] != nullptr;

@@ -14,6 +14,19 @@
 
 namespace dfp {
 
+#ifdef DFP_EXPERIMENTS
+__device__ unsigned long long g_prof_dh[32];
+extern "C" int dfp_exp_read_prof_dh(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_prof_dh, sizeof(g_prof_dh)); }
+extern "C" int dfp_exp_clear_prof_dh() { unsigned long long z[32] = {}; return (int)cudaMemcpyToSymbol(g_prof_dh, z, sizeof(z)); }
+#define PROF_DECL long long pt_ = clock64(); const bool prof_ = (blockIdx.x == 0 && tid == 32 && DEC == 2);
+#define PROF_TILE if (prof_) atomicAdd(&g_prof_dh[31], 1ull);
+#define PROF(i) { const long long n_ = clock64(); if (prof_) atomicAdd(&g_prof_dh[i], (unsigned long long)(n_ - pt_)); pt_ = n_; }
+#else
+#define PROF_DECL
+#define PROF_TILE
+#define PROF(i)
+#endif
+
 struct DhLayout {                                       // shared memory, in floats
     static constexpr int WH = 0;                        // 4 tiles [32 j][32 kin]: pts_linears.1, .2, .3[:, 93:], .4
     static constexpr int W03 = WH + 4 * 1024;           // 3 column blocks of [64 j][32 kin]: rows 0..31 pts_linears.0, 32..63 pts_linears.3[:, :93]
@@ -113,11 +126,12 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
     const int64_t n = dec_items(a);
     const int64_t tiles = (n + 127) / 128;
     const bool issuer_warp = __shfl_sync(0xffffffffu, gt >> 5, 0) == 0;   // warp-uniform by construction
-    const bool planes = a.gparams != nullptr;
+    const bool planes = a.gparams != nullptr && !DFP_EXP(a, 1);
     const float bmax = embed_bmax(sm + T::S_B);
     const int c0 = 16 * hf;
 
     for (int64_t tile = (int64_t)blockIdx.x * 2 + grp; tile < tiles; tile += (int64_t)gridDim.x * 2) {
+        PROF_DECL
         const int64_t i_raw = tile * 128 + r;
         const bool valid = i_raw < n;
         const int64_t ia = valid ? i_raw : n - 1;                    // list position: index of saved activations and scratch
@@ -136,7 +150,9 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
         for (int o = 0; o < NOUT; ++o) any = any || (dout[o] != 0.f);
         // kernel 2 reads the scratch of every sample of a tile it processes, so a skipped tile is marked by zero deltas:
         // it decides with the same predicate (all upstream gradients of the tile are zero)
+        PROF(0)
         if (!group_any(any, 1 + grp)) continue;
+        PROF(1)
 
         float dh[16];
 #pragma unroll
@@ -166,7 +182,9 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             tc::tmem_store_split16(tl + T::T_A + 64, tl + T::T_A + 96, dacc);     // for dh_{i-1} = dacc_i * W_i
             tc::wait_st();
             tc::fence_before_sync();
+            PROF(2)
             tc::named_bar_sync(3 + grp, 256);
+            PROF(3)
             if (issuer_warp && tc::elect_one()) {
                 tc::fence_after_sync();
                 tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + (T::WC + i * 1024) * 4, wlo + (T::WC + i * 1024) * 4,
@@ -179,10 +197,13 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) dacc3[j] = dacc[j];
             }
+            PROF(4)
             tc::mbar_wait(bar, parity); parity ^= 1;
             tc::fence_after_sync();
+            PROF(5)
             tc::tmem_ld16(tl + T::T_DX, dh);
             tc::wait_ld();
+            PROF(6)
         }
         // block 0: fc_c[0] path, then the embedding
         {
@@ -209,8 +230,10 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                     pl::store8(r_dl0, 0, d8);
                 }
             }
+            PROF(7)
             tc::mbar_wait(bar, parity); parity ^= 1;
             tc::fence_after_sync();
+            PROF(8)
             // A = [dacc_0 | dacc_3]: hi in columns 0..63, lo in 64..127
             tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 64, dh);
             tc::tmem_store_split16(tl + T::T_A + 32, tl + T::T_A + 96, dacc3);
@@ -223,6 +246,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                 tc::mma_commit(bar);
             }
         }
+        PROF(9)
         // while the embedding product runs: point, trilinear set-up
         PT p[3];
         load_point<MODE>(a.ps, s, p);
@@ -231,11 +255,13 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
         const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
         const bool fast = embed_fast_ok(pf, bmax);
         const Tri tri = tri_setup(xn, a.grid.W, a.grid.H, a.grid.D);
+        PROF(10)
         tc::mbar_wait(bar, parity); parity ^= 1;
         tc::fence_after_sync();
+        PROF(11)
         float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
 #pragma unroll 1
-        for (int ch = 0; ch < 3; ++ch) {
+        for (int ch = 0; ch < (DFP_EXP(a, 4) ? 0 : 3); ++ch) {
             float de[16];
             tc::tmem_ld16(tl + T::T_DX + ch * 32, de);
             tc::wait_ld();
@@ -279,12 +305,13 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             const float p8[8] = {pf[0], pf[1], pf[2], 0.f, 0.f, 0.f, 0.f, 0.f};
             pl::store8(r_ex, 96, p8);
         }
+        PROF(12)
         float d_c[16];
         tc::tmem_ld16(tl + T::T_DC, d_c);
         tc::wait_ld();
         const bool want_coord = a.dp != nullptr;
         float gn[3] = {0.f, 0.f, 0.f};
-        if (a.ggrid && !want_coord) {
+        if (a.ggrid && !want_coord && !DFP_EXP(a, 2)) {
             // Cooperative scatter.  A thread's own reduction would touch 32 different lines per warp instruction (one
             // 16-byte piece per lane, ~2 cycles of the load/store unit each: measured, this was half of the kernel).
             // Instead the tile's feature gradients go through shared memory and eight lanes add one corner's whole
@@ -302,7 +329,9 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                                                                __float_as_int(tri_weight(tri, 4 * hf + cc)));
                 }
             }
+            PROF(13)
             tc::named_bar_sync(3 + grp, 256);
+            PROF(14)
             const int sub = gt >> 3, q = gt & 7;
             float4* gg4 = reinterpret_cast<float4*>(a.ggrid);
 #pragma unroll 4
@@ -314,9 +343,11 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                 const float4 v = *reinterpret_cast<const float4*>(&s_dc[grp][pair >> 3][4 * q]);
                 red_add_v4(reinterpret_cast<float*>(gg4 + ent.x + q), v.x * wgt, v.y * wgt, v.z * wgt, v.w * wgt);
             }
-        } else if (valid && any && (a.ggrid || want_coord)) {
+        } else if (valid && any && (a.ggrid || want_coord) && !DFP_EXP(a, 2)) {
             scatter_features16(a.grid, a.ggrid, tri, hf, d_c, want_coord, gn);
         }
+        PROF(15)
+        PROF_TILE
         if (want_coord) {                                            // uniform: the two halves of a sample add up in the lower one
             if (hf == 1) {
                 part[grp][0][r] = gn[0]; part[grp][1][r] = gn[1]; part[grp][2][r] = gn[2];

@@ -14,6 +14,20 @@
 
 namespace dfp {
 
+#ifdef DFP_EXPERIMENTS
+// phase timeline of one non-issuer thread (group 0, warp 1, lane 0) of CTA 0: cycles summed per phase over its tiles
+__device__ unsigned long long g_prof_fwd[32];
+extern "C" int dfp_exp_read_prof_fwd(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_prof_fwd, sizeof(g_prof_fwd)); }
+extern "C" int dfp_exp_clear_prof_fwd() { unsigned long long z[32] = {}; return (int)cudaMemcpyToSymbol(g_prof_fwd, z, sizeof(z)); }
+#define PROF_DECL long long pt_ = clock64(); const bool prof_ = (blockIdx.x == 0 && tid == 32 && DEC == 2);
+#define PROF_TILE if (prof_) atomicAdd(&g_prof_fwd[31], 1ull);
+#define PROF(i) { const long long n_ = clock64(); if (prof_) atomicAdd(&g_prof_fwd[i], (unsigned long long)(n_ - pt_)); pt_ = n_; }
+#else
+#define PROF_DECL
+#define PROF_TILE
+#define PROF(i)
+#endif
+
 template <int CD>
 struct TcLayout {                                   // shared memory, in floats
     static constexpr int W03 = 0;                   // B [64][96]  rows 0..31 pts_linears.0, 32..63 pts_linears.3[:, :93]
@@ -114,6 +128,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
     const float bmax = embed_bmax(sm + T::S_B);
 
     for (int64_t tile = (int64_t)blockIdx.x * T::GROUPS + grp; tile < tiles; tile += (int64_t)gridDim.x * T::GROUPS) {
+        PROF_DECL
         const int64_t i_raw = tile * 128 + r;
         const bool valid = i_raw < nitems;
         const int64_t ia = valid ? i_raw : nitems - 1;               // position in the (optional) list: index of saved activations
@@ -125,6 +140,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
         const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
         const bool fast = embed_fast_ok(pf, bmax);
         pl::Row r_c, r_h;
+        const bool save_pl = a.act_c && !DFP_EXP(a, 16);
         if (a.act_c) { r_c = pl::row_of(a.act_c, pl::f_cx(CD), i_raw); r_h = pl::row_of(a.act_h, pl::F_H, i_raw); }
         {   // trilinear features -> A_C.  Cooperative gather: a thread fetching its own 16 channels touches 32 different
             // lines per warp instruction (one 16-byte piece per lane); instead eight lanes fetch one corner's whole
@@ -143,7 +159,9 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                     e[cc] = make_int2(ok ? ((z * g.H + y) * g.W + x) * (CDIM / 4) : -1, __float_as_int(tri_weight(t0, 4 * hf + cc)));
                 }
             }
+            PROF(0)
             tc::named_bar_sync(3 + grp, 256);
+            PROF(1)
             {
                 const int sub = gt >> 3, q = gt & 7;
 #pragma unroll 1
@@ -159,8 +177,8 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                         for (int c2 = 0; c2 < 4; ++c2) {
                             const int4 ent = e4[c2];                       // two (offset, weight) pairs
                             wgt[2 * c2] = __int_as_float(ent.y); wgt[2 * c2 + 1] = __int_as_float(ent.w);
-                            v[2 * c2] = ent.x >= 0 ? __ldg(gdata + ent.x + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            v[2 * c2 + 1] = ent.z >= 0 ? __ldg(gdata + ent.z + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            v[2 * c2] = (ent.x >= 0 && !DFP_EXP(a, 32)) ? __ldg(gdata + ent.x + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            v[2 * c2 + 1] = (ent.z >= 0 && !DFP_EXP(a, 32)) ? __ldg(gdata + ent.z + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -172,7 +190,9 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                     }
                 }
             }
+            PROF(2)
             tc::named_bar_sync(3 + grp, 256);
+            PROF(3)
             float c[16];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
@@ -182,7 +202,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             tc::tmem_store_split16(tl + T::T_C_HI, tl + T::T_C_LO, c);
             // saved operands go out as bf16 planes at the row's own position (every row of a tile is written: rows past
             // the end repeat the last sample, their deltas are zero in the backward)
-            if (a.act_c) {
+            if (save_pl) {
                 pl::store16(r_c, 16 * hf, c);
                 if (hf == 0) pl::store_ones8(r_c, CD);
             }
@@ -193,9 +213,10 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                     c[4 * q4] = v.x; c[4 * q4 + 1] = v.y; c[4 * q4 + 2] = v.z; c[4 * q4 + 3] = v.w;
                 }
                 tc::tmem_store_split16(tl + T::T_C_HI + 32, tl + T::T_C_LO + 32, c);
-                if (a.act_c) pl::store16(r_c, 32 + 16 * hf, c);
+                if (save_pl) pl::store16(r_c, 32 + 16 * hf, c);
             }
         }
+        PROF(4)
         // Fourier embedding in three 32-wide K chunks (16 per thread), each accumulated into D03 = [z0 | skip part of z3]
 #pragma unroll 1
         for (int ch = 0; ch < 3; ++ch) {
@@ -204,7 +225,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
 #pragma unroll
                 for (int kk = 0; kk < 16; ++kk) {
                     const int k = ch * 32 + 16 * hf + kk;
-                    e[kk] = (k < EMB) ? sin_cw(embed_arg(sm + T::S_B, pf, k)) : 0.f;   // full-precision polynomial: forward errors move ReLU masks
+                    e[kk] = (k < EMB && !DFP_EXP(a, 64)) ? sin_cw(embed_arg(sm + T::S_B, pf, k)) : 0.f;   // full-precision polynomial: forward errors move ReLU masks
                 }
             } else {
 #pragma unroll 1
@@ -215,11 +236,15 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                     for (int u = 0; u < 16; ++u) if (u == kk) e[u] = v;
                 }
             }
+            PROF(5)
             if (ch > 0) { tc::mbar_wait(bar, parity); parity ^= 1; tc::fence_after_sync(); }   // previous chunk consumed A_X
+            PROF(6)
             tc::tmem_store_split16(tl + T::T_X_HI, tl + T::T_X_LO, e);
             tc::wait_st();
             tc::fence_before_sync();
+            PROF(7)
             tc::named_bar_sync(1 + grp, 256);
+            PROF(8)
             if (issuer_warp && tc::elect_one()) {
                 tc::fence_after_sync();
                 const uint32_t koff = (uint32_t)ch * 8u * (64u * 16u);             // 8 K-chunks of 16 B per 32 k, LBO = N*16
@@ -230,8 +255,10 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                 tc::mma_commit(bar);
             }
         }
+        PROF(9)
         tc::mbar_wait(bar, parity); parity ^= 1;
         tc::fence_after_sync();
+        PROF(10)
         float h[16];
         {
             float z[16], f[16];
@@ -247,16 +274,19 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             }
             if (a.act_h) {                                            // kept for the backward (DFP_FLAG_SAVE_ACT)
                 if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, 0, 5))[hf] = (uint16_t)m;
-                pl::store16(r_h, pl::h_pos(0) * 32 + 16 * hf, h);
-                if (hf == 0) pl::store_ones8(r_h, 160);
+                if (save_pl) pl::store16(r_h, pl::h_pos(0) * 32 + 16 * hf, h);
+                if (hf == 0 && save_pl) pl::store_ones8(r_h, 160);
             }
         }
+        PROF(11)
 #pragma unroll 1
         for (int i = 1; i < 5; ++i) {
             tc::tmem_store_split16(tl + T::T_X_HI, tl + T::T_X_LO, h);
             tc::wait_st();
             tc::fence_before_sync();
+            PROF(12)
             tc::named_bar_sync(1 + grp, 256);
+            PROF(13)
             if (issuer_warp && tc::elect_one()) {
                 tc::fence_after_sync();
                 tc::mma_3xtf32(tb + T::T_DH, tb + T::T_X_HI, tb + T::T_X_LO, bhi + (T::WH + (i - 1) * 1024) * 4,
@@ -265,8 +295,10 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                                blo + (T::WC + i * CD * 32) * 4, CD, 32, false);
                 tc::mma_commit(bar);
             }
+            PROF(14)
             tc::mbar_wait(bar, parity); parity ^= 1;
             tc::fence_after_sync();
+            PROF(15)
             float z[16], f[16];
             tc::tmem_ld16(tl + T::T_DH, z);
             tc::tmem_ld16(tl + T::T_DC, f);
@@ -279,6 +311,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             } else {
                 tc::wait_ld();
             }
+            PROF(16)
             uint32_t m = 0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -288,9 +321,10 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             }
             if (a.act_h) {
                 if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, i, 5))[hf] = (uint16_t)m;
-                pl::store16(r_h, pl::h_pos(i) * 32 + 16 * hf, h);
+                if (save_pl) pl::store16(r_h, pl::h_pos(i) * 32 + 16 * hf, h);
             }
         }
+        PROF(17)
         // output layer: each half sums its 16 inputs, the lower half adds the upper half's partial and the bias
         float out[NOUT];
 #pragma unroll
@@ -311,6 +345,8 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             if (NOUT == 1) a.out[s] = out[0];
             else *reinterpret_cast<float4*>(a.out + 4 * s) = make_float4(out[0], out[NOUT > 1 ? 1 : 0], out[NOUT > 2 ? 2 : 0], out[NOUT > 3 ? 3 : 0]);
         }
+        PROF(18)
+        PROF_TILE
     }
     tc::fence_before_sync();
     __syncthreads();

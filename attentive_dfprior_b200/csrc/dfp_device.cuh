@@ -294,7 +294,15 @@ struct DecArgs {
     // saved activations / scratch by list position.  Used for the high decoder, whose output and gradient only matter
     // on TSDF-band samples (decoder.py:326-333: f_add_m_occ is read under the band mask only).
     const int* list; const int* count;
+#ifdef DFP_EXPERIMENTS
+    int dbg;                 // timing experiments only (tools/exp_build.sh): bits switch parts of a kernel off; never in the product build
+#endif
 };
+#ifdef DFP_EXPERIMENTS
+#define DFP_EXP(a, bit) (((a).dbg & (bit)) != 0)
+#else
+#define DFP_EXP(a, bit) false
+#endif
 // number of work items and the sample id of item idx
 __device__ __forceinline__ int64_t dec_items(const DecArgs& a) { return a.list ? (int64_t)*a.count : a.n; }
 __device__ __forceinline__ int64_t dec_sample(const DecArgs& a, int64_t idx) { return a.list ? (int64_t)a.list[idx] : idx; }
