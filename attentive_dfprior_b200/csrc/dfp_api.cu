@@ -109,6 +109,7 @@ static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with
     w.low = (float*)take(ns * 4); w.high = (float*)take(ns * 4); w.tsdf = (float*)take(ns * 4);
     w.fused = (float*)take(ns * 4); w.w_attn = (float*)take(ns * 4);
     w.rgb = (float*)take(ns * 16);
+    w.xnpf = (float4*)take(ns * 32);
     w.flags = (int*)take(ns * 4); w.band_list = (int*)take(ns * 4); w.band_count = (int*)take(16);
     w.d_low = (float*)take(ns * 4); w.d_high = (float*)take(ns * 4); w.d_fused = (float*)take(ns * 4);
     w.d_rgb = (float*)take(ns * 16);
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(256) k_sample_z(const SampleArgs a) {
 struct PrepArgs {
     PointSrc ps; int64_t n; Bounds bound; Bounds tsdf_bnds; DfpTsdf tsdf; int need_tsdf;
     float* tsdf_out; int* flags; float* w_attn; int* band_list; int* band_count; int apply_mask;
+    float4* xnpf;
 };
 
 template <int MODE>
@@ -231,6 +233,12 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs a) {
             PT p[3];
             load_point<MODE>(a.ps, s, p);
             int f = (!a.apply_mask || in_bound(p, box)) ? 1 : 0;
+            {   // the decoders' per-sample inputs, once for all of them (DecArgs::xnpf)
+                float xb[3];
+                normalize(p, box, xb);
+                a.xnpf[2 * s] = make_float4(xb[0], xb[1], xb[2], 0.f);
+                a.xnpf[2 * s + 1] = make_float4((float)p[0], (float)p[1], (float)p[2], 0.f);
+            }
             if (a.need_tsdf) {
                 float xn[3];
                 normalize(p, tbox, xn);
@@ -599,13 +607,13 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
     PrepArgs pa;
     pa.ps = ps; pa.n = n; pa.bound = to_bounds(sc->bound); pa.tsdf_bnds = to_bounds(sc->tsdf_bnds); pa.tsdf = sc->tsdf;
     pa.need_tsdf = hi; pa.tsdf_out = w.tsdf; pa.flags = w.flags; pa.w_attn = w.w_attn;
-    pa.band_list = w.band_list; pa.band_count = w.band_count; pa.apply_mask = apply_mask;
+    pa.band_list = w.band_list; pa.band_count = w.band_count; pa.apply_mask = apply_mask; pa.xnpf = w.xnpf;
     DFP_TIMED("k_prep", st, k_prep<MODE><<<grid_for(n, 256, 8 * num_sms()), 256, 0, st>>>(pa));
     DFP_LAUNCH_CHECK("k_prep");
 
     DecArgs da;
     memset(&da, 0, sizeof(da));
-    da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params;
+    da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params; da.xnpf = w.xnpf;
 #ifdef DFP_EXPERIMENTS
     { const char* e = getenv("DFP_EXP"); da.dbg = e ? atoi(e) : 0; }
 #endif
@@ -665,7 +673,7 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
     }
     DecArgs da;
     memset(&da, 0, sizeof(da));
-    da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params;
+    da.ps = ps; da.n = n; da.bound = to_bounds(sc->bound); da.params = params; da.xnpf = w.xnpf;
 #ifdef DFP_EXPERIMENTS
     { const char* e = getenv("DFP_EXP"); da.dbg = e ? atoi(e) : 0; }
 #endif

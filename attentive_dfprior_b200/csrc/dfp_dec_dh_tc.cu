@@ -248,11 +248,8 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
         }
         PROF(9)
         // while the embedding product runs: point, trilinear set-up
-        PT p[3];
-        load_point<MODE>(a.ps, s, p);
-        float xn[3];
-        normalize(p, box, xn);
-        const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
+        float xn[3], pf[3];
+        point_inputs<MODE>(a, box, s, xn, pf);
         const bool fast = embed_fast_ok(pf, bmax);
         const Tri tri = tri_setup(xn, a.grid.W, a.grid.H, a.grid.D);
         PROF(10)

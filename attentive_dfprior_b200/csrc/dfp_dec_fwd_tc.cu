@@ -133,11 +133,8 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
         const bool valid = i_raw < nitems;
         const int64_t ia = valid ? i_raw : nitems - 1;               // position in the (optional) list: index of saved activations
         const int64_t s = dec_sample(a, ia);                         // sample id: index of points and outputs
-        PT p[3];
-        load_point<MODE>(a.ps, s, p);
-        float xn[3];
-        normalize(p, box, xn);
-        const float pf[3] = {(float)p[0], (float)p[1], (float)p[2]};
+        float xn[3], pf[3];
+        point_inputs<MODE>(a, box, s, xn, pf);
         const bool fast = embed_fast_ok(pf, bmax);
         pl::Row r_c, r_h;
         const bool save_pl = a.act_c && !DFP_EXP(a, 16);

@@ -84,6 +84,7 @@ struct Ws {                        // per-sample workspace arrays (NS samples)
     float* depthmax;               // [nchunks][2]: max(gt_depth*1.2), max(gt_depth)
     float* low; float* high; float* tsdf; float* fused; float* w_attn;   // [NS]
     float* rgb;                    // [NS][4]  colour decoder output (rgb + its unused 4th channel)
+    float4* xnpf;                  // [NS][2]: (point normalised to the scene bound, 0) and ((float)point, 0), written by k_prep
     int* flags;                    // [NS] bit0 in-bound, bit1 in TSDF band
     int* band_list;                // [NS] compacted band sample ids
     int* band_count;               // [4]
@@ -294,6 +295,9 @@ struct DecArgs {
     // saved activations / scratch by list position.  Used for the high decoder, whose output and gradient only matter
     // on TSDF-band samples (decoder.py:326-333: f_add_m_occ is read under the band mask only).
     const int* list; const int* count;
+    // per-sample (normalised point | float point) pairs written by k_prep (same dtype chain as load_point + normalize,
+    // so the values are bit-identical): the decoder kernels then skip the f64 ray-point / division chain.  May be null.
+    const float4* xnpf;
 #ifdef DFP_EXPERIMENTS
     int dbg;                 // timing experiments only (tools/exp_build.sh): bits switch parts of a kernel off; never in the product build
 #endif
@@ -303,6 +307,21 @@ struct DecArgs {
 #else
 #define DFP_EXP(a, bit) false
 #endif
+// the two per-sample inputs of a decoder: the point normalised to the scene bound (trilinear coordinates) and the point
+// itself in f32 (Fourier embedding)
+template <int MODE>
+__device__ __forceinline__ void point_inputs(const DecArgs& a, const BoxT<typename PtT<MODE>::T>& box, int64_t s, float xn[3], float pf[3]) {
+    if (a.xnpf) {
+        const float4 u = __ldg(a.xnpf + 2 * s), v = __ldg(a.xnpf + 2 * s + 1);
+        xn[0] = u.x; xn[1] = u.y; xn[2] = u.z;
+        pf[0] = v.x; pf[1] = v.y; pf[2] = v.z;
+    } else {
+        typename PtT<MODE>::T p[3];
+        load_point<MODE>(a.ps, s, p);
+        normalize(p, box, xn);
+        pf[0] = (float)p[0]; pf[1] = (float)p[1]; pf[2] = (float)p[2];
+    }
+}
 // number of work items and the sample id of item idx
 __device__ __forceinline__ int64_t dec_items(const DecArgs& a) { return a.list ? (int64_t)*a.count : a.n; }
 __device__ __forceinline__ int64_t dec_sample(const DecArgs& a, int64_t idx) { return a.list ? (int64_t)a.list[idx] : idx; }
