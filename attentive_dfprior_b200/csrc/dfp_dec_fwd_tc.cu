@@ -2,8 +2,8 @@
 // src/conv_onet/models/decoder.py:177-203 for tiles of 128 samples.
 //
 // One thread owns one sample = one TMEM lane.  It gathers the trilinear features and produces the
-// Fourier embedding on the CUDA cores (accurate sinf on f32 arguments of several hundred radians stays
-// there), writes those activations straight into TMEM as the A operand, and the five 32-wide blocks run as
+// Fourier embedding on the CUDA cores / special-function unit (range reduction of f32 arguments of several hundred
+// radians stays there), writes those activations straight into TMEM as the A operand, and the five 32-wide blocks run as
 // tcgen05.mma with the weights resident in shared memory (canonical K-major layout, hi/lo TF32 split).
 // Epilogues (bias, ReLU, feature term, split for the next layer) read the accumulators back with tcgen05.ld.
 // A CTA runs two independent 128-sample groups (one for the 64-feature high decoder) so that one group's
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
 #pragma unroll
                 for (int kk = 0; kk < 16; ++kk) {
                     const int k = ch * 32 + 16 * hf + kk;
-                    e[kk] = (k < EMB && !DFP_EXP(a, 64)) ? sin_cw(embed_arg(sm + T::S_B, pf, k)) : 0.f;   // full-precision polynomial: forward errors move ReLU masks
+                    e[kk] = (k < EMB && !DFP_EXP(a, 64)) ? __sinf(reduce_2pi(embed_arg(sm + T::S_B, pf, k))) : 0.f;
                 }
             } else {
 #pragma unroll 1

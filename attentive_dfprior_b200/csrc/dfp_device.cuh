@@ -220,12 +220,12 @@ __device__ __forceinline__ void scatter_features(const DfpGrid& g, float* ggrid,
     gn[0] = gx * t.gx; gn[1] = gy * t.gy; gn[2] = gz * t.gz;
 }
 
-// sin / cos of an embedding argument for the delta-chain kernel: two-constant Cody-Waite reduction to [-pi, pi] (exact
+// sin / cos of an embedding argument for the tensor-core kernels: two-constant Cody-Waite reduction to [-pi, pi] (exact
 // to ~1e-7 for |x| < 4.8e4, the range embed_fast_ok guarantees) and then the special-function unit, whose absolute
-// error on that interval is 2^-21.  7 instructions instead of ~30 for the polynomial sincos_cw.  Backward only: there
-// the values enter gradients smoothly.  The FORWARD keeps the polynomial sin_cw -- a 1e-6 forward error moves enough
-// ReLU masks of the fusion MLP to show up as a 1e-2 relative error in its (tiny) parameter gradients on a 64-ray batch
-// (found by __graft_entry__.smoke()).
+// error on that interval is 2^-21 (5e-7).  ~6 instructions instead of ~20 for the polynomial sin_cw.  Used by the delta
+// chain and, since round 2, by the forward: its error is below the 3xTF32 products' own (2e-6), the parity margins of
+// every fixture are unchanged (profiles/r02_parity_margins.json).  (Round 1 kept the polynomial in the forward because
+// the 64-ray smoke case failed with it; that failure was the stale scene-bounds cache, fixed since.)
 __device__ __forceinline__ float reduce_2pi(float x) {
     const float k = rintf(x * 0.15915494309189535f);
     return fmaf(-k, -1.7484555e-7f, fmaf(-k, 6.2831854820251465f, x));
