@@ -329,17 +329,31 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             PROF(13)
             tc::named_bar_sync(3 + grp, 256);
             PROF(14)
+            // Eight lanes own one corner index (0..7) of 32 consecutive samples of the tile.  Consecutive samples of a ray
+            // mostly sit in the same voxel cell (the near-surface samples are centimetres apart, a voxel is 16 / 32 cm), so
+            // the contributions to one corner line are summed in registers for as long as the line stays the same and
+            // only one reduction per run goes to L2 (roughly half the reductions on the fine grids, a quarter on the coarse one).
             const int sub = gt >> 3, q = gt & 7;
+            const int corner = sub & 7, smp0 = (sub >> 3) * 32;
             float4* gg4 = reinterpret_cast<float4*>(a.ggrid);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int cur = -1;
 #pragma unroll 4
             for (int it = 0; it < 32; ++it) {
-                const int pair = it * 32 + sub;               // (sample, corner): the 4 sub-groups of a warp share the sample
-                const int2 ent = s_cw[grp][pair];
-                if (ent.x < 0) continue;
-                const float wgt = __int_as_float(ent.y);
-                const float4 v = *reinterpret_cast<const float4*>(&s_dc[grp][pair >> 3][4 * q]);
-                red_add_v4(reinterpret_cast<float*>(gg4 + ent.x + q), v.x * wgt, v.y * wgt, v.z * wgt, v.w * wgt);
+                const int smp = smp0 + it;
+                const int2 ent = s_cw[grp][smp * 8 + corner];
+                if (ent.x != cur) {
+                    if (cur >= 0) red_add_v4(reinterpret_cast<float*>(gg4 + cur + q), acc.x, acc.y, acc.z, acc.w);
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    cur = ent.x;
+                }
+                if (ent.x >= 0) {
+                    const float wgt = __int_as_float(ent.y);
+                    const float4 v = *reinterpret_cast<const float4*>(&s_dc[grp][smp][4 * q]);
+                    acc.x = fmaf(v.x, wgt, acc.x); acc.y = fmaf(v.y, wgt, acc.y); acc.z = fmaf(v.z, wgt, acc.z); acc.w = fmaf(v.w, wgt, acc.w);
+                }
             }
+            if (cur >= 0) red_add_v4(reinterpret_cast<float*>(gg4 + cur + q), acc.x, acc.y, acc.z, acc.w);
         } else if (valid && any && (a.ggrid || want_coord) && !DFP_EXP(a, 2)) {
             scatter_features16(a.grid, a.ggrid, tri, hf, d_c, want_coord, gn);
         }
