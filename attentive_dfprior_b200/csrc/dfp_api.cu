@@ -127,6 +127,7 @@ static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with
     for (int d = 0; d < 3; ++d) w.fcc[d] = (float*)take(act ? (size_t)(65 * 144) * 4 : 0);      // contiguous: one memset
     w.sc_darg = (float*)take(act ? pl::array_bytes(nsp, pl::F_DL0) : 0);
     w.sc_dl1 = (float*)take(act ? pl::array_bytes(nsp, pl::F_DL1) : 0);
+    w.dec_tileflag = (int*)take(act ? (size_t)(nsp / 128) * 4 : 0);
     // fusion MLP (tensor-core path): activations, ReLU masks, softmax outputs kept by the forward and the delta planes of
     // the backward, per 128-sample tile of the band list (which can be as long as the sample list)
     const bool att = act && stage >= DFP_STAGE_HIGH;
@@ -680,7 +681,7 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
     da.gparams = g->params_packed; da.dp = want_dp ? w.dp : nullptr;
     // tensor-core backward (needs the activations saved by the tensor-core forward): K1 = delta chain, K2 = weight grads
     const bool tcb = flags_tc(flags) && (flags & DFP_FLAG_SAVE_ACT) && w.act_h[0] != nullptr;
-    da.sc_e = w.sc_e; da.sc_darg = w.sc_darg; da.sc_dl1 = w.sc_dl1;
+    da.sc_e = w.sc_e; da.sc_darg = w.sc_darg; da.sc_dl1 = w.sc_dl1; da.tileflag = w.dec_tileflag;
     if (tcb && da.gparams) DFP_CUDA(cudaMemsetAsync(w.fcc[0], 0, (size_t)((char*)w.fcc[2] - (char*)w.fcc[0]) + 65 * 144 * 4, st));
     auto run = [&](auto dec_tag) -> int {
         constexpr int DEC = decltype(dec_tag)::value;

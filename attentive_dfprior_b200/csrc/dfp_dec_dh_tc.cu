@@ -148,10 +148,12 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
         bool any = false;
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) any = any || (dout[o] != 0.f);
-        // kernel 2 reads the scratch of every sample of a tile it processes, so a skipped tile is marked by zero deltas:
-        // it decides with the same predicate (all upstream gradients of the tile are zero)
+        // kernel 2 reads the planes of every sample of a tile it processes; a tile whose upstream gradients are all zero is
+        // skipped by both kernels: the flag written here is kernel 2's tile list
         PROF(0)
-        if (!group_any(any, 1 + grp)) continue;
+        const bool tile_any = group_any(any, 1 + grp);
+        if (gt == 0 && planes) a.tileflag[tile] = tile_any ? 1 : 0;
+        if (!tile_any) continue;
         PROF(1)
 
         float dh[16];

@@ -102,6 +102,7 @@ struct Ws {                        // per-sample workspace arrays (NS samples)
     float* fcc[3];                 // per decoder: accumulated [c | 1]^T [dout8 | dacc..] ((CD + 1) x 144 floats, zeroed before the backward)
     float* sc_darg;                // DL0: upstream gradient and masked deltas of blocks 4, 2, 1, 3
     float* sc_dl1;                 // DL1: masked deltas of blocks 3, 0 and the gradient of the embedding arguments
+    int* dec_tileflag;             // [tiles]: 1 if the 128-sample tile carries any upstream gradient (written by K1, read by K2 of the same decoder)
     float* att_act;                // SIMT path: fusion MLP activations per band-list position (AttArgs::act)
     unsigned char* att_planes; uint32_t* att_masks; float* att_soft; unsigned char* att_dplanes; int* att_tileflag;   // tensor-core path (AttArgs::tc_*)
 };
@@ -295,6 +296,7 @@ struct DecArgs {
     // saved activations / scratch by list position.  Used for the high decoder, whose output and gradient only matter
     // on TSDF-band samples (decoder.py:326-333: f_add_m_occ is read under the band mask only).
     const int* list; const int* count;
+    int* tileflag;           // tensor-core backward: per 128-sample tile, 1 if any upstream gradient is non-zero (K1 writes, K2 reads)
     // per-sample (normalised point | float point) pairs written by k_prep (same dtype chain as load_point + normalize,
     // so the values are bit-identical): the decoder kernels then skip the f64 ray-point / division chain.  May be null.
     const float4* xnpf;
