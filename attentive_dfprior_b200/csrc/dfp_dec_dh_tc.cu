@@ -266,11 +266,13 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             tc::wait_ld();
             float sn[16], da[16];
             if (fast) {                                   // branch hoisted out of the unrolled loop (code size / I-cache)
+                float arg[16];
+                embed_arg16(sm + T::S_B, pf, ch * 32 + c0, arg);
 #pragma unroll
                 for (int kk = 0; kk < 16; ++kk) {
                     const int k = ch * 32 + c0 + kk;
                     float s1 = (k == EMB) ? 1.f : 0.f, c1 = 0.f;    // column 93 of the sin array: constant 1 (bias of block 0 in kernel 2)
-                    if (k < EMB) sincos_sfu(embed_arg(sm + T::S_B, pf, k), s1, c1);
+                    if (k < EMB) sincos_sfu(arg[kk], s1, c1);
                     sn[kk] = s1;
                     da[kk] = de[kk] * c1;
                 }

@@ -219,10 +219,12 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
         for (int ch = 0; ch < 3; ++ch) {
             float e[16];
             if (fast) {                                   // branch hoisted: one copy of each path keeps the kernel inside the I-cache
+                float arg[16];
+                embed_arg16(sm + T::S_B, pf, ch * 32 + 16 * hf, arg);           // columns 93..95 of the staged matrix are zero padding
 #pragma unroll
                 for (int kk = 0; kk < 16; ++kk) {
                     const int k = ch * 32 + 16 * hf + kk;
-                    e[kk] = (k < EMB && !DFP_EXP(a, 64)) ? __sinf(reduce_2pi(embed_arg(sm + T::S_B, pf, k))) : 0.f;
+                    e[kk] = (k < EMB && !DFP_EXP(a, 64)) ? __sinf(reduce_2pi(arg[kk])) : 0.f;
                 }
             } else {
 #pragma unroll 1
