@@ -158,11 +158,13 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
 
         float dh[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float acc = 0.f;
+        for (int j = 0; j < 16; ++j) dh[j] = 0.f;
 #pragma unroll
-            for (int o = 0; o < NOUT; ++o) acc = fmaf(sm[T::S_WO + o * 32 + c0 + j], dout[o], acc);
-            dh[j] = acc;
+        for (int o = 0; o < NOUT; ++o) {
+            float wo[16];
+            tc::lds16(sm + T::S_WO + o * 32 + c0, wo);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dh[j] = fmaf(wo[j], dout[o], dh[j]);
         }
         float dacc3[16];
 #pragma unroll

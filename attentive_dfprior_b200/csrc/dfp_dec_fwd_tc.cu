@@ -265,11 +265,14 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             tc::tmem_ld16(tl + T::T_DC, f);
             tc::wait_ld();
             uint32_t m = 0;
+            float bp[16], bc[16];
+            tc::lds16(sm + T::S_BP + 16 * hf, bp);
+            tc::lds16(sm + T::S_BC + 16 * hf, bc);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float pre = z[j] + sm[T::S_BP + 16 * hf + j];
+                const float pre = z[j] + bp[j];
                 m |= (pre > 0.f ? 1u : 0u) << j;
-                h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + 16 * hf + j]);
+                h[j] = fmaxf(pre, 0.f) + (f[j] + bc[j]);
             }
             if (a.act_h) {                                            // kept for the backward (DFP_FLAG_SAVE_ACT)
                 if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, 0, 5))[hf] = (uint16_t)m;
@@ -312,11 +315,14 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             }
             PROF(16)
             uint32_t m = 0;
+            float bp[16], bc[16];
+            tc::lds16(sm + T::S_BP + i * 32 + 16 * hf, bp);
+            tc::lds16(sm + T::S_BC + i * 32 + 16 * hf, bc);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float pre = z[j] + sm[T::S_BP + i * 32 + 16 * hf + j];
+                const float pre = z[j] + bp[j];
                 m |= (pre > 0.f ? 1u : 0u) << j;
-                h[j] = fmaxf(pre, 0.f) + (f[j] + sm[T::S_BC + i * 32 + 16 * hf + j]);
+                h[j] = fmaxf(pre, 0.f) + (f[j] + bc[j]);
             }
             if (a.act_h) {
                 if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, i, 5))[hf] = (uint16_t)m;
@@ -328,9 +334,10 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
         float out[NOUT];
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) {
-            float acc = 0.f;
+            float acc = 0.f, wo[16];
+            tc::lds16(sm + T::S_WO + o * 32 + 16 * hf, wo);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc = fmaf(sm[T::S_WO + o * 32 + 16 * hf + j], h[j], acc);
+            for (int j = 0; j < 16; ++j) acc = fmaf(wo[j], h[j], acc);
             out[o] = acc;
         }
         if (hf == 1) {
