@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libdfprior_b200.so")
 ABI_VERSION = 8
 FLAG_SAVE_ACT = 1
 FLAG_SIMT = 2
+FLAG_FROZEN = (4, 8, 16)          # low, high, colour decoder: no parameter gradient wanted (DFP_FLAG_FROZEN_*)
 MAX_RAY_SAMPLES = 64
 N_PARAM_TENSORS = 79
 N_PARAMS = 86029

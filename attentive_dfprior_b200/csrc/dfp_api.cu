@@ -83,7 +83,11 @@ void timing_end(cudaStream_t st) {
 // state: default = tcgen05 tensor-core kernels; DFP_FLAG_SIMT selects the fp32 SIMT kernels (in-tree cross-check).
 // The saved-activation training path (DFP_FLAG_SAVE_ACT) exists only on the tensor-core kernels.
 static inline bool flags_tc(int flags) { return (flags & DFP_FLAG_SIMT) == 0; }
-static int train_flags(int flags) { return flags_tc(flags) ? (flags & DFP_FLAG_SAVE_ACT) : DFP_FLAG_SIMT; }
+static int train_flags(int flags) {
+    return flags_tc(flags) ? (flags & (DFP_FLAG_SAVE_ACT | DFP_FLAG_FROZEN_LOW | DFP_FLAG_FROZEN_HIGH | DFP_FLAG_FROZEN_COLOR)) : DFP_FLAG_SIMT;
+}
+// decoder d (0 low, 1 high, 2 colour) takes part in the weight-gradient path of this call
+static inline bool dec_frozen(int flags, int d) { return (flags & (d == 0 ? DFP_FLAG_FROZEN_LOW : d == 1 ? DFP_FLAG_FROZEN_HIGH : DFP_FLAG_FROZEN_COLOR)) != 0; }
 
 static int g_num_sms = 0;
 int num_sms() {
@@ -118,10 +122,12 @@ static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with
     const int64_t nsp = (ns + 127) / 128 * 128;          // tile-major arrays cover whole 128-sample tiles
     for (int d = 0; d < 3; ++d) {
         const bool used = act && (d == 0 || (d == 1 && stage >= DFP_STAGE_HIGH) || (d == 2 && stage == DFP_STAGE_COLOR));
-        w.act_h[d] = (float*)take(used ? pl::array_bytes(nsp, pl::F_H) : 0);
+        const bool wg = used && !dec_frozen(flags, d);      // weight-gradient operands only for decoders that are trained
+        w.act_h[d] = (float*)take(wg ? pl::array_bytes(nsp, pl::F_H) : 0);
         w.act_m[d] = (uint32_t*)take(used ? nsp * 5 * 4 : 0);
-        w.act_c[d] = (float*)take(used ? pl::array_bytes(nsp, pl::f_cx(d == 1 ? 64 : 32)) : 0);
-        if (!used) { w.act_h[d] = nullptr; w.act_m[d] = nullptr; w.act_c[d] = nullptr; }
+        w.act_c[d] = (float*)take(wg ? pl::array_bytes(nsp, pl::f_cx(d == 1 ? 64 : 32)) : 0);
+        if (!wg) { w.act_h[d] = nullptr; w.act_c[d] = nullptr; }
+        if (!used) w.act_m[d] = nullptr;
     }
     w.sc_e = (float*)take(act ? pl::array_bytes(nsp, pl::F_EX) : 0);
     for (int d = 0; d < 3; ++d) w.fcc[d] = (float*)take(act ? (size_t)(65 * 144) * 4 : 0);      // contiguous: one memset
@@ -680,7 +686,7 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
 #endif
     da.gparams = g->params_packed; da.dp = want_dp ? w.dp : nullptr;
     // tensor-core backward (needs the activations saved by the tensor-core forward): K1 = delta chain, K2 = weight grads
-    const bool tcb = flags_tc(flags) && (flags & DFP_FLAG_SAVE_ACT) && w.act_h[0] != nullptr;
+    const bool tcb = flags_tc(flags) && (flags & DFP_FLAG_SAVE_ACT) && w.act_m[0] != nullptr;
     da.sc_e = w.sc_e; da.sc_darg = w.sc_darg; da.sc_dl1 = w.sc_dl1; da.tileflag = w.dec_tileflag;
     if (tcb && da.gparams) DFP_CUDA(cudaMemsetAsync(w.fcc[0], 0, (size_t)((char*)w.fcc[2] - (char*)w.fcc[0]) + 65 * 144 * 4, st));
     auto run = [&](auto dec_tag) -> int {
@@ -688,9 +694,12 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
         if (!tcb) return launch_decoder_bwd<DEC, MODE>(da, st);
         da.act_h = w.act_h[DEC]; da.act_m = w.act_m[DEC]; da.act_c = w.act_c[DEC]; da.fcc = w.fcc[DEC];
         da.list = (DEC == 1) ? w.band_list : nullptr; da.count = (DEC == 1) ? w.band_count : nullptr;   // as in the forward
+        float* const gp = da.gparams;
+        if (dec_frozen(flags, DEC)) da.gparams = nullptr;        // K1 then writes no operands for K2, and K2 does not run
         int r = launch_decoder_dh_tc<DEC, MODE>(da, st);
-        if (r || !da.gparams) return r;
-        return launch_decoder_dw_tc<DEC>(da, st);
+        if (!r && da.gparams) r = launch_decoder_dw_tc<DEC>(da, st);
+        da.gparams = gp;
+        return r;
     };
     if (hi) {
         da.grid = sc->high; da.grid_low = sc->low; da.dout = w.d_high; da.ggrid = g->grid_high;

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                 m |= (pre > 0.f ? 1u : 0u) << j;
                 h[j] = fmaxf(pre, 0.f) + (f[j] + bc[j]);
             }
-            if (a.act_h) {                                            // kept for the backward (DFP_FLAG_SAVE_ACT)
+            if (a.act_m) {                                            // kept for the backward (DFP_FLAG_SAVE_ACT)
                 if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, 0, 5))[hf] = (uint16_t)m;
                 if (save_pl) pl::store16(r_h, pl::h_pos(0) * 32 + 16 * hf, h);
                 if (hf == 0 && save_pl) pl::store_ones8(r_h, 160);
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
                 m |= (pre > 0.f ? 1u : 0u) << j;
                 h[j] = fmaxf(pre, 0.f) + (f[j] + bc[j]);
             }
-            if (a.act_h) {
+            if (a.act_m) {
                 if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, i, 5))[hf] = (uint16_t)m;
                 if (save_pl) pl::store16(r_h, pl::h_pos(i) * 32 + 16 * hf, h);
             }

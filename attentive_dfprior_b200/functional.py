@@ -242,6 +242,20 @@ def _reduce_buckets(flat, spans, overlap, group):
 WORKSPACE_BUDGET_BYTES = 24 << 30
 
 
+def _frozen_flags(need_params, train):
+    """DFP_FLAG_FROZEN_* for the decoders none of whose 23 tensors (state_dict order: low, high, colour) needs a gradient:
+    the library then keeps no weight-gradient operands for them and skips their weight-gradient kernel.  The reference's
+    Mapper never optimises the low decoder and, with fix_high / fix_color, leaves those out as well (src/Mapper.py:364-371);
+    a caller that also sets ``requires_grad_(False)`` on them gets this for free, like autograd's own pruning."""
+    if not train or len(need_params) < 69:
+        return 0
+    f = 0
+    for d in range(3):
+        if not any(need_params[23 * d:23 * (d + 1)]):
+            f |= L.FLAG_FROZEN[d]
+    return f
+
+
 class _RenderBatchRay(torch.autograd.Function):
     @staticmethod
     def _fwd_call(aux, scene, packed, ro, rd, gt, dmax, lo, hi, flags, outs, want_aux):
@@ -275,7 +289,7 @@ class _RenderBatchRay(torch.autograd.Function):
         packed = aux.pack.get(list(params))
         scene = _scene_struct(grids_cl, aux.tsdf_volume, aux.tsdf_bnds, aux.bound)
         train = any(ctx.needs_input_grad)
-        flags = (L.FLAG_SIMT if aux.simt else 0) | (L.FLAG_SAVE_ACT if train else 0)
+        flags = (L.FLAG_SIMT if aux.simt else 0) | (L.FLAG_SAVE_ACT if train else 0) | _frozen_flags(ctx.needs_input_grad[6:], train)
         depth = torch.empty(N, device=dev, dtype=torch.float64)
         unc = torch.empty(N, device=dev, dtype=torch.float64)
         color = torch.empty(N, 3, device=dev, dtype=torch.float32)
@@ -413,7 +427,8 @@ class _EvalPoints(torch.autograd.Function):
         grids_cl = {k: (_grid_ndhwc(given[k]) if k in _needed_grids(aux.stage) else None) for k in GRID_KEYS}
         packed = aux.pack.get(list(params))
         scene = _scene_struct(grids_cl, aux.tsdf_volume, aux.tsdf_bnds, aux.bound)
-        flags = (L.FLAG_SIMT if aux.simt else 0) | (L.FLAG_SAVE_ACT if any(ctx.needs_input_grad) else 0)
+        flags = ((L.FLAG_SIMT if aux.simt else 0) | (L.FLAG_SAVE_ACT if any(ctx.needs_input_grad) else 0)
+                 | _frozen_flags(ctx.needs_input_grad[5:], any(ctx.needs_input_grad)))
         P = L.DfpPoints(p.data_ptr(), 1 if p.dtype == torch.float64 else 0, 1 if aux.apply_bound_mask else 0, n, flags, 0)
         raw = torch.empty(n, 4, device=dev, dtype=torch.float32)
         w = torch.empty(n, device=dev, dtype=torch.float32)

@@ -57,6 +57,12 @@ typedef enum DfpStage { DFP_STAGE_LOW = 0, DFP_STAGE_HIGH = 1, DFP_STAGE_COLOR =
                                   kernels (in-tree cross-check of the product path; several times slower).  Like
                                   every flag it belongs to the call: pass the same value to the workspace-size
                                   function, the forward and the backward.  The library keeps no switches. */
+#define DFP_FLAG_FROZEN_LOW 4   /* with DFP_FLAG_SAVE_ACT: no PARAMETER gradient is wanted for the low / high / colour */
+#define DFP_FLAG_FROZEN_HIGH 8  /* decoder (none of its tensors requires grad -- the reference's Mapper never optimises the */
+#define DFP_FLAG_FROZEN_COLOR 16 /* low decoder and, with fix_high / fix_color, leaves those out too: src/Mapper.py:364-371).
+                                  The forward then keeps no weight-gradient operands for that decoder and the backward
+                                  skips its weight-gradient kernel; its rows of DfpGrads.params_packed stay untouched.
+                                  Grid gradients, the fusion MLP's gradients and d(rays) are unaffected. */
 
 /* One feature grid.  Logical shape is the reference's [1, C, D, H, W]
  * (src/DF_Prior.py:243-266) but memory is channels-last: element (z, y, x, c)

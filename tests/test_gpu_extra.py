@@ -57,6 +57,41 @@ def test_extra_render_fixture(name, channels_last):
             assert rel_err(named[k].grad, g, name + ".grad.decoders") <= 1e-3, k
 
 
+def test_frozen_decoders_skip_their_weight_gradients():
+    """The reference's Mapper keeps the low decoder (and, with fix_high, the high decoder) out of its optimiser
+    (src/Mapper.py:364-371).  With requires_grad=False on their tensors the library keeps no weight-gradient operands for
+    them (DFP_FLAG_FROZEN_*): the remaining gradients must still match the reference's, the frozen tensors get none, and
+    the call needs less workspace."""
+    from attentive_dfprior_b200 import _lib as L
+    fx = load_extra("extra_nodepth_color")
+    inp, stage = fx["inputs"], fx["stage"]
+    model, renderer, grids, tsdf, tb = build(inp, True)
+    grids = {k: v.requires_grad_(True) for k, v in grids.items()}
+    for prm in list(model.low_decoder.parameters()) + list(model.high_decoder.parameters()):
+        prm.requires_grad_(False)
+    rays_o, rays_d = inp["rays_o"].to(DEV), inp["rays_d"].to(DEV)
+    depth, unc, color, weight = renderer.render_batch_ray(grids, model, rays_d, rays_o, DEV, tsdf, tb, stage, gt_depth=None)
+    loss = extra_loss(fx, depth, unc, color, weight)
+    loss.backward()
+    assert abs(float(loss) - float(fx["outputs"]["loss"])) <= 1e-4 * abs(float(fx["outputs"]["loss"]))
+    for k, g in fx["grads"]["grids"].items():
+        if g is not None and float(g.abs().max()) > 0:
+            assert rel_err(grids[k].grad, g) <= 1e-3, k
+    named = dict(model.named_parameters())
+    seen = 0
+    for k, g in fx["grads"]["params"].items():
+        if k.startswith(("low_decoder.", "high_decoder.")):
+            assert named[k].grad is None, k
+        elif g is not None and float(g.abs().max()) > 0:
+            assert rel_err(named[k].grad, g) <= 1e-3, k
+            seen += 1
+    assert seen >= 20
+    lib = L.lib()
+    full = lib.dfp_render_workspace_bytes(1024, 32, 0, L.STAGES["color"], L.FLAG_SAVE_ACT)
+    part = lib.dfp_render_workspace_bytes(1024, 32, 0, L.STAGES["color"], L.FLAG_SAVE_ACT | L.FLAG_FROZEN[0] | L.FLAG_FROZEN[1])
+    assert part < full - 2 * 1024 * 32 * 800          # the H / CX planes of two decoders (>= 832 B per sample each) are gone
+
+
 def test_tsdf_sampling_matches_reference():
     """Renderer / Mesher eval_points_tsdf and sample_grid_tsdf (dfp_tsdf_sample) on f64 and f32 points."""
     import attentive_dfprior_b200 as A

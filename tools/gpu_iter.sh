@@ -11,6 +11,7 @@ import json
 d = json.loads(open("gpurun_out/bench.json").read())
 print("ms/step", round(d["ms_per_step"], 3), "rays/s", round(d["value"]), "e2e", round(d["e2e"]["value"]), "clk", d["clocks"])
 print(d["roofline"]["kernels_ms_per_step"])
+if d.get("mapping_frozen_low_high"): print("frozen low+high", round(d["mapping_frozen_low_high"]["ms_per_step"], 3))
 for k in ("mapping_1000_rays", "tracker_200_rays"):
     s = d.get(k)
     if s: print(k, round(s["ms_per_step"], 4), "graph", s.get("cuda_graph", {}).get("ms_per_step"), "graph e2e", s.get("cuda_graph", {}).get("e2e", {}).get("ms_per_step"))
