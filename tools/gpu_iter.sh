@@ -4,8 +4,8 @@
 mkdir -p gpurun_out
 {
 if [ "${FULL:-0}" = "1" ]; then targets="tests"; else targets="tests/test_gpu_parity.py tests/test_gpu_extra.py tests/test_gpu_tc.py"; fi
-timeout 900 python -m pytest $targets -m gpu -x -q 2>&1 | tail -4
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-baseline ${BENCH_ARGS} 2>gpurun_out/bench.err | tail -1 > gpurun_out/bench.json
+timeout 240 python -m pytest $targets -m gpu -x -q 2>&1 | tail -4
+timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-baseline ${BENCH_ARGS} 2>gpurun_out/bench.err | tail -1 > gpurun_out/bench.json
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/bench.json").read())
