@@ -517,7 +517,36 @@ constexpr int ATT_IMG_BLOCKS = 16;      // 4096 (row, 8-input chunk) tasks of th
 
 constexpr int PACK_SPLIT = 8;           // blocks per tensor (the largest tensor has 16 384 elements: one block per tensor is latency-bound)
 
+constexpr int DEC_M_BLOCKS = 3 * 17;     // per decoder: 4096 entries of M_1..M_4 (16 blocks of 256) + one block for V
+
 __global__ void k_pack_params(const PtrTable tab, float* __restrict__ packed) {
+    if (blockIdx.x >= N_TENSORS + ATT_IMG_BLOCKS) {
+        // delta-chain products of the decoders (dfp_layout.h, DecM), straight from the native [out][in] tensors
+        if (blockIdx.y != 0) return;
+        const int b = blockIdx.x - N_TENSORS - ATT_IMG_BLOCKS, dec = b / 17, blk = b % 17;
+        const int cd = dec_cd(dec), nout = dec_nout(dec);
+        float* dst = packed + OFF_DEC_M + dec * DecM::SIZE;
+        const int t0 = 23 * dec;                                         // fc_c.i.weight = t0 + 2 i, pts_linears.i.weight = t0 + 11 + 2 i
+        if (blk < 16) {
+            const int e = blk * 256 + threadIdx.x, slot = e >> 10, j = (e >> 5) & 31, q = e & 31, i = slot + 1;
+            const float* W = tab.p[t0 + 11 + 2 * i];                     // [32][32], or [32][93 + 32] for i = 3 (hidden part last)
+            const int ld = (i == 3) ? EMB + HID : HID, k0 = (i == 3) ? EMB : 0;
+            const float* Wc = tab.p[t0 + 2 * (i - 1)];                   // fc_c.(i-1).weight [32][cd]
+            float acc = 0.f;
+            for (int k = 0; k < HID; ++k) acc = fmaf(W[j * ld + k0 + k], Wc[k * cd + q], acc);
+            dst[DecM::M + e] = acc;
+        } else if (threadIdx.x < 4 * HID) {
+            const int o = threadIdx.x >> 5, q = threadIdx.x & 31;
+            float acc = 0.f;
+            if (o < nout) {
+                const float* Wo = tab.p[t0 + 21];                        // output_linear.weight [nout][32]
+                const float* Wc = tab.p[t0 + 8];                         // fc_c.4.weight [32][cd]
+                for (int k = 0; k < HID; ++k) acc = fmaf(Wo[o * HID + k], Wc[k * cd + q], acc);
+            }
+            dst[DecM::V + threadIdx.x] = acc;
+        }
+        return;
+    }
     if (blockIdx.x >= N_TENSORS) {
         if (blockIdx.y != 0) return;
         // tensor-core image of the fusion MLP (dfp_layout.h, AttImg): 8 consecutive inputs of one output row are 32
@@ -785,7 +814,7 @@ int dfp_pack_params(const float* const* tensors79, float* packed, void* stream) 
         if (!tensors79[t]) return fail(DFP_ERR_INVALID, "parameter tensor %d is null", t);
         tab.p[t] = tensors79[t];
     }
-    DFP_TIMED("k_pack_params", (cudaStream_t)stream, k_pack_params<<<dim3(N_TENSORS + ATT_IMG_BLOCKS, PACK_SPLIT), 256, 0, (cudaStream_t)stream>>>(tab, packed));
+    DFP_TIMED("k_pack_params", (cudaStream_t)stream, k_pack_params<<<dim3(N_TENSORS + ATT_IMG_BLOCKS + DEC_M_BLOCKS, PACK_SPLIT), 256, 0, (cudaStream_t)stream>>>(tab, packed));
     DFP_LAUNCH_CHECK("k_pack_params");
     return DFP_OK;
 }

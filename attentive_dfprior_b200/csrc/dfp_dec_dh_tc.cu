@@ -2,9 +2,12 @@
 //
 // For tiles of 128 samples (one sample = one TMEM lane, served by two threads that own 16 columns each) this back-propagates through the five blocks
 // of one decoder (src/conv_onet/models/decoder.py:192-203 reversed) using the activations the tensor-core forward
-// kept (ReLU masks): per block  d_c += dh_i * Wc_i  and  dh_{i-1} = mask_i(dh_i) * W_i  run as tcgen05.mma with the
-// deltas written into TMEM by their owner threads and the weights resident in shared memory in their natural
-// [out][in] layout (the MN-major / transposed B operand, dfp_tc.cuh).  The embedding gradient
+// kept (ReLU masks): per block ONE product  [d_c | dh_{i-1}] (+)= dacc_i * [M_i | W_i]  with dacc_i = mask_i(dh_i) written
+// into TMEM by its owner threads (the feature gradient d_c = sum_i dh_i Wc_i is linear in the masked deltas, so
+// M_i = W_i Wc_{i-1} comes precomputed from the pack kernel, dfp_layout.h DecM, and dh_i itself is never an operand; the
+// dh_4 = dout W_o term is added on the CUDA cores) and the weights resident in shared memory in their natural [out][in]
+// layout (the MN-major / transposed B operand, dfp_tc.cuh).  The tensor pipe is shared by the CTA's two tile groups and
+// runs their MMAs in order, so halving the MMA count shortens both groups' chains.  The embedding gradient
 // d_e = [dacc_0 | dacc_3] * [W_0 ; W_3e] is one K=64, N=96 product.  Outputs: the feature gradient scattered into
 // the dense grid gradient (vector reductions), d(point) for the Tracker, and -- for kernel 2 (dfp_dec_dw_tc.cu) --
 // the per-block deltas, sin(arg) and d(arg) in the feature-major scratch arrays.
@@ -28,22 +31,22 @@ extern "C" int dfp_exp_clear_prof_dh() { unsigned long long z[32] = {}; return (
 #endif
 
 struct DhLayout {                                       // shared memory, in floats
-    static constexpr int WH = 0;                        // 4 tiles [32 j][32 kin]: pts_linears.1, .2, .3[:, 93:], .4
-    static constexpr int W03 = WH + 4 * 1024;           // 3 column blocks of [64 j][32 kin]: rows 0..31 pts_linears.0, 32..63 pts_linears.3[:, :93]
-    static constexpr int WC = W03 + 3 * 2048;           // 5 tiles [32 j][32 kin]: fc_c.i restricted to this decoder's own grid features
-    static constexpr int BSIZE = WC + 5 * 1024;         // one split half (hi or lo)
+    static constexpr int PAIR = 0;                      // 4 x {M_i tile [32 j][32 q], W_i tile [32 j][32 kin]} for blocks i = 1..4 (W: pts_linears.1, .2, .3[:, 93:], .4)
+    static constexpr int W03 = PAIR + 4 * 2048;         // 3 column blocks of [64 j][32 kin]: rows 0..31 pts_linears.0, 32..63 pts_linears.3[:, :93]
+    static constexpr int BSIZE = W03 + 3 * 2048;        // one split half (hi or lo)
     static constexpr int S_WO = 2 * BSIZE;              // [4][32] output rows
     static constexpr int S_B = S_WO + 128;              // [3][96] embedding matrix
-    static constexpr int FLOATS = S_B + 288;
+    static constexpr int S_V = S_B + 288;               // [4][32] V = W_o Wc_4
+    static constexpr int FLOATS = S_V + 128;
     // TMEM columns of one 128-sample group
     static constexpr int T_A = 0;                       // 128 columns of A operands (see kernel)
-    static constexpr int T_DC = 128;                    // d_c accumulator
-    static constexpr int T_DX = 160;                    // dh_{i-1} (32) / d_e (96)
+    static constexpr int T_DC = 128;                    // d_c accumulator ...
+    static constexpr int T_DX = 160;                    // ... directly followed by dh_{i-1} (32) / later d_e (96)
     static constexpr int T_COLS = 256;
 };
 
 template <int CD>
-__device__ __forceinline__ void stage_weights_dh(float* sm, const float* __restrict__ P) {
+__device__ __forceinline__ void stage_weights_dh(float* sm, const float* __restrict__ P, const float* __restrict__ PM /* DecM block */) {
     using L = DecOff<CD>;
     float* hi = sm;
     float* lo = sm + DhLayout::BSIZE;
@@ -52,7 +55,14 @@ __device__ __forceinline__ void stage_weights_dh(float* sm, const float* __restr
         const int slot = i >> 10, kin = (i >> 5) & 31, j = i & 31;
         const float w = P[L::WH + i];
         const float h = tc::tf32_rna(w);
-        const int o = DhLayout::WH + slot * 1024 + tc::mn_tile_index(j, kin);
+        const int o = DhLayout::PAIR + slot * 2048 + 1024 + tc::mn_tile_index(j, kin);
+        hi[o] = h; lo[o] = tc::tf32_rna(w - h);
+    }
+    for (int i = threadIdx.x; i < 4 * 1024; i += nt) {                 // DecM::M: [slot][j][q]
+        const int slot = i >> 10, j = (i >> 5) & 31, q = i & 31;
+        const float w = PM[DecM::M + i];
+        const float h = tc::tf32_rna(w);
+        const int o = DhLayout::PAIR + slot * 2048 + tc::mn_tile_index(j, q);
         hi[o] = h; lo[o] = tc::tf32_rna(w - h);
     }
     for (int i = threadIdx.x; i < 96 * 64; i += nt) {                  // packed W03: [kin][64 j]
@@ -62,14 +72,7 @@ __device__ __forceinline__ void stage_weights_dh(float* sm, const float* __restr
         const int o = DhLayout::W03 + (kin >> 5) * 2048 + tc::mn_tile_index(j, kin & 31);
         hi[o] = h; lo[o] = tc::tf32_rna(w - h);
     }
-    for (int i = threadIdx.x; i < 5 * 1024; i += nt) {                 // packed WC: [layer][kin < CD][j], first 32 kin only
-        const int layer = i >> 10, kin = (i >> 5) & 31, j = i & 31;
-        const float w = P[L::WC + layer * CD * 32 + kin * 32 + j];
-        const float h = tc::tf32_rna(w);
-        const int o = DhLayout::WC + layer * 1024 + tc::mn_tile_index(j, kin);
-        hi[o] = h; lo[o] = tc::tf32_rna(w - h);
-    }
-    for (int i = threadIdx.x; i < 128; i += nt) sm[DhLayout::S_WO + i] = P[L::WO + i];
+    for (int i = threadIdx.x; i < 128; i += nt) { sm[DhLayout::S_WO + i] = P[L::WO + i]; sm[DhLayout::S_V + i] = PM[DecM::V + i]; }
     for (int i = threadIdx.x; i < 288; i += nt) sm[DhLayout::S_B + i] = P[L::B + i];
 }
 
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5;
     const int grp = tid >> 8, gt = tid & 255;
     const int r = gt & 127, hf = gt >> 7;
-    stage_weights_dh<CD>(sm, a.params + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR)));
+    stage_weights_dh<CD>(sm, a.params + (DEC == 0 ? OFF_LOW : (DEC == 1 ? OFF_HIGH : OFF_COLOR)), a.params + OFF_DEC_M + DEC * DecM::SIZE);
     if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
     if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_mbar_init(); }
     tc::fence_proxy_async();
@@ -182,8 +185,11 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                 pl::store16(r_dl0, 8 + pl::dl0_pos(i) * 32 + c0, dacc);
                 if (i == 3) pl::store16(r_dl1, c0, dacc);
             }
-            tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 32, dh);            // for d_c += dh_i * Wc_i
-            tc::tmem_store_split16(tl + T::T_A + 64, tl + T::T_A + 96, dacc);     // for dh_{i-1} = dacc_i * W_i
+            tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 32, dacc);          // the block's only operand
+            if (i != 4) {                                                         // the product accumulates (d_c adds up): dh starts from zero
+                const uint32_t zero[16] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                tc::tmem_st16(tl + T::T_DX, zero);
+            }
             tc::wait_st();
             tc::fence_before_sync();
             PROF(2)
@@ -191,10 +197,9 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             PROF(3)
             if (issuer_warp && tc::elect_one()) {
                 tc::fence_after_sync();
-                tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + (T::WC + i * 1024) * 4, wlo + (T::WC + i * 1024) * 4,
-                                  32, 32, 4096u, i != 4);
-                tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A + 64, tb + T::T_A + 96, whi + (T::WH + (i - 1) * 1024) * 4,
-                                  wlo + (T::WH + (i - 1) * 1024) * 4, 32, 32, 4096u, false);
+                // [d_c | dh_{i-1}] (+)= dacc_i * [M_i | W_i]
+                tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + (T::PAIR + (i - 1) * 2048) * 4,
+                                  wlo + (T::PAIR + (i - 1) * 2048) * 4, 32, 64, 4096u, i != 4);
                 tc::mma_commit(bar);
             }
             if (i == 3) {
@@ -209,17 +214,8 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             tc::wait_ld();
             PROF(6)
         }
-        // block 0: fc_c[0] path, then the embedding
+        // block 0: the embedding
         {
-            tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 32, dh);
-            tc::wait_st();
-            tc::fence_before_sync();
-            tc::named_bar_sync(3 + grp, 256);
-            if (issuer_warp && tc::elect_one()) {
-                tc::fence_after_sync();
-                tc::mma_3xtf32_bT(tb + T::T_DC, tb + T::T_A, tb + T::T_A + 32, whi + T::WC * 4, wlo + T::WC * 4, 32, 32, 4096u, true);
-                tc::mma_commit(bar);
-            }
             const uint32_t m0 = m_next >> c0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) dh[j] = ((m0 >> j) & 1u) ? dh[j] : 0.f;      // dacc_0
@@ -234,10 +230,6 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
                     pl::store8(r_dl0, 0, d8);
                 }
             }
-            PROF(7)
-            tc::mbar_wait(bar, parity); parity ^= 1;
-            tc::fence_after_sync();
-            PROF(8)
             // A = [dacc_0 | dacc_3]: hi in columns 0..63, lo in 64..127
             tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 64, dh);
             tc::tmem_store_split16(tl + T::T_A + 32, tl + T::T_A + 96, dacc3);
@@ -312,6 +304,13 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
         float d_c[16];
         tc::tmem_ld16(tl + T::T_DC, d_c);
         tc::wait_ld();
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {                                 // + dh_4 Wc_4 = dout (W_o Wc_4)
+            float vo[16];
+            tc::lds16(sm + T::S_V + o * 32 + c0, vo);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) d_c[j] = fmaf(vo[j], dout[o], d_c[j]);
+        }
         const bool want_coord = a.dp != nullptr;
         float gn[3] = {0.f, 0.f, 0.f};
         if (a.ggrid && !want_coord && !DFP_EXP(a, 2)) {

@@ -81,7 +81,16 @@ struct AttImg {
 constexpr float ATT_IMG_F16_SCALE = 64.f;          // the fp16 image holds 64 w: a weight of 0.1 keeps its "mid" part a normal fp16 number
 constexpr int OFF_ATT_IMG = (PACKED_FLOATS + 31) / 32 * 32;             // 128-byte aligned (bulk-copy source)
 constexpr int OFF_ATT_IMG_F16 = OFF_ATT_IMG + AttImg::BYTES / 4;
-constexpr int PACKED_TOTAL_FLOATS = OFF_ATT_IMG_F16 + AttImg::BYTES / 4;
+// Decoders, backward: the feature gradient d_c = sum_i dh_i Wc_i is linear in the ReLU-masked deltas (dh_{i-1} = dacc_i W_i),
+// so the delta-chain kernel multiplies every masked delta by [M_i | W_i] in ONE product, M_i = W_i Wc_{i-1} (restricted to
+// the decoder's own 32 grid features), and adds the dh_4 = dout W_o term as dout V, V = W_o Wc_4.  Per decoder:
+struct DecM {
+    static constexpr int M = 0;                            // [4][32 j][32 q]  M_1 .. M_4 (slot i - 1), row = delta index j
+    static constexpr int V = M + 4 * HID * HID;            // [4][32 q]        rows of V (1 or 4 used)
+    static constexpr int SIZE = V + 4 * HID;
+};
+constexpr int OFF_DEC_M = OFF_ATT_IMG_F16 + AttImg::BYTES / 4;          // low, high, colour
+constexpr int PACKED_TOTAL_FLOATS = OFF_DEC_M + 3 * DecM::SIZE;
 
 static_assert(DecOff<32>::SIZE % 4 == 0 && DecOff<64>::SIZE % 4 == 0 && AttOff::SIZE % 4 == 0, "float4 copies");
 
