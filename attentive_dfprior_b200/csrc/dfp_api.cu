@@ -131,8 +131,8 @@ static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with
     }
     w.sc_e = (float*)take(act ? pl::array_bytes(nsp, pl::F_EX) : 0);
     for (int d = 0; d < 3; ++d) w.fcc[d] = (float*)take(act ? (size_t)(65 * 144) * 4 : 0);      // contiguous: one memset
-    w.sc_darg = (float*)take(act ? pl::array_bytes(nsp, pl::F_DL0) : 0);
-    w.sc_dl1 = (float*)take(act ? pl::array_bytes(nsp, pl::F_DL1) : 0);
+    w.sc_darg = (float*)take(act ? pl::array_bytes(nsp, pl::F_DLX) + 4096 : 0);      // DLX (+ slack for the last group's over-read)
+    w.sc_dl1 = nullptr;
     w.dec_tileflag = (int*)take(act ? (size_t)(nsp / 128) * 4 : 0);
     // fusion MLP (tensor-core path): activations, ReLU masks, softmax outputs kept by the forward and the delta planes of
     // the backward, per 128-sample tile of the band list (which can be as long as the sample list)

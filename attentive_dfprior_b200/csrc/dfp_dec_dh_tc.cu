@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
         const bool valid = i_raw < n;
         const int64_t ia = valid ? i_raw : n - 1;                    // list position: index of saved activations and scratch
         const int64_t s = dec_sample(a, ia);                         // sample id: index of points, dout, dp
-        const pl::Row r_dl0 = pl::row_of(a.sc_darg, pl::F_DL0, i_raw), r_dl1 = pl::row_of(a.sc_dl1, pl::F_DL1, i_raw),
-                      r_ex = pl::row_of(a.sc_e, pl::F_EX, i_raw);
+        const pl::Row r_dx = pl::row_of(a.sc_darg, pl::F_DLX, i_raw), r_ex = pl::row_of(a.sc_e, pl::F_EX, i_raw);
+        constexpr int DL1 = pl::DL1_AT;                              // [dacc3 | dacc0 | darg96] starts at dacc3's place in DLX
         float dout[NOUT];
         if (NOUT == 1) dout[0] = valid ? a.dout[s] : 0.f;
         else {
@@ -182,8 +182,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) dacc[j] = ((m >> j) & 1u) ? dh[j] : 0.f;
             if (planes) {                                     // operands of kernel 2 (rows past the end carry zero deltas)
-                pl::store16(r_dl0, 8 + pl::dl0_pos(i) * 32 + c0, dacc);
-                if (i == 3) pl::store16(r_dl1, c0, dacc);
+                pl::store16(r_dx, 8 + pl::dl0_pos(i) * 32 + c0, dacc);           // dacc3 lands at DL1 + 0: stored once for both passes
             }
             tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 32, dacc);          // the block's only operand
             if (i != 4) {                                                         // the product accumulates (d_c adds up): dh starts from zero
@@ -220,14 +219,14 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) dh[j] = ((m0 >> j) & 1u) ? dh[j] : 0.f;      // dacc_0
             if (planes) {
-                pl::store16(r_dl1, 32 + c0, dh);
+                pl::store16(r_dx, DL1 + 32 + c0, dh);
                 if (hf == 0) {                                // upstream gradient, padded to 8 columns
                     float d8[8];
 #pragma unroll
                     for (int o = 0; o < 8; ++o) d8[o] = 0.f;
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o) d8[o] = dout[o];
-                    pl::store8(r_dl0, 0, d8);
+                    pl::store8(r_dx, 0, d8);
                 }
             }
             // A = [dacc_0 | dacc_3]: hi in columns 0..63, lo in 64..127
@@ -293,7 +292,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             }
             if (planes) {
                 pl::store16(r_ex, ch * 32 + c0, sn);
-                pl::store16(r_dl1, 64 + ch * 32 + c0, da);
+                pl::store16(r_dx, DL1 + 64 + ch * 32 + c0, da);
             }
         }
         if (planes && hf == 0) {                              // the point itself (A operand of embedder._B's gradient)

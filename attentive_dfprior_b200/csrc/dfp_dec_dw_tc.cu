@@ -116,7 +116,6 @@ __device__ __forceinline__ void dw_body(const DecArgs& a, const int cta, const i
                 const unsigned char* gCX = reinterpret_cast<const unsigned char*>(a.act_c);
                 const unsigned char* gDL0 = reinterpret_cast<const unsigned char*>(a.sc_darg);
                 const unsigned char* gEX = reinterpret_cast<const unsigned char*>(a.sc_e);
-                const unsigned char* gDL1 = reinterpret_cast<const unsigned char*>(a.sc_dl1);
                 for (uint32_t q = 0; q < total; ++q) {
                     const int st = q % NST;
                     if (q >= NST) tc::mbar_wait(&empty_bar[st], ((q / NST) - 1) & 1);     // MMAs of the previous use are done
@@ -129,8 +128,17 @@ __device__ __forceinline__ void dw_body(const DecArgs& a, const int cta, const i
                             tc::bulk_copy_g2s(dst + off + plane * dw::piece(F), g + (tile * 2 + plane) * (int64_t)(256 * F) + quarter * dw::piece(F),
                                               dw::piece(F), &full_bar[st]);
                     };
-                    if (PASS == 0) { copy(gH, pl::F_H, O_H); copy(gCX, FCX, O_CX); copy(gDL0, pl::F_DL0, O_DL0); }
-                    else { copy(gEX, pl::F_EX, O_EX); copy(gDL1, pl::F_DL1, O_DL1); }
+                    // feature range [f0, f0 + F) of the stored DLX array: per 8-sample group the range is contiguous
+                    // (16 F bytes), the groups are 16 F_DLX apart; in shared memory the groups are packed (stride 16 F)
+                    auto copy_range = [&](const unsigned char* g, int f0, int F, uint32_t off) {
+                        for (int plane = 0; plane < 2; ++plane)
+                            for (int grp8 = 0; grp8 < 4; ++grp8)
+                                tc::bulk_copy_g2s(dst + off + plane * dw::piece(F) + grp8 * 16u * F,
+                                                  g + (tile * 2 + plane) * (int64_t)(256 * pl::F_DLX) + (quarter * 4 + grp8) * (16 * pl::F_DLX) + f0 * 16,
+                                                  16u * F, &full_bar[st]);
+                    };
+                    if (PASS == 0) { copy(gH, pl::F_H, O_H); copy(gCX, FCX, O_CX); copy_range(gDL0, 0, pl::F_DL0, O_DL0); }
+                    else { copy(gEX, pl::F_EX, O_EX); copy_range(gDL0, pl::DL1_AT, pl::F_DL1, O_DL1); }
                 }
             }
         } else if (warp == 1) {

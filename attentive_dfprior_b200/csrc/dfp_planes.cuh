@@ -25,10 +25,13 @@ namespace pl {
 // CX  : [c (CD) | ones8]                     gathered grid features, then a constant 1
 // (the gradients dh_i of the blocks' outputs, which feed fc_c.i, are NOT stored: dh_{i-1} = dacc_i W_i is linear in the
 //  masked delta, so  c^T dh_{i-1} = (c^T dacc_i) W_i  is formed from the accumulated CX^T DL0 product afterwards)
-// DL0 : [dout8 | dacc4 | dacc2 | dacc1 | dacc3]   upstream gradient, then ReLU-masked deltas in H's block order
-// DL1 : [dacc3 | dacc0 | darg96]             deltas that meet the embedding, then d(embedding argument)
+// DLX : [dout8 | dacc4 | dacc2 | dacc1 | dacc3 | dacc0 | darg96]   ONE array of which the weight-gradient kernel reads two
+//       overlapping feature ranges, so that dacc3 (needed by both) is stored once:
+//   DL0 = DLX[0:136)   : upstream gradient, then ReLU-masked deltas in H's block order
+//   DL1 = DLX[104:264) : [dacc3 | dacc0 | darg96], deltas that meet the embedding, then d(embedding argument)
 // EX  : [e96 (column 93 == 1) | p0 p1 p2 0*5] sin(embedding argument) and the point (for embedder._B)
 constexpr int F_H = 168, F_DL0 = 136, F_DL1 = 160, F_EX = 104;
+constexpr int F_DLX = 264, DL1_AT = 104;          // features of the stored array; first feature of the DL1 range
 __host__ __device__ constexpr int f_cx(int CD) { return CD + 8; }
 // position (32-feature block) of h_i inside H, and of dacc_i inside DL0 (after the 8 dout features)
 __host__ __device__ constexpr int h_pos(int i) { return i == 0 ? 2 : i == 1 ? 1 : i == 2 ? 3 : i == 3 ? 0 : 4; }
