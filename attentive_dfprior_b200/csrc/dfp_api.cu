@@ -123,9 +123,9 @@ static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with
     for (int d = 0; d < 3; ++d) {
         const bool used = act && (d == 0 || (d == 1 && stage >= DFP_STAGE_HIGH) || (d == 2 && stage == DFP_STAGE_COLOR));
         const bool wg = used && !dec_frozen(flags, d);      // weight-gradient operands only for decoders that are trained
-        w.act_h[d] = (float*)take(wg ? pl::array_bytes(nsp, pl::F_H) : 0);
+        w.act_h[d] = (float*)take(wg ? pl::array_bytes(nsp, pl::F_H_ST) : 0);
         w.act_m[d] = (uint32_t*)take(used ? nsp * 5 * 4 : 0);
-        w.act_c[d] = (float*)take(wg ? pl::array_bytes(nsp, pl::f_cx(d == 1 ? 64 : 32)) : 0);
+        w.act_c[d] = (float*)take(wg ? pl::array_bytes(nsp, d == 1 ? 64 : 32) : 0);
         if (!wg) { w.act_h[d] = nullptr; w.act_c[d] = nullptr; }
         if (!used) w.act_m[d] = nullptr;
     }

@@ -32,8 +32,11 @@ constexpr int MAX_TILES = 1024;               // active tiles of one CTA
 constexpr int THREADS = 192;                  // warp 0: tile list + producer, warp 1: MMA issuer, warps 2..5: flush
 constexpr int FCC_N = 144;                    // row length of the [c | 1]^T [dout8 | dacc4 | dacc2 | dacc1 | dacc3] scratch (136 used)
 __host__ __device__ constexpr uint32_t piece(int F) { return 64u * (uint32_t)F; }          // one plane, 32 samples
-template <int CD, int PASS> __host__ __device__ constexpr uint32_t stage_bytes() {
+template <int CD, int PASS> __host__ __device__ constexpr uint32_t stage_bytes() {          // shared-memory size of a stage
     return PASS == 0 ? 2u * (piece(pl::F_H) + piece(pl::f_cx(CD)) + piece(pl::F_DL0)) : 2u * (piece(pl::F_EX) + piece(pl::F_DL1));
+}
+template <int CD, int PASS> __host__ __device__ constexpr uint32_t copied_bytes() {         // bytes the bulk copies bring per stage (no constant chunks)
+    return PASS == 0 ? 2u * (piece(pl::F_H_ST) + piece(CD) + piece(pl::F_DL0)) : 2u * (piece(pl::F_EX) + piece(pl::F_DL1));
 }
 template <int CD, int PASS> __host__ __device__ constexpr int nst() { return RING_BYTES / (int)stage_bytes<CD, PASS>(); }
 }  // namespace dw
@@ -77,6 +80,17 @@ __device__ __forceinline__ void dw_body(const DecArgs& a, const int cta, const i
 
     // the stage ring must never hold NaN bit patterns where the over-long feature ranges read: clear it once
     for (uint32_t i = tid; i < NST * STAGE / 16; i += dw::THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (PASS == 0) {
+        // the constant-one chunks of H and CX ([1 0 0 0 0 0 0 0] per sample in the hi plane, zero in the mid plane) live
+        // only here: the copies below never touch them
+        __syncthreads();
+        for (uint32_t i = tid; i < (uint32_t)NST * 32u; i += dw::THREADS) {
+            const uint32_t st = i >> 5, g8 = (i >> 3) & 3, k = i & 7;
+            unsigned char* s0 = sm + st * STAGE;
+            *reinterpret_cast<uint4*>(s0 + O_H + g8 * 16u * pl::F_H + (pl::F_H_ST / 8) * 128u + k * 16u) = make_uint4(0x00003f80u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(s0 + O_CX + g8 * 16u * FCX + (CD / 8) * 128u + k * 16u) = make_uint4(0x00003f80u, 0u, 0u, 0u);
+        }
+    }
     if (tid == 0) n_active_s = 0;
     __syncthreads();
     // the CTA's tiles that carry any upstream gradient (kernel 1 wrote its planes only for those, and left one flag per
@@ -122,23 +136,29 @@ __device__ __forceinline__ void dw_body(const DecArgs& a, const int cta, const i
                     const int64_t tile = tile_list[q >> 2];
                     const uint32_t quarter = q & 3;
                     const uint32_t dst = sm_base + st * STAGE;
-                    tc::mbar_arrive_expect_tx(&full_bar[st], STAGE);
+                    tc::mbar_arrive_expect_tx(&full_bar[st], dw::copied_bytes<CD, PASS>());
                     auto copy = [&](const unsigned char* g, int F, uint32_t off) {
                         for (int plane = 0; plane < 2; ++plane)
                             tc::bulk_copy_g2s(dst + off + plane * dw::piece(F), g + (tile * 2 + plane) * (int64_t)(256 * F) + quarter * dw::piece(F),
                                               dw::piece(F), &full_bar[st]);
                     };
-                    // feature range [f0, f0 + F) of the stored DLX array: per 8-sample group the range is contiguous
-                    // (16 F bytes), the groups are 16 F_DLX apart; in shared memory the groups are packed (stride 16 F)
-                    auto copy_range = [&](const unsigned char* g, int f0, int F, uint32_t off) {
+                    // feature range [f0, f0 + F) of an array stored with FS features per sample: per 8-sample group the range
+                    // is contiguous (16 F bytes), the groups are 16 FS apart; in shared memory the groups are FSM features apart
+                    auto copy_range = [&](const unsigned char* g, int FS, int f0, int F, uint32_t off, int FSM) {
                         for (int plane = 0; plane < 2; ++plane)
                             for (int grp8 = 0; grp8 < 4; ++grp8)
-                                tc::bulk_copy_g2s(dst + off + plane * dw::piece(F) + grp8 * 16u * F,
-                                                  g + (tile * 2 + plane) * (int64_t)(256 * pl::F_DLX) + (quarter * 4 + grp8) * (16 * pl::F_DLX) + f0 * 16,
+                                tc::bulk_copy_g2s(dst + off + plane * dw::piece(FSM) + grp8 * 16u * FSM,
+                                                  g + (tile * 2 + plane) * (int64_t)(256 * FS) + (quarter * 4 + grp8) * (16 * FS) + f0 * 16,
                                                   16u * F, &full_bar[st]);
                     };
-                    if (PASS == 0) { copy(gH, pl::F_H, O_H); copy(gCX, FCX, O_CX); copy_range(gDL0, 0, pl::F_DL0, O_DL0); }
-                    else { copy(gEX, pl::F_EX, O_EX); copy_range(gDL0, pl::DL1_AT, pl::F_DL1, O_DL1); }
+                    if (PASS == 0) {
+                        copy_range(gH, pl::F_H_ST, 0, pl::F_H_ST, O_H, pl::F_H);              // the stage keeps its constant chunk
+                        copy_range(gCX, CD, 0, CD, O_CX, FCX);
+                        copy_range(gDL0, pl::F_DLX, 0, pl::F_DL0, O_DL0, pl::F_DL0);
+                    } else {
+                        copy(gEX, pl::F_EX, O_EX);
+                        copy_range(gDL0, pl::F_DLX, pl::DL1_AT, pl::F_DL1, O_DL1, pl::F_DL1);
+                    }
                 }
             }
         } else if (warp == 1) {

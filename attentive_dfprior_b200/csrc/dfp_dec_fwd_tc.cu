@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
         const bool fast = embed_fast_ok(pf, bmax);
         pl::Row r_c, r_h;
         const bool save_pl = a.act_c && !DFP_EXP(a, 16);
-        if (a.act_c) { r_c = pl::row_of(a.act_c, pl::f_cx(CD), i_raw); r_h = pl::row_of(a.act_h, pl::F_H, i_raw); }
+        if (a.act_c) { r_c = pl::row_of(a.act_c, CD, i_raw); r_h = pl::row_of(a.act_h, pl::F_H_ST, i_raw); }
         {   // trilinear features -> A_C.  Cooperative gather: a thread fetching its own 16 channels touches 32 different
             // lines per warp instruction (one 16-byte piece per lane); instead eight lanes fetch one corner's whole
             // 128-byte line and the interpolated features go to their owners through shared memory.
@@ -201,7 +201,6 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             // the end repeat the last sample, their deltas are zero in the backward)
             if (save_pl) {
                 pl::store16(r_c, 16 * hf, c);
-                if (hf == 0) pl::store_ones8(r_c, CD);
             }
             if (DEC == 1) {
 #pragma unroll
@@ -277,7 +276,6 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
             if (a.act_m) {                                            // kept for the backward (DFP_FLAG_SAVE_ACT)
                 if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, 0, 5))[hf] = (uint16_t)m;
                 if (save_pl) pl::store16(r_h, pl::h_pos(0) * 32 + 16 * hf, h);
-                if (hf == 0 && save_pl) pl::store_ones8(r_h, 160);
             }
         }
         PROF(11)

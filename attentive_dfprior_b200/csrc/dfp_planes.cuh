@@ -23,6 +23,8 @@ namespace pl {
 // ---- the arrays of one decoder (features per sample) --------------------------------------------------------
 // H   : [h3 | h1 | h0 | h2 | h4 | ones8]     inputs of pts_linears.4/.2/.1/.3 and of output_linear, then a constant 1
 // CX  : [c (CD) | ones8]                     gathered grid features, then a constant 1
+//       (the constant chunks [1 0 0 0 0 0 0 0] exist only in the weight-gradient kernel's shared-memory stages, written
+//        once per CTA: global memory holds F_H_ST = 160 and CD features per sample, copied group by group)
 // (the gradients dh_i of the blocks' outputs, which feed fc_c.i, are NOT stored: dh_{i-1} = dacc_i W_i is linear in the
 //  masked delta, so  c^T dh_{i-1} = (c^T dacc_i) W_i  is formed from the accumulated CX^T DL0 product afterwards)
 // DLX : [dout8 | dacc4 | dacc2 | dacc1 | dacc3 | dacc0 | darg96]   ONE array of which the weight-gradient kernel reads two
@@ -31,7 +33,8 @@ namespace pl {
 //   DL1 = DLX[104:264) : [dacc3 | dacc0 | darg96], deltas that meet the embedding, then d(embedding argument)
 // EX  : [e96 (column 93 == 1) | p0 p1 p2 0*5] sin(embedding argument) and the point (for embedder._B)
 constexpr int F_H = 168, F_DL0 = 136, F_DL1 = 160, F_EX = 104;
-constexpr int F_DLX = 264, DL1_AT = 104;          // features of the stored array; first feature of the DL1 range
+constexpr int F_DLX = 264, DL1_AT = 104;
+constexpr int F_H_ST = 160;                       // features of H kept in global memory (H without its constant chunk)          // features of the stored array; first feature of the DL1 range
 __host__ __device__ constexpr int f_cx(int CD) { return CD + 8; }
 // position (32-feature block) of h_i inside H, and of dacc_i inside DL0 (after the 8 dout features)
 __host__ __device__ constexpr int h_pos(int i) { return i == 0 ? 2 : i == 1 ? 1 : i == 2 ? 3 : i == 3 ? 0 : 4; }
