@@ -104,6 +104,8 @@ int num_sms() {
 
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+// calls with at most this many samples run their decoders in one launch per direction (148 SMs x 2 tiles x 3 rounds)
+constexpr int64_t MERGED_MAX_SAMPLES = 148 * 2 * 128 * 3;
 
 static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with_z, int stage = DFP_STAGE_COLOR, int flags = 0) {
     size_t off = 0;
@@ -129,11 +131,11 @@ static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with
         if (!wg) { w.act_h[d] = nullptr; w.act_c[d] = nullptr; }
         if (!used) w.act_m[d] = nullptr;
     }
-    w.sc_e = (float*)take(act ? pl::array_bytes(nsp, pl::F_EX) : 0);
+    const int nscr = (act && ns <= MERGED_MAX_SAMPLES) ? 3 : 1;       // merged launches: the decoders' delta chains run side by side
+    for (int d = 0; d < 3; ++d) w.sc_e[d] = d < nscr ? (float*)take(act ? pl::array_bytes(nsp, pl::F_EX) : 0) : w.sc_e[0];
     for (int d = 0; d < 3; ++d) w.fcc[d] = (float*)take(act ? (size_t)(65 * 144) * 4 : 0);      // contiguous: one memset
-    w.sc_darg = (float*)take(act ? pl::array_bytes(nsp, pl::F_DLX) + 4096 : 0);      // DLX (+ slack for the last group's over-read)
-    w.sc_dl1 = nullptr;
-    w.dec_tileflag = (int*)take(act ? (size_t)(nsp / 128) * 4 : 0);
+    for (int d = 0; d < 3; ++d) w.sc_darg[d] = d < nscr ? (float*)take(act ? pl::array_bytes(nsp, pl::F_DLX) + 4096 : 0) : w.sc_darg[0];   // DLX (+ slack for the last group's over-read)
+    for (int d = 0; d < 3; ++d) w.dec_tileflag[d] = d < nscr ? (int*)take(act ? (size_t)(nsp / 128) * 4 : 0) : w.dec_tileflag[0];
     // fusion MLP (tensor-core path): activations, ReLU masks, softmax outputs kept by the forward and the delta planes of
     // the backward, per 128-sample tile of the band list (which can be as long as the sample list)
     const bool att = act && stage >= DFP_STAGE_HIGH;
@@ -659,6 +661,22 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
     auto set_act = [&](int d) {
         da.act_h = save ? w.act_h[d] : nullptr; da.act_m = save ? w.act_m[d] : nullptr; da.act_c = save ? w.act_c[d] : nullptr;
     };
+    // small batches: one launch for all decoders of the stage (dfp_device.cuh, DecArgs3)
+    if (tcp && n <= MERGED_MAX_SAMPLES) {
+        DecArgs3 a3;
+        memset(&a3, 0, sizeof(a3));
+        if (hi) {
+            set_act(1);
+            da.grid = sc->high; da.grid_low = sc->low; da.out = w.high; da.list = w.band_list; da.count = w.band_count;
+            a3.d[0] = da; a3.on[0] = 1;
+            da.list = nullptr; da.count = nullptr;
+        }
+        if (stage == DFP_STAGE_COLOR) { set_act(2); da.grid = sc->color; da.out = w.rgb; a3.d[1] = da; a3.on[1] = 1; }
+        set_act(0);
+        da.grid = sc->low; da.out = w.low;
+        a3.d[2] = da; a3.on[2] = 1;
+        if ((rc = launch_decoder_fwd_tc_all<MODE>(a3, st))) return rc;
+    } else {
     if (hi) {
         set_act(1);
         da.grid = sc->high; da.grid_low = sc->low; da.out = w.high;
@@ -674,6 +692,7 @@ static int eval_samples_fwd(const DfpScene* sc, const float* params, const Point
     set_act(0);
     da.grid = sc->low; da.out = w.low;
     if ((rc = tcp ? launch_decoder_fwd_tc<0, MODE>(da, st) : launch_decoder_fwd<0, MODE>(da, st))) return rc;
+    }
     if (hi) {
         AttArgs aa;
         memset(&aa, 0, sizeof(aa));
@@ -716,13 +735,48 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
     da.gparams = g->params_packed; da.dp = want_dp ? w.dp : nullptr;
     // tensor-core backward (needs the activations saved by the tensor-core forward): K1 = delta chain, K2 = weight grads
     const bool tcb = flags_tc(flags) && (flags & DFP_FLAG_SAVE_ACT) && w.act_m[0] != nullptr;
-    da.sc_e = w.sc_e; da.sc_darg = w.sc_darg; da.sc_dl1 = w.sc_dl1; da.tileflag = w.dec_tileflag;
     if (tcb && da.gparams) DFP_CUDA(cudaMemsetAsync(w.fcc[0], 0, (size_t)((char*)w.fcc[2] - (char*)w.fcc[0]) + 65 * 144 * 4, st));
+    auto set_dec = [&](int dec) {
+        da.act_h = w.act_h[dec]; da.act_m = w.act_m[dec]; da.act_c = w.act_c[dec]; da.fcc = w.fcc[dec];
+        da.sc_e = w.sc_e[dec]; da.sc_darg = w.sc_darg[dec]; da.tileflag = w.dec_tileflag[dec];
+        da.list = (dec == 1) ? w.band_list : nullptr; da.count = (dec == 1) ? w.band_count : nullptr;   // as in the forward
+        if (dec == 1) { da.grid = sc->high; da.grid_low = sc->low; da.dout = w.d_high; da.ggrid = g->grid_high; }
+        else if (dec == 2) { da.grid = sc->color; da.dout = w.d_rgb; da.ggrid = g->grid_color; }
+        else { da.grid = sc->low; da.dout = w.d_low; da.ggrid = g->grid_low; }
+    };
+    // small batches (no all-reduce events to record in between): the decoders' delta chains in one launch, then their
+    // weight-gradient kernels in one launch
+    if (tcb && n <= MERGED_MAX_SAMPLES && !g->ev_high && !g->ev_color) {
+        DecArgs3 a3;
+        memset(&a3, 0, sizeof(a3));
+        float* const gp = da.gparams;
+        const int decs[3] = {1, 2, 0};
+        bool any_w = false;
+        for (int i = 0; i < 3; ++i) {
+            const int dec = decs[i];
+            if ((dec == 1 && !hi) || (dec == 2 && stage != DFP_STAGE_COLOR)) continue;
+            set_dec(dec);
+            da.gparams = dec_frozen(flags, dec) ? nullptr : gp;
+            a3.d[i] = da; a3.on[i] = 1;
+            any_w = any_w || da.gparams != nullptr;
+        }
+        da.gparams = gp;
+        if ((rc = launch_decoder_dh_tc_all<MODE>(a3, st))) return rc;
+        if (any_w) {
+            for (int i = 0; i < 3; ++i) a3.on[i] = a3.on[i] && a3.d[i].gparams != nullptr;
+            if ((rc = launch_decoder_dw_tc_all(a3, st))) return rc;
+        }
+        return DFP_OK;
+    }
     auto run = [&](auto dec_tag) -> int {
         constexpr int DEC = decltype(dec_tag)::value;
-        if (!tcb) return launch_decoder_bwd<DEC, MODE>(da, st);
-        da.act_h = w.act_h[DEC]; da.act_m = w.act_m[DEC]; da.act_c = w.act_c[DEC]; da.fcc = w.fcc[DEC];
-        da.list = (DEC == 1) ? w.band_list : nullptr; da.count = (DEC == 1) ? w.band_count : nullptr;   // as in the forward
+        if (!tcb) {
+            if (DEC == 1) { da.grid = sc->high; da.grid_low = sc->low; da.dout = w.d_high; da.ggrid = g->grid_high; }
+            else if (DEC == 2) { da.grid = sc->color; da.dout = w.d_rgb; da.ggrid = g->grid_color; }
+            else { da.grid = sc->low; da.dout = w.d_low; da.ggrid = g->grid_low; }
+            return launch_decoder_bwd<DEC, MODE>(da, st);
+        }
+        set_dec(DEC);
         float* const gp = da.gparams;
         if (dec_frozen(flags, DEC)) da.gparams = nullptr;        // K1 then writes no operands for K2, and K2 does not run
         int r = launch_decoder_dh_tc<DEC, MODE>(da, st);
@@ -730,17 +784,10 @@ static int eval_samples_bwd(const DfpScene* sc, const float* params, const Point
         da.gparams = gp;
         return r;
     };
-    if (hi) {
-        da.grid = sc->high; da.grid_low = sc->low; da.dout = w.d_high; da.ggrid = g->grid_high;
-        if ((rc = run(std::integral_constant<int, 1>{}))) return rc;
-    }
+    if (hi && (rc = run(std::integral_constant<int, 1>{}))) return rc;
     if (g->ev_high) DFP_CUDA(cudaEventRecord((cudaEvent_t)g->ev_high, st));        // grid_high's gradient is final
-    if (stage == DFP_STAGE_COLOR) {
-        da.grid = sc->color; da.dout = w.d_rgb; da.ggrid = g->grid_color;
-        if ((rc = run(std::integral_constant<int, 2>{}))) return rc;
-    }
+    if (stage == DFP_STAGE_COLOR && (rc = run(std::integral_constant<int, 2>{}))) return rc;
     if (g->ev_color) DFP_CUDA(cudaEventRecord((cudaEvent_t)g->ev_color, st));      // grid_color's gradient is final
-    da.grid = sc->low; da.dout = w.d_low; da.ggrid = g->grid_low;
     if ((rc = run(std::integral_constant<int, 0>{}))) return rc;
     return DFP_OK;
 }

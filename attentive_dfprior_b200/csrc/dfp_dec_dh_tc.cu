@@ -92,12 +92,14 @@ __device__ __forceinline__ bool group_any(bool v, int id) {
 
 // Two threads per sample (as in the forward, dfp_dec_fwd_tc.cu): thread (row r, half hf) owns columns 16*hf..16*hf+15
 // of every 32-wide delta block of sample r.
+// `cta` of `nctas` CTAs work on this decoder (the whole grid, or a share of it in the merged kernel).
 template <int DEC, int MODE>
-__global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
+__device__ __forceinline__ void decoder_dh_tc_body(const DecArgs& a, const int cta, const int nctas) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
     constexpr int NOUT = (DEC == 2) ? 4 : 1;
     using PT = typename PtT<MODE>::T;
     using T = DhLayout;
+    if ((int64_t)cta * 256 >= dec_items(a)) return;                      // no tile for this CTA: skip the staging too
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
     __shared__ __align__(8) uint64_t bars[2];
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
     const float bmax = embed_bmax(sm + T::S_B);
     const int c0 = 16 * hf;
 
-    for (int64_t tile = (int64_t)blockIdx.x * 2 + grp; tile < tiles; tile += (int64_t)gridDim.x * 2) {
+    for (int64_t tile = (int64_t)cta * 2 + grp; tile < tiles; tile += (int64_t)nctas * 2) {
         PROF_DECL
         const int64_t i_raw = tile * 128 + r;
         const bool valid = i_raw < n;
@@ -372,9 +374,10 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
             if (hf == 0 && valid && any) {
                 gn[0] += part[grp][0][r]; gn[1] += part[grp][1][r]; gn[2] += part[grp][2][r];
                 gp0 += part[grp][3][r]; gp1 += part[grp][4][r]; gp2 += part[grp][5][r];
-                a.dp[3 * s + 0] += gn[0] * (float)(2.0 / (a.bound.b[0][1] - a.bound.b[0][0])) + gp0;
-                a.dp[3 * s + 1] += gn[1] * (float)(2.0 / (a.bound.b[1][1] - a.bound.b[1][0])) + gp1;
-                a.dp[3 * s + 2] += gn[2] * (float)(2.0 / (a.bound.b[2][1] - a.bound.b[2][0])) + gp2;
+                // reductions: in the merged launch the decoders' chains add to the same d(point) concurrently
+                atomicAdd(a.dp + 3 * s + 0, gn[0] * (float)(2.0 / (a.bound.b[0][1] - a.bound.b[0][0])) + gp0);
+                atomicAdd(a.dp + 3 * s + 1, gn[1] * (float)(2.0 / (a.bound.b[1][1] - a.bound.b[1][0])) + gp1);
+                atomicAdd(a.dp + 3 * s + 2, gn[2] * (float)(2.0 / (a.bound.b[2][1] - a.bound.b[2][0])) + gp2);
             }
         }
     }
@@ -382,6 +385,41 @@ __global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
+
+template <int DEC, int MODE>
+__global__ void __launch_bounds__(512, 1) k_decoder_dh_tc(const DecArgs a) {
+    decoder_dh_tc_body<DEC, MODE>(a, blockIdx.x, gridDim.x);
+}
+
+__device__ __forceinline__ int64_t dh_iterations(const DecArgs& a, int on) { return on ? (dec_items(a) + 255) / 256 : 0; }
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) k_decoder_dh_tc_all(const DecArgs3 A) {
+    const int64_t it[3] = {dh_iterations(A.d[0], A.on[0]), dh_iterations(A.d[1], A.on[1]), dh_iterations(A.d[2], A.on[2])};
+    int first, count;
+    split_ctas(it, gridDim.x, 0, first, count);
+    if ((int)blockIdx.x < first + count) { decoder_dh_tc_body<1, MODE>(A.d[0], blockIdx.x - first, count); return; }
+    split_ctas(it, gridDim.x, 1, first, count);
+    if ((int)blockIdx.x < first + count) { decoder_dh_tc_body<2, MODE>(A.d[1], blockIdx.x - first, count); return; }
+    split_ctas(it, gridDim.x, 2, first, count);
+    if ((int)blockIdx.x < first + count) decoder_dh_tc_body<0, MODE>(A.d[2], blockIdx.x - first, count);
+}
+
+template <int MODE>
+int launch_decoder_dh_tc_all(const DecArgs3& a, cudaStream_t st) {
+    const size_t smem = (DhLayout::FLOATS + 2 * 128 * 36 + 2 * 1024 * 2) * sizeof(float) + 1024;
+    int rc = set_smem(k_decoder_dh_tc_all<MODE>, smem);
+    if (rc) return rc;
+    int64_t its = 0;                                         // upper bound (the high decoder's list may be shorter)
+    for (int d = 0; d < 3; ++d) if (a.on[d]) its += (a.d[d].n + 255) / 256;
+    const int blocks = (int)(its < (int64_t)num_sms() ? (its < 1 ? 1 : its) : num_sms());
+    DFP_TIMED("k_decoder_dh_tc_all", st, k_decoder_dh_tc_all<MODE><<<blocks, 512, smem, st>>>(a));
+    DFP_LAUNCH_CHECK("k_decoder_dh_tc_all");
+    return DFP_OK;
+}
+template int launch_decoder_dh_tc_all<0>(const DecArgs3&, cudaStream_t);
+template int launch_decoder_dh_tc_all<1>(const DecArgs3&, cudaStream_t);
+template int launch_decoder_dh_tc_all<2>(const DecArgs3&, cudaStream_t);
 
 template <int DEC, int MODE>
 int launch_decoder_dh_tc(const DecArgs& a, cudaStream_t st) {

@@ -77,6 +77,7 @@ __device__ __forceinline__ void dw_body(const DecArgs& a, const int cta, const i
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n = dec_items(a);
     const int64_t tiles = (n + 127) / 128;
+    if (cta >= tiles) return;                                        // nothing for this CTA (short band list, small batch)
 
     // the stage ring must never hold NaN bit patterns where the over-long feature ranges read: clear it once
     for (uint32_t i = tid; i < NST * STAGE / 16; i += dw::THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -313,6 +314,93 @@ __global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc(const DecArgs 
     __shared__ __align__(8) DwShared S;
     if ((int)blockIdx.x < n0) dw_body<DEC, 0>(a, blockIdx.x, n0, S);
     else dw_body<DEC, 1>(a, blockIdx.x - n0, gridDim.x - n0, S);
+}
+
+// fc_c finish of up to three decoders in one launch (grid: 5 layers x 65 rows x 3 decoders, order high / colour / low)
+struct FccArgs3 { const float* fcc[3]; const float* params; float* gparams[3]; int on[3]; };
+template <int CD, int NOUT>
+__device__ __forceinline__ void fcc_finish_body(const float* __restrict__ fcc, const float* __restrict__ P, float* __restrict__ g, int layer, int row, int k) {
+    using L = DecOff<CD>;
+    if (row > CD) return;
+    const float* G = fcc + row * dw::FCC_N;
+    float acc = 0.f;
+    if (layer == 4) {
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) acc = fmaf(G[o], P[L::WO + o * 32 + k], acc);
+    } else {
+        const int i = layer + 1;
+        const int col0 = i == 4 ? 8 : i == 2 ? 40 : i == 1 ? 72 : 104;
+        const float* W = P + L::WH + (i - 1) * 1024 + k * 32;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) acc = fmaf(G[col0 + j], W[j], acc);
+    }
+    if (row < CD) g[L::WC + layer * CD * 32 + row * 32 + k] += acc;
+    else g[L::BC + layer * 32 + k] += acc;
+}
+__global__ void k_fcc_finish_all(const FccArgs3 a) {
+    const int d = blockIdx.z;
+    if (!a.on[d]) return;
+    if (d == 0) fcc_finish_body<64, 1>(a.fcc[0], a.params + OFF_HIGH, a.gparams[0] + OFF_HIGH, blockIdx.x, blockIdx.y, threadIdx.x);
+    else if (d == 1) fcc_finish_body<32, 4>(a.fcc[1], a.params + OFF_COLOR, a.gparams[1] + OFF_COLOR, blockIdx.x, blockIdx.y, threadIdx.x);
+    else fcc_finish_body<32, 1>(a.fcc[2], a.params + OFF_LOW, a.gparams[2] + OFF_LOW, blockIdx.x, blockIdx.y, threadIdx.x);
+}
+
+// Both passes of up to three decoders in one launch: bounds[i] = first CTA of (decoder i/2, pass i%2), order high / colour / low
+struct DwSplit { int first[7]; };
+__global__ void __launch_bounds__(dw::THREADS, 1) k_decoder_dw_tc_all(const DecArgs3 A, const DwSplit sp) {
+    __shared__ __align__(8) DwShared S;
+    const int b = blockIdx.x;
+    if (b < sp.first[1]) dw_body<1, 0>(A.d[0], b - sp.first[0], sp.first[1] - sp.first[0], S);
+    else if (b < sp.first[2]) dw_body<1, 1>(A.d[0], b - sp.first[1], sp.first[2] - sp.first[1], S);
+    else if (b < sp.first[3]) dw_body<2, 0>(A.d[1], b - sp.first[2], sp.first[3] - sp.first[2], S);
+    else if (b < sp.first[4]) dw_body<2, 1>(A.d[1], b - sp.first[3], sp.first[4] - sp.first[3], S);
+    else if (b < sp.first[5]) dw_body<0, 0>(A.d[2], b - sp.first[4], sp.first[5] - sp.first[4], S);
+    else if (b < sp.first[6]) dw_body<0, 1>(A.d[2], b - sp.first[5], sp.first[6] - sp.first[5], S);
+}
+
+int launch_decoder_dw_tc_all(const DecArgs3& a, cudaStream_t st) {
+    auto smem_of = [](auto cd_tag) {
+        constexpr int CD = decltype(cd_tag)::value;
+        constexpr size_t s0 = dw::nst<CD, 0>() * dw::stage_bytes<CD, 0>() + 1024 + 256, s1 = dw::nst<CD, 1>() * dw::stage_bytes<CD, 1>() + 1024 + 256;
+        return s0 > s1 ? s0 : s1;
+    };
+    const size_t sm32 = smem_of(std::integral_constant<int, 32>{}), sm64 = smem_of(std::integral_constant<int, 64>{});
+    const size_t smem = sm32 > sm64 ? sm32 : sm64;
+    int rc = set_smem(k_decoder_dw_tc_all, smem);
+    if (rc) return rc;
+    // CTAs in proportion to (tiles x bytes per tile) of each (decoder, pass); at least one where there is work
+    double wgt[6]; double total = 0;
+    int64_t tiles[3];
+    for (int d = 0; d < 3; ++d) {
+        tiles[d] = a.on[d] ? (a.d[d].n + 127) / 128 : 0;
+        const double b0 = d == 0 ? (double)dw::copied_bytes<64, 0>() : (double)dw::copied_bytes<32, 0>();
+        const double b1 = d == 0 ? (double)dw::copied_bytes<64, 1>() : (double)dw::copied_bytes<32, 1>();
+        wgt[2 * d] = tiles[d] * b0; wgt[2 * d + 1] = tiles[d] * b1;
+        total += wgt[2 * d] + wgt[2 * d + 1];
+    }
+    if (total <= 0) return DFP_OK;
+    const int G = num_sms();
+    DwSplit sp;
+    int at = 0;
+    for (int i = 0; i < 6; ++i) {
+        sp.first[i] = at;
+        if (wgt[i] <= 0) continue;
+        int64_t c = (int64_t)(G * wgt[i] / total + 0.5);
+        if (c < 1) c = 1;
+        if (c > tiles[i / 2]) c = tiles[i / 2];
+        const int64_t min_blocks = (tiles[i / 2] + dw::MAX_TILES - 1) / dw::MAX_TILES;
+        if (c < min_blocks) c = min_blocks;
+        at += (int)c;
+    }
+    sp.first[6] = at;
+    DFP_TIMED("k_decoder_dw_tc_all", st, k_decoder_dw_tc_all<<<at, dw::THREADS, smem, st>>>(a, sp));
+    DFP_LAUNCH_CHECK("k_decoder_dw_tc_all");
+    FccArgs3 f;
+    memset(&f, 0, sizeof(f));
+    for (int d = 0; d < 3; ++d) { f.fcc[d] = a.d[d].fcc; f.gparams[d] = a.d[d].gparams; f.on[d] = a.on[d]; f.params = a.on[d] ? a.d[d].params : f.params; }
+    DFP_TIMED("k_fcc_finish_all", st, k_fcc_finish_all<<<dim3(5, 65, 3), 32, 0, st>>>(f));
+    DFP_LAUNCH_CHECK("k_fcc_finish_all");
+    return DFP_OK;
 }
 
 template <int DEC>

@@ -88,12 +88,15 @@ __device__ __forceinline__ void stage_weights_tc(float* sm, const float* __restr
 // Two threads per sample: thread (row r, half hf) owns columns 16*hf..16*hf+15 of every 32-wide block of sample r
 // (both halves sit in warps with the same warp%4, i.e. the same TMEM lane quarter).  That doubles the warps per SM at
 // the same TMEM budget; the single-thread-per-sample version of this kernel ran at ~30 % issue utilisation with 8 warps.
+// `cta` of `nctas` CTAs work on this decoder (the whole grid for the one-decoder kernel, a share of it for the merged one;
+// the CTA may have more threads than this decoder's GROUPS * 256: the rest only takes part in the CTA-wide barriers).
 template <int DEC, int MODE>
-__global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 1) k_decoder_fwd_tc(const DecArgs a) {
+__device__ __forceinline__ void decoder_fwd_tc_body(const DecArgs& a, const int cta, const int nctas) {
     constexpr int CD = (DEC == 1) ? 64 : 32;
     constexpr int NOUT = (DEC == 2) ? 4 : 1;
     using PT = typename PtT<MODE>::T;
     using T = TcLayout<CD>;
+    if ((int64_t)cta * T::GROUPS * 128 >= dec_items(a)) return;          // no tile for this CTA (short band list, small batch): skip the staging too
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sm = reinterpret_cast<float*>(smem_raw);
     __shared__ __align__(8) uint64_t bars[2];
@@ -127,7 +130,8 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
     const bool issuer_warp = __shfl_sync(0xffffffffu, gt >> 5, 0) == 0;   // warp-uniform by construction
     const float bmax = embed_bmax(sm + T::S_B);
 
-    for (int64_t tile = (int64_t)blockIdx.x * T::GROUPS + grp; tile < tiles; tile += (int64_t)gridDim.x * T::GROUPS) {
+    if (grp < T::GROUPS)
+    for (int64_t tile = (int64_t)cta * T::GROUPS + grp; tile < tiles; tile += (int64_t)nctas * T::GROUPS) {
         PROF_DECL
         const int64_t i_raw = tile * 128 + r;
         const bool valid = i_raw < nitems;
@@ -356,6 +360,48 @@ __global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
+
+template <int DEC, int MODE>
+__global__ void __launch_bounds__(TcLayout<(DEC == 1) ? 64 : 32>::GROUPS * 256, 1) k_decoder_fwd_tc(const DecArgs a) {
+    decoder_fwd_tc_body<DEC, MODE>(a, blockIdx.x, gridDim.x);
+}
+
+// CTA-iterations a decoder needs: tiles / groups per CTA
+template <int DEC>
+__device__ __forceinline__ int64_t fwd_iterations(const DecArgs& a, int on) {
+    if (!on) return 0;
+    constexpr int G = TcLayout<(DEC == 1) ? 64 : 32>::GROUPS;
+    const int64_t tiles = (dec_items(a) + 127) / 128;
+    return (tiles + G - 1) / G;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) k_decoder_fwd_tc_all(const DecArgs3 A) {
+    const int64_t it[3] = {fwd_iterations<1>(A.d[0], A.on[0]), fwd_iterations<2>(A.d[1], A.on[1]), fwd_iterations<0>(A.d[2], A.on[2])};
+    int first, count;
+    split_ctas(it, gridDim.x, 0, first, count);
+    if ((int)blockIdx.x < first + count) { decoder_fwd_tc_body<1, MODE>(A.d[0], blockIdx.x - first, count); return; }
+    split_ctas(it, gridDim.x, 1, first, count);
+    if ((int)blockIdx.x < first + count) { decoder_fwd_tc_body<2, MODE>(A.d[1], blockIdx.x - first, count); return; }
+    split_ctas(it, gridDim.x, 2, first, count);
+    if ((int)blockIdx.x < first + count) decoder_fwd_tc_body<0, MODE>(A.d[2], blockIdx.x - first, count);
+}
+
+template <int MODE>
+int launch_decoder_fwd_tc_all(const DecArgs3& a, cudaStream_t st) {
+    const size_t smem = (TcLayout<64>::TOTAL > TcLayout<32>::TOTAL ? TcLayout<64>::TOTAL : TcLayout<32>::TOTAL) * sizeof(float);
+    int rc = set_smem(k_decoder_fwd_tc_all<MODE>, smem);
+    if (rc) return rc;
+    int64_t its = 0;                                         // upper bound (the high decoder's list may be shorter)
+    for (int d = 0; d < 3; ++d) if (a.on[d]) { const int64_t tiles = (a.d[d].n + 127) / 128; its += d == 0 ? tiles : (tiles + 1) / 2; }
+    const int blocks = (int)(its < (int64_t)num_sms() ? (its < 1 ? 1 : its) : num_sms());
+    DFP_TIMED("k_decoder_fwd_tc_all", st, k_decoder_fwd_tc_all<MODE><<<blocks, 512, smem, st>>>(a));
+    DFP_LAUNCH_CHECK("k_decoder_fwd_tc_all");
+    return DFP_OK;
+}
+template int launch_decoder_fwd_tc_all<0>(const DecArgs3&, cudaStream_t);
+template int launch_decoder_fwd_tc_all<1>(const DecArgs3&, cudaStream_t);
+template int launch_decoder_fwd_tc_all<2>(const DecArgs3&, cudaStream_t);
 
 template <int DEC, int MODE>
 int launch_decoder_fwd_tc(const DecArgs& a, cudaStream_t st) {

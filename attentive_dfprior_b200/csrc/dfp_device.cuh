@@ -98,11 +98,11 @@ struct Ws {                        // per-sample workspace arrays (NS samples)
     uint32_t* act_m[3];            // [5][NS] tile-major: ReLU masks of pts_linears.0..4
     float* act_c[3];               // CX: gathered grid features + constant 1
     // scratch shared by the decoders during the tensor-core backward
-    float* sc_e;                   // EX:  sin(embedding argument), point
+    float* sc_e[3];                // EX:  sin(embedding argument), point.  Per decoder; the three entries alias ONE buffer unless the
+                                   //      call is small enough for the merged launches (then the decoders' K1 run concurrently)
     float* fcc[3];                 // per decoder: accumulated [c | 1]^T [dout8 | dacc..] ((CD + 1) x 144 floats, zeroed before the backward)
-    float* sc_darg;                // DL0: upstream gradient and masked deltas of blocks 4, 2, 1, 3
-    float* sc_dl1;                 // DL1: masked deltas of blocks 3, 0 and the gradient of the embedding arguments
-    int* dec_tileflag;             // [tiles]: 1 if the 128-sample tile carries any upstream gradient (written by K1, read by K2 of the same decoder)
+    float* sc_darg[3];             // DLX: upstream gradient, masked deltas, gradient of the embedding arguments (same aliasing rule)
+    int* dec_tileflag[3];          // [tiles]: 1 if the 128-sample tile carries any upstream gradient (written by K1, read by K2 of the same decoder)
     float* att_act;                // SIMT path: fusion MLP activations per band-list position (AttArgs::act)
     unsigned char* att_planes; uint32_t* att_masks; float* att_soft; unsigned char* att_dplanes; int* att_tileflag;   // tensor-core path (AttArgs::tc_*)
 };
@@ -291,7 +291,7 @@ struct DecArgs {
     float* gparams;          // packed parameter gradient or null
     float* dp;               // [n][3] accumulated, or null
     // tensor-core training path (DFP_FLAG_SAVE_ACT): saved activations / backward scratch, feature-major with stride n
-    float* act_h; uint32_t* act_m; float* act_c; float* sc_e; float* sc_darg; float* sc_dl1; float* fcc;   // see Ws
+    float* act_h; uint32_t* act_m; float* act_c; float* sc_e; float* sc_darg; float* fcc;   // see Ws
     // optional compacted sample list (device): the kernel then processes samples list[0..*count) only and indexes the
     // saved activations / scratch by list position.  Used for the high decoder, whose output and gradient only matter
     // on TSDF-band samples (decoder.py:326-333: f_add_m_occ is read under the band mask only).
@@ -442,6 +442,33 @@ inline Bounds to_bounds(const double b[3][2]) {
 template <int DEC, int MODE> int launch_decoder_fwd(const DecArgs& a, cudaStream_t st);
 template <int DEC, int MODE> int launch_decoder_bwd(const DecArgs& a, cudaStream_t st);
 template <int DEC, int MODE> int launch_decoder_fwd_tc(const DecArgs& a, cudaStream_t st);   // tcgen05 path
+// Small batches: the decoders of a call in ONE launch.  d[0] = high, d[1] = colour, d[2] = low; n_dec[i] = 0 leaves decoder i
+// out.  Every CTA works out the same split of the grid from the decoders' tile counts (the band list's length is only
+// known on the device) and runs one decoder's body.  At the reference's batch sizes (1000 / 200 rays) a decoder kernel is
+// one or two tile rounds plus weight staging: three launches leave most SMs idle in every tail.
+struct DecArgs3 { DecArgs d[3]; int on[3]; };
+template <int MODE> int launch_decoder_fwd_tc_all(const DecArgs3& a, cudaStream_t st);
+template <int MODE> int launch_decoder_dh_tc_all(const DecArgs3& a, cudaStream_t st);
+int launch_decoder_dw_tc_all(const DecArgs3& a, cudaStream_t st);      // K2 of the decoders that are `on` + the fc_c finish, two launches
+// (first CTA, number of CTAs) of decoder `which` when `G` CTAs are split over decoders needing it[0..2] CTA-iterations
+__host__ __device__ inline void split_ctas(const int64_t it[3], int G, int which, int& first, int& count) {
+    const int64_t total = it[0] + it[1] + it[2];
+    int n[3] = {0, 0, 0};
+    if (total > 0) {
+        int used = 0, big = 0;
+        for (int d = 0; d < 3; ++d) {
+            if (it[d] > 0) { n[d] = (int)((it[d] * G) / total); if (n[d] < 1) n[d] = 1; if ((int64_t)n[d] > it[d]) n[d] = (int)it[d]; }
+            used += n[d];
+            if (it[d] > it[big]) big = d;
+        }
+        // rounding: hand spare CTAs to (or take missing ones from) the decoder with the most work
+        if (used < G) { const int64_t room = it[big] - n[big]; n[big] += (int)((G - used) < room ? (G - used) : room); }
+        while (used > G) { int m = 0; for (int d = 1; d < 3; ++d) if (n[d] > n[m]) m = d; --n[m]; --used; }
+    }
+    first = 0;
+    for (int d = 0; d < which; ++d) first += n[d];
+    count = n[which];
+}
 template <int DEC, int MODE> int launch_decoder_dh_tc(const DecArgs& a, cudaStream_t st);      // backward K1: delta chain
 template <int DEC> int launch_decoder_dw_tc(const DecArgs& a, cudaStream_t st);                // backward K2: weight gradients
 int launch_attn_fwd(const AttArgs& a, int64_t n, cudaStream_t st);
