@@ -240,6 +240,7 @@ def _reduce_buckets(flat, spans, overlap, group):
 # in ray chunks instead: the forward keeps nothing, and the backward re-runs each chunk's forward right before that
 # chunk's backward (one extra forward, bounded memory).  SURVEY 8d's 1 048 576-ray variant needs this.
 WORKSPACE_BUDGET_BYTES = 24 << 30
+MERGED_MAX_SAMPLES = 148 * 2 * 128 * 3       # dfp_api.cu: calls up to this size run their decoders in one launch per direction
 
 
 def _frozen_flags(need_params, train):
@@ -344,7 +345,8 @@ class _RenderBatchRay(torch.autograd.Function):
             # sharded + single-chunk: the library records an event when each big grid's gradient is final, so that its
             # all-reduce runs on a side stream under the remaining decoders' backward
             overlap = None
-            if aux.group is not None and flat is not None and k.step >= k.N and aux.overlap:
+            # (not for small shards: those run their decoders in merged launches, which beat three overlapped buckets)
+            if aux.group is not None and flat is not None and k.step >= k.N and aux.overlap and k.N * k.S > MERGED_MAX_SAMPLES:
                 overlap = (torch.cuda.Event(), torch.cuda.Event(), torch.cuda.current_stream(), _comm_stream(dev))
                 overlap[0].record(); overlap[1].record()                  # create the CUDA events (lazily created otherwise)
                 g.ev_high, g.ev_color = overlap[0].cuda_event, overlap[1].cuda_event
