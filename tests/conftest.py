@@ -15,7 +15,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_addoption(parser):
+    parser.addoption("--shuffle", type=int, default=None, metavar="SEED",
+                     help="run the collected tests in a random order (order-dependence check: the library and the host layer keep no state between calls)")
+
+
 def pytest_collection_modifyitems(config, items):
+    seed = config.getoption("--shuffle")
+    if seed is not None:
+        import random
+        random.Random(seed).shuffle(items)
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")
