@@ -259,6 +259,7 @@ def ncu_traffic(kernels):
         return None, f"ncu capture is from sources {d.get('source_hash')}, benchmarked sources are {mine}: not reported"
     total = 0.0
     for name, rec in d.get("kernels", {}).items():
+        name = name.replace("void ", "").strip()
         if any(k == name or name.startswith(k + "<") for k in kernels):
             total += rec["dram_bytes_per_step"]
     return (total or None), f"{NCU_TRAFFIC} (ncu --set full, {d.get('command', '?')}; sources {mine})"

@@ -35,7 +35,7 @@ SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12,
 
 
 def short_name(full):
-    name = full.split("(")[0]
+    name = full.split("(")[0].replace("void ", "")
     if "::" in name:
         name = name.split("::")[-1]
     return name.split("<")[0].strip()
