@@ -492,9 +492,9 @@ def run_ours(args):
         # scatter, k_decoder_dw_tc: weight gradients) or as one (k_decoder_bwd) on the SIMT path; its algorithmic bytes
         # are SURVEY 8d's backward figure (re-gather + gradient scatter).
         ops = {
-            "decoder_bwd": (["k_decoder_bwd", "k_decoder_dh_tc", "k_decoder_dw_tc"], {"low": 2048, "high": 3072, "color": 2048}),
-            "decoder_fwd": (["k_decoder_fwd", "k_decoder_fwd_tc"], {"low": 1024, "high": 2048, "color": 1024}),
-            "attention": (["k_attn_fwd", "k_attn_bwd"], {"low": 0, "high": 0, "color": 48 + 60}),
+            "decoder_bwd": (["k_decoder_bwd", "k_decoder_dh_tc", "k_decoder_dw_tc", "k_decoder_dh_tc_all", "k_decoder_dw_tc_all"], {"low": 2048, "high": 3072, "color": 2048}),
+            "decoder_fwd": (["k_decoder_fwd", "k_decoder_fwd_tc", "k_decoder_fwd_tc_all"], {"low": 1024, "high": 2048, "color": 1024}),
+            "attention": (["k_attn_fwd", "k_attn_bwd", "k_attn_fwd_tc", "k_attn_dh_tc", "k_attn_dw_tc"], {"low": 0, "high": 0, "color": 48 + 60}),
         }
         op_ms = {o: sum(kt[k][1] for k in ks if k in kt) / prof_steps for o, (ks, _) in ops.items()}
         top_op = max(op_ms, key=op_ms.get)
