@@ -183,9 +183,6 @@ __device__ __forceinline__ void decoder_dh_tc_body(const DecArgs& a, const int c
             float dacc[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) dacc[j] = ((m >> j) & 1u) ? dh[j] : 0.f;
-            if (planes) {                                     // operands of kernel 2 (rows past the end carry zero deltas)
-                pl::store16(r_dx, 8 + pl::dl0_pos(i) * 32 + c0, dacc);           // dacc3 lands at DL1 + 0: stored once for both passes
-            }
             tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 32, dacc);          // the block's only operand
             if (i != 4) {                                                         // the product accumulates (d_c adds up): dh starts from zero
                 const uint32_t zero[16] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -203,6 +200,9 @@ __device__ __forceinline__ void decoder_dh_tc_body(const DecArgs& a, const int c
                                   wlo + (T::PAIR + (i - 1) * 2048) * 4, 32, 64, 4096u, i != 4);
                 tc::mma_commit(bar);
             }
+            // while the product runs (off the chain store -> barrier -> issue -> wait): operands of kernel 2 (rows past the
+            // end carry zero deltas); dacc3 lands at DL1 + 0, stored once for both passes
+            if (planes) pl::store16(r_dx, 8 + pl::dl0_pos(i) * 32 + c0, dacc);
             if (i == 3) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) dacc3[j] = dacc[j];

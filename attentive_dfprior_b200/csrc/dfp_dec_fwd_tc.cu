@@ -262,6 +262,7 @@ __device__ __forceinline__ void decoder_fwd_tc_body(const DecArgs& a, const int 
         tc::fence_after_sync();
         PROF(10)
         float h[16];
+        uint32_t m_prev;                                              // ReLU bits of the block whose output `h` holds
         {
             float z[16], f[16];
             tc::tmem_ld16(tl + T::T_D03, z);
@@ -277,10 +278,7 @@ __device__ __forceinline__ void decoder_fwd_tc_body(const DecArgs& a, const int 
                 m |= (pre > 0.f ? 1u : 0u) << j;
                 h[j] = fmaxf(pre, 0.f) + (f[j] + bc[j]);
             }
-            if (a.act_m) {                                            // kept for the backward (DFP_FLAG_SAVE_ACT)
-                if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, 0, 5))[hf] = (uint16_t)m;
-                if (save_pl) pl::store16(r_h, pl::h_pos(0) * 32 + 16 * hf, h);
-            }
+            m_prev = m;
         }
         PROF(11)
 #pragma unroll 1
@@ -298,6 +296,12 @@ __device__ __forceinline__ void decoder_fwd_tc_body(const DecArgs& a, const int 
                 tc::mma_3xtf32(tb + T::T_DC, tb + T::T_C_HI, tb + T::T_C_LO, bhi + (T::WC + i * CD * 32) * 4,
                                blo + (T::WC + i * CD * 32) * 4, CD, 32, false);
                 tc::mma_commit(bar);
+            }
+            // while the block's products run: what the backward needs of the PREVIOUS block's output (ReLU bits, H plane) --
+            // kept off the chain store -> barrier -> issue -> wait, which the tile's latency is made of
+            if (a.act_m) {
+                if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, i - 1, 5))[hf] = (uint16_t)m_prev;
+                if (save_pl) pl::store16(r_h, pl::h_pos(i - 1) * 32 + 16 * hf, h);
             }
             PROF(14)
             tc::mbar_wait(bar, parity); parity ^= 1;
@@ -326,10 +330,11 @@ __device__ __forceinline__ void decoder_fwd_tc_body(const DecArgs& a, const int 
                 m |= (pre > 0.f ? 1u : 0u) << j;
                 h[j] = fmaxf(pre, 0.f) + (f[j] + bc[j]);
             }
-            if (a.act_m) {
-                if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, i, 5))[hf] = (uint16_t)m;
-                if (save_pl) pl::store16(r_h, pl::h_pos(i) * 32 + 16 * hf, h);
-            }
+            m_prev = m;
+        }
+        if (a.act_m) {                                                // the last block's output
+            if (valid) reinterpret_cast<uint16_t*>(a.act_m + tm_index(ia, 4, 5))[hf] = (uint16_t)m_prev;
+            if (save_pl) pl::store16(r_h, pl::h_pos(4) * 32 + 16 * hf, h);
         }
         PROF(17)
         // output layer: each half sums its 16 inputs, the lower half adds the upper half's partial and the bias
