@@ -220,17 +220,6 @@ __device__ __forceinline__ void decoder_dh_tc_body(const DecArgs& a, const int c
             const uint32_t m0 = m_next >> c0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) dh[j] = ((m0 >> j) & 1u) ? dh[j] : 0.f;      // dacc_0
-            if (planes) {
-                pl::store16(r_dx, DL1 + 32 + c0, dh);
-                if (hf == 0) {                                // upstream gradient, padded to 8 columns
-                    float d8[8];
-#pragma unroll
-                    for (int o = 0; o < 8; ++o) d8[o] = 0.f;
-#pragma unroll
-                    for (int o = 0; o < NOUT; ++o) d8[o] = dout[o];
-                    pl::store8(r_dx, 0, d8);
-                }
-            }
             // A = [dacc_0 | dacc_3]: hi in columns 0..63, lo in 64..127
             tc::tmem_store_split16(tl + T::T_A, tl + T::T_A + 64, dh);
             tc::tmem_store_split16(tl + T::T_A + 32, tl + T::T_A + 96, dacc3);
@@ -241,6 +230,17 @@ __device__ __forceinline__ void decoder_dh_tc_body(const DecArgs& a, const int c
                 tc::fence_after_sync();
                 tc::mma_3xtf32_bT(tb + T::T_DX, tb + T::T_A, tb + T::T_A + 64, whi + T::W03 * 4, wlo + T::W03 * 4, 64, 96, 8192u, false);
                 tc::mma_commit(bar);
+            }
+            if (planes) {                                     // while the embedding product runs
+                pl::store16(r_dx, DL1 + 32 + c0, dh);
+                if (hf == 0) {                                // upstream gradient, padded to 8 columns
+                    float d8[8];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) d8[o] = 0.f;
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) d8[o] = dout[o];
+                    pl::store8(r_dx, 0, d8);
+                }
             }
         }
         PROF(9)
