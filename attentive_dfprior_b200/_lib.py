@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfprior_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 FLAG_SAVE_ACT = 1
 FLAG_SIMT = 2
 FLAG_FROZEN = (4, 8, 16)          # low, high, colour decoder: no parameter gradient wanted (DFP_FLAG_FROZEN_*)

@@ -104,8 +104,10 @@ int num_sms() {
 
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
-// calls with at most this many samples run their decoders in one launch per direction (148 SMs x 2 tiles x 3 rounds)
-constexpr int64_t MERGED_MAX_SAMPLES = 148 * 2 * 128 * 3;
+// calls with at most this many samples run their decoders in one launch per direction (148 SMs x 2 tiles x 10 rounds = 7 893 rays of
+// 48 samples: covers the reference's mapping batches, 1000 rays on Replica and 5000 on ScanNet -- measured at 5000 rays: decoder
+// kernels 834 -> 712 us; equal at 16 384 rays; the per-decoder scratch planes it needs cost 3 KB per sample more)
+constexpr int64_t MERGED_MAX_SAMPLES = 148 * 2 * 128 * 10;
 
 static size_t carve_ws(Ws& w, char* base, int64_t ns, int64_t nchunks, bool with_z, int stage = DFP_STAGE_COLOR, int flags = 0) {
     size_t off = 0;

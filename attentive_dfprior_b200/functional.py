@@ -240,7 +240,7 @@ def _reduce_buckets(flat, spans, overlap, group):
 # in ray chunks instead: the forward keeps nothing, and the backward re-runs each chunk's forward right before that
 # chunk's backward (one extra forward, bounded memory).  SURVEY 8d's 1 048 576-ray variant needs this.
 WORKSPACE_BUDGET_BYTES = 24 << 30
-MERGED_MAX_SAMPLES = 148 * 2 * 128 * 3       # dfp_api.cu: calls up to this size run their decoders in one launch per direction
+MERGED_MAX_SAMPLES = 148 * 2 * 128 * 10      # dfp_api.cu: calls up to this size run their decoders in one launch per direction
 
 
 def _frozen_flags(need_params, train):

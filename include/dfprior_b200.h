@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFP_ABI_VERSION 8
+#define DFP_ABI_VERSION 9
 
 #define DFP_C_DIM 32            /* configs/df_prior.yaml:102 (model.c_dim) */
 #define DFP_HIDDEN 32           /* src/conv_onet/models/decoder.py:278 */
