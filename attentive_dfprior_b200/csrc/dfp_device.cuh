@@ -450,25 +450,7 @@ struct DecArgs3 { DecArgs d[3]; int on[3]; };
 template <int MODE> int launch_decoder_fwd_tc_all(const DecArgs3& a, cudaStream_t st);
 template <int MODE> int launch_decoder_dh_tc_all(const DecArgs3& a, cudaStream_t st);
 int launch_decoder_dw_tc_all(const DecArgs3& a, cudaStream_t st);      // K2 of the decoders that are `on` + the fc_c finish, two launches
-// (first CTA, number of CTAs) of decoder `which` when `G` CTAs are split over decoders needing it[0..2] CTA-iterations
-__host__ __device__ inline void split_ctas(const int64_t it[3], int G, int which, int& first, int& count) {
-    const int64_t total = it[0] + it[1] + it[2];
-    int n[3] = {0, 0, 0};
-    if (total > 0) {
-        int used = 0, big = 0;
-        for (int d = 0; d < 3; ++d) {
-            if (it[d] > 0) { n[d] = (int)((it[d] * G) / total); if (n[d] < 1) n[d] = 1; if ((int64_t)n[d] > it[d]) n[d] = (int)it[d]; }
-            used += n[d];
-            if (it[d] > it[big]) big = d;
-        }
-        // rounding: hand spare CTAs to (or take missing ones from) the decoder with the most work
-        if (used < G) { const int64_t room = it[big] - n[big]; n[big] += (int)((G - used) < room ? (G - used) : room); }
-        while (used > G) { int m = 0; for (int d = 1; d < 3; ++d) if (n[d] > n[m]) m = d; --n[m]; --used; }
-    }
-    first = 0;
-    for (int d = 0; d < which; ++d) first += n[d];
-    count = n[which];
-}
+// split_ctas (the grid split every CTA of a merged launch derives for itself) lives in dfp_layout.h: it is host-testable
 template <int DEC, int MODE> int launch_decoder_dh_tc(const DecArgs& a, cudaStream_t st);      // backward K1: delta chain
 template <int DEC> int launch_decoder_dw_tc(const DecArgs& a, cudaStream_t st);                // backward K2: weight gradients
 int launch_attn_fwd(const AttArgs& a, int64_t n, cudaStream_t st);

@@ -166,4 +166,26 @@ DFP_HD int packed_index(int t, int r, int c) {
     return OFF_ATT + woff[i] + c * dout[i] + r;                                 // k-major: [k=c][j=r]
 }
 
+
+// ---- merged launches: one kernel for up to three decoders (dfp_device.cuh, DecArgs3) ----
+// (first CTA, number of CTAs) of decoder `which` when `G` CTAs are split over decoders needing it[0..2] CTA-iterations
+DFP_HD void split_ctas(const int64_t it[3], int G, int which, int& first, int& count) {
+    const int64_t total = it[0] + it[1] + it[2];
+    int n[3] = {0, 0, 0};
+    if (total > 0) {
+        int used = 0, big = 0;
+        for (int d = 0; d < 3; ++d) {
+            if (it[d] > 0) { n[d] = (int)((it[d] * G) / total); if (n[d] < 1) n[d] = 1; if ((int64_t)n[d] > it[d]) n[d] = (int)it[d]; }
+            used += n[d];
+            if (it[d] > it[big]) big = d;
+        }
+        // rounding: hand spare CTAs to (or take missing ones from) the decoder with the most work
+        if (used < G) { const int64_t room = it[big] - n[big]; n[big] += (int)((G - used) < room ? (G - used) : room); }
+        while (used > G) { int m = 0; for (int d = 1; d < 3; ++d) if (n[d] > n[m]) m = d; --n[m]; --used; }
+    }
+    first = 0;
+    for (int d = 0; d < which; ++d) first += n[d];
+    count = n[which];
+}
+
 }  // namespace dfp

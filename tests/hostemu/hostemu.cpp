@@ -261,4 +261,9 @@ int emu_render(const DfpScene* sc, const float* packed, const DfpRays* rays, con
     return 0;
 }
 
+// grid split of the merged decoder launches (dfp_layout.h): first CTA and CTA count of each of the three decoders
+void emu_split_ctas(const int64_t* it, int G, int* first3, int* count3) {
+    for (int d = 0; d < 3; ++d) dfp::split_ctas(it, G, d, first3[d], count3[d]);
+}
+
 }  // extern "C"

@@ -179,3 +179,31 @@ def test_hostemu_matches_reference(emu, name):
             assert rel_err(mine, v.grad) <= 1e-3, k
     assert rel_err(g_ro, ro_t.grad) <= 1e-3
     assert rel_err(g_rd, rd_t.grad) <= 1e-3
+
+
+def test_merged_launch_grid_split(emu):
+    """The split every CTA of a merged decoder launch derives for itself (dfp_layout.h split_ctas): the decoders' CTA ranges
+    tile the front of the grid without overlap, a decoder with work gets at least one CTA and never more CTAs than it has
+    iterations, a decoder without work gets none, and the grid is used up whenever there is that much work."""
+    import itertools
+    import random
+    rng = random.Random(0)
+    cases = [(a, b, c, g) for a, b, c in itertools.product((0, 1, 2, 5, 40), repeat=3) for g in (1, 2, 3, 7, 148)]
+    cases += [(rng.randrange(0, 30000), rng.randrange(0, 30000), rng.randrange(0, 30000), 148) for _ in range(300)]
+    cases += [(rng.randrange(0, 4), rng.randrange(0, 300), rng.randrange(0, 300), rng.randrange(1, 149)) for _ in range(300)]
+    for a, b, c, g in cases:
+        it = (C.c_int64 * 3)(a, b, c)
+        active = sum(1 for v in (a, b, c) if v > 0)
+        if g < active:
+            continue                      # the launchers size the grid as min(SMs, total iterations) >= active decoders
+        first, count = (C.c_int * 3)(), (C.c_int * 3)()
+        emu.emu_split_ctas(it, g, first, count)
+        at = 0
+        for d, v in enumerate((a, b, c)):
+            assert first[d] == at, (a, b, c, g, list(first), list(count))
+            assert (count[d] == 0) == (v == 0), (a, b, c, g, list(count))
+            assert 0 <= count[d] <= v
+            at += count[d]
+        assert at <= g
+        if a + b + c >= g:
+            assert at == g or at >= g - 2, (a, b, c, g, list(count))       # spare CTAs only when the largest decoder is saturated
