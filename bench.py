@@ -334,7 +334,7 @@ def run_ours(args):
 
     def step_e2e():
         dv = [t.to(dev, non_blocking=True) for t in host]
-        return float(step(*dv, gmax))                                  # D2H of the loss closes the step
+        return float(step(*dv, gmax).detach())                                  # D2H of the loss closes the step
 
     def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
