@@ -148,6 +148,10 @@ SYMBOLS = {
     "dfp_point_masks": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double,
                                   C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfp_mapper_loss": (C.c_int, [C.POINTER(DfpMapLoss), C.c_void_p]),
+    # include/dfprior_mesh.h
+    "dfp_mc_count": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    "dfp_mc_emit": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfp_launch_count": (C.c_int64, []),
     "dfp_timing_enable": (C.c_int, [C.c_int]),
     "dfp_timing_collect": (C.c_int, [C.c_char_p, C.c_size_t]),

@@ -12,9 +12,9 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "libdfprior_b200.so")
-SOURCES = ["dfp_api.cu", "dfp_dec_fwd.cu", "dfp_dec_bwd_m0.cu", "dfp_dec_bwd_m1.cu", "dfp_dec_bwd_m2.cu", "dfp_attn.cu", "dfp_attn_tc.cu", "dfp_dec_fwd_tc.cu", "dfp_dec_dh_tc.cu", "dfp_dec_dw_tc.cu", "dfp_mapper.cu", "dfp_fusion.cu"]
-HEADERS = ["dfp_math.h", "dfp_layout.h", "dfp_device.cuh", "dfp_dec_bwd.inl", "dfp_tc.cuh", "dfp_planes.cuh", "dfp_attn_tc.cuh",
-           os.path.join("..", "..", "include", "dfprior_b200.h")]
+SOURCES = ["dfp_api.cu", "dfp_dec_fwd.cu", "dfp_dec_bwd_m0.cu", "dfp_dec_bwd_m1.cu", "dfp_dec_bwd_m2.cu", "dfp_attn.cu", "dfp_attn_tc.cu", "dfp_dec_fwd_tc.cu", "dfp_dec_dh_tc.cu", "dfp_dec_dw_tc.cu", "dfp_mapper.cu", "dfp_fusion.cu", "dfp_mesh.cu"]
+HEADERS = ["dfp_math.h", "dfp_layout.h", "dfp_device.cuh", "dfp_dec_bwd.inl", "dfp_tc.cuh", "dfp_planes.cuh", "dfp_attn_tc.cuh", "dfp_mesh_tables.h",
+           os.path.join("..", "..", "include", "dfprior_b200.h"), os.path.join("..", "..", "include", "dfprior_mesh.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -126,3 +126,132 @@ class Mesher(object):
                 sizes = [b - a for a, b in (shard_range(n, r, world) for r in range(world))]
                 z = gather_concat(z.contiguous(), sizes, group)
             return z
+
+
+    # -- Mesher.py:395-535 (without the open3d convex-hull bound, see ``inside_mask``)
+    def get_mesh(self, mesh_out_file, c, decoders, keyframe_dict, estimate_c2w_list, idx, tsdf_volume, device="cuda:0", color=True,
+                 clean_mesh=True, get_mask_use_all_frames=False, inside_mask=None, get_largest_components=False,
+                 remove_small_geometry_threshold=0.2):
+        """The reference's ``get_mesh`` on the GPU: dense occupancy query, marching cubes, unseen-face culling, component
+        filter, vertex colours by point query, PLY file.  Returns ``(verts, faces, colors)`` (device tensors; colours uint8
+        or None); nothing is written when ``mesh_out_file`` is None.
+
+        ``inside_mask``: bool per lattice point, False = outside the region to mesh (the reference builds it from an open3d
+        TSDF integration + trimesh convex hull of the keyframes, ``get_bound_from_frames``, Mesher.py:219-283 -- packages
+        this image does not have; pass the mask of whatever bound is available, or None for the whole lattice)."""
+        with torch.no_grad():
+            grid = self.get_grid_uniform(self.resolution)
+            z = self.query_occupancy(c, decoders, tsdf_volume, device, points=grid["grid_points"], inside_mask=inside_mask)
+            ax = grid["xyz"]
+            # Mesher.py:450-453: the lattice comes out of np.meshgrid's 'xy' order as [y][x][z]; marching cubes wants [x][y][z]
+            vol = z.reshape(ax[1].shape[0], ax[0].shape[0], ax[2].shape[0]).permute(1, 0, 2).contiguous()
+            spacing = tuple(float(ax[k][2] - ax[k][1]) for k in range(3))
+            origin = tuple(float(ax[k][0]) for k in range(3))
+            verts, faces = marching_cubes(vol, self.level_set, spacing, origin)
+            if faces.shape[0] == 0:
+                print("marching_cubes error. Possibly no surface extracted from the level set.")
+                return None
+            if clean_mesh:
+                seen, _, _ = self.point_masks(verts, keyframe_dict, estimate_c2w_list, idx, device=device,
+                                              get_mask_use_all_frames=get_mask_use_all_frames)
+                faces = cull_unseen_faces(faces, seen)
+                verts, faces = filter_components(verts, faces, largest=get_largest_components,
+                                                 min_area=remove_small_geometry_threshold * self.scale * self.scale)
+            colors = None
+            if color:
+                ret = self.eval_points(verts.to(device).float(), decoders, tsdf_volume, self.tsdf_bnds, c, "color", device)
+                colors = (torch.clamp(ret[..., :3], 0, 1) * 255).to(torch.uint8)
+            if mesh_out_file is not None:
+                write_ply(mesh_out_file, verts / self.scale, faces, colors)          # Mesher.py:531
+            return verts, faces, colors
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# mesh extraction after the dense query (src/utils/Mesher.py:463-512): marching cubes, unseen-face culling, components
+# ---------------------------------------------------------------------------------------------------------------------
+def marching_cubes(volume, level, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0)):
+    """Replaces ``skimage.measure.marching_cubes(volume, level, spacing)`` + the shift back to world coordinates
+    (src/utils/Mesher.py:463-484) on the GPU.  ``volume`` [nx, ny, nz] float32 CUDA tensor (the reference's ``z_uni_m``).
+
+    Returns ``(verts [V, 3] float32, faces [F, 3] int64)`` on the device: welded (one vertex per cut lattice edge, in
+    ascending edge order), watertight, normals pointing out of the region whose values are below ``level``.  The case
+    tables are generated (oracle/mc_tables.py), not skimage's Lewiner tables: on ambiguous cells the triangulation may
+    differ from the reference's, and vertex / face order differs (include/dfprior_mesh.h)."""
+    import ctypes as C
+    from . import _lib as L
+    lib = L.lib()
+    if not volume.is_cuda:
+        raise ValueError("marching_cubes needs a CUDA tensor (there is no CPU path)")
+    vol = volume.detach().to(torch.float32).contiguous()
+    nx, ny, nz = (int(v) for v in vol.shape)
+    dev = vol.device
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ncell = (nx - 1) * (ny - 1) * (nz - 1)
+        counts = torch.empty(max(ncell, 1), device=dev, dtype=torch.int32)
+        L.check(lib.dfp_mc_count(vol.data_ptr(), nx, ny, nz, float(level), counts.data_ptr(), st))
+        incl = torch.cumsum(counts, 0, dtype=torch.int64)
+        offs = incl - counts
+        total = int(incl[-1]) if ncell > 0 else 0               # one D2H: sizes the outputs
+        if total == 0:
+            return torch.zeros(0, 3, device=dev), torch.zeros(0, 3, device=dev, dtype=torch.int64)
+        tris = torch.empty(total, 3, 3, device=dev, dtype=torch.float32)
+        keys = torch.empty(total, 3, device=dev, dtype=torch.int64)
+        sp = (C.c_float * 3)(*[float(v) for v in spacing])
+        og = (C.c_float * 3)(*[float(v) for v in origin])
+        L.check(lib.dfp_mc_emit(vol.data_ptr(), nx, ny, nz, float(level), sp, og, counts.data_ptr(), offs.data_ptr(),
+                                tris.data_ptr(), keys.data_ptr(), st))
+        uniq, inv = torch.unique(keys.reshape(-1), return_inverse=True)
+        verts = torch.empty(uniq.shape[0], 3, device=dev, dtype=torch.float32)
+        verts[inv] = tris.reshape(-1, 3)                        # duplicates of one edge carry identical coordinates
+        return verts, inv.reshape(-1, 3)
+
+
+def cull_unseen_faces(faces, seen_mask):
+    """src/utils/Mesher.py:489-493: drop the faces ALL of whose vertices are unseen (``seen_mask`` per vertex, bool)."""
+    seen = torch.as_tensor(seen_mask, device=faces.device, dtype=torch.bool)
+    return faces[seen[faces].any(dim=1)]
+
+
+def filter_components(verts, faces, largest=False, min_area=0.0):
+    """src/utils/Mesher.py:495-507: connected components of the face graph; keep the largest by area, or every component
+    whose area exceeds ``min_area``.  Labelling runs on the host (scipy.sparse.csgraph), areas on the device.
+    Returns ``(verts, faces)`` re-indexed to the vertices in use."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    if faces.shape[0] == 0:
+        return verts[:0], faces
+    f = faces.cpu().numpy()
+    nv = verts.shape[0]
+    g = coo_matrix((np.ones(2 * f.shape[0], dtype=np.int8), (np.concatenate([f[:, 0], f[:, 1]]), np.concatenate([f[:, 1], f[:, 2]]))),
+                   shape=(nv, nv))
+    _, vlab = connected_components(g, directed=False)
+    flab = torch.from_numpy(vlab[f[:, 0]]).to(faces.device)
+    a = 0.5 * torch.linalg.norm(torch.cross(verts[faces[:, 1]] - verts[faces[:, 0]], verts[faces[:, 2]] - verts[faces[:, 0]], dim=1), dim=1)
+    area = torch.zeros(int(vlab.max()) + 1, device=faces.device, dtype=a.dtype).index_add_(0, flab, a)
+    keep_lab = (area == area.max()) if largest else (area > min_area)
+    faces = faces[keep_lab[flab]]
+    used, inv = torch.unique(faces.reshape(-1), return_inverse=True)
+    return verts[used], inv.reshape(-1, 3)
+
+
+def write_ply(path, verts, faces, colors=None):
+    """Binary little-endian PLY of a triangle mesh (what trimesh's export writes for Mesher.py:533-535)."""
+    v = verts.detach().cpu().numpy().astype("<f4")
+    f = faces.detach().cpu().numpy().astype("<i4")
+    with open(path, "wb") as fh:
+        hdr = ["ply", "format binary_little_endian 1.0", f"element vertex {v.shape[0]}", "property float x", "property float y", "property float z"]
+        if colors is not None:
+            hdr += ["property uchar red", "property uchar green", "property uchar blue"]
+        hdr += [f"element face {f.shape[0]}", "property list uchar int vertex_indices", "end_header"]
+        fh.write(("\n".join(hdr) + "\n").encode())
+        if colors is None:
+            fh.write(v.tobytes())
+        else:
+            c = np.asarray(colors.detach().cpu().numpy() if hasattr(colors, "detach") else colors, dtype=np.uint8)
+            rec = np.empty(v.shape[0], dtype=[("p", "<f4", 3), ("c", "u1", 3)])
+            rec["p"], rec["c"] = v, c
+            fh.write(rec.tobytes())
+        rec = np.empty(f.shape[0], dtype=[("n", "u1"), ("i", "<i4", 3)])
+        rec["n"], rec["i"] = 3, f
+        fh.write(rec.tobytes())

@@ -1,5 +1,5 @@
 """CPU: the C-ABI library loads and exports every symbol include/dfprior_b200.h declares
-(no compute calls -- there is no GPU here), and the binding's table matches the header."""
+(no compute calls -- there is no GPU here), and the binding's table matches the headers."""
 import ctypes as C
 import os
 import re
@@ -9,13 +9,16 @@ import pytest
 from conftest import REPO
 from attentive_dfprior_b200 import _lib as L
 
-HEADER = os.path.join(REPO, "include", "dfprior_b200.h")
+HEADERS = [os.path.join(REPO, "include", h) for h in ("dfprior_b200.h", "dfprior_mesh.h")]
 
 
 def declared_symbols():
-    txt = open(HEADER).read()
-    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(dfp_[a-z0-9_]+)\s*\(", txt)))
+    names = set()
+    for header in HEADERS:
+        txt = open(header).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        names |= set(re.findall(r"\b(dfp_[a-z0-9_]+)\s*\(", txt))
+    return sorted(names)
 
 
 @pytest.fixture(scope="module")
