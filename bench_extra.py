@@ -183,6 +183,19 @@ def main():
     npts = pts.shape[0]
     out.append({"workload": f"mesher_query_{args.resolution}^3_scannet0000", "points": npts, "stage": "high", "n_gpus": world,
                 "ms": ms, "points_per_s": npts / ms * 1e3, "algorithmic_GBps": npts / ms * 1e3 * 2096 / 1e9})
+    if world == 1:
+        # marching cubes over the queried lattice (replaces skimage.measure.marching_cubes, Mesher.py:463-480)
+        from attentive_dfprior_b200 import mesher as MS
+        z = query()
+        r = args.resolution
+        vol = z.reshape(r, r, r).permute(1, 0, 2).contiguous()
+        level = float(vol[vol < 50].median())                     # random-init decoders: take a level the lattice actually crosses
+        def mc():
+            return MS.marching_cubes(vol, level, (0.03, 0.03, 0.03), (0.0, 0.0, 0.0))
+        ms_mc = timeit(mc, 1, 3)
+        v, f = mc()
+        out.append({"workload": f"marching_cubes_{r}^3", "cells": (r - 1) ** 3, "triangles": int(f.shape[0]), "vertices": int(v.shape[0]),
+                    "ms": ms_mc, "note": "count + prefix sum + emit + weld (torch.unique); one D2H for the triangle count"})
     if rank == 0:
         for o in out:
             print(json.dumps(o))
