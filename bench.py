@@ -51,6 +51,17 @@ KERNEL_BYTES_PER_SAMPLE = {
 }
 
 
+def cpu_model():
+    """CPU model string of the host the CPU baseline ran on (state core count and CPU model)."""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def load_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -183,7 +194,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.rays, args.gpus, tsdf_shape=list(scene.tsdf_volume.shape[2:])),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores if dev == "cpu" else 0, "kind": "port", "sample": sample,
-                         "device": dev},
+                         "device": dev, "cpu_model": cpu_model()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -200,7 +211,7 @@ def cpu_baseline(scene_cpu, n_total, budget_s=20.0):
         step()
         reps += 1
     dt = time.perf_counter() - t0
-    return {"value": n * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": n * reps / dt, "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_model(),
             "sample": f"{reps} steps of {n} rays sampled evenly from the {n_total}-ray batch (stage {STAGE}, fwd+bwd, room0 shapes) "
                       f"through the oracle, torch CPU {cores} threads"}
 
