@@ -10,7 +10,8 @@
 // runs their MMAs in order, so halving the MMA count shortens both groups' chains.  The embedding gradient
 // d_e = [dacc_0 | dacc_3] * [W_0 ; W_3e] is one K=64, N=96 product.  Outputs: the feature gradient scattered into
 // the dense grid gradient (vector reductions), d(point) for the Tracker, and -- for kernel 2 (dfp_dec_dw_tc.cu) --
-// the per-block deltas, sin(arg) and d(arg) in the feature-major scratch arrays.
+// the per-block deltas and d(arg) (one array, DLX) and sin(arg) (EX) as bf16 hi/mid planes (dfp_planes.cuh), plus one flag
+// per tile (any upstream gradient?) that is kernel 2's tile list.
 #include "dfp_device.cuh"
 #include "dfp_planes.cuh"
 #include "dfp_tc.cuh"

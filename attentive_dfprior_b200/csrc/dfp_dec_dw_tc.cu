@@ -3,7 +3,7 @@
 //
 // The forward and kernel 1 leave their per-sample operands in global memory as bf16 hi/mid "planes" already in the
 // tensor cores' MN-major operand layout (dfp_planes.cuh).  This kernel therefore never touches a value in registers:
-// one thread streams 32-sample slices of the planes into a 3-stage shared-memory ring with cp.async.bulk (completion
+// one thread streams 32-sample slices of the planes into a shared-memory ring (as many stages as fit 216 KB: 4 to 6) with cp.async.bulk (completion
 // counted in bytes on an mbarrier), one thread issues SS-mode tcgen05.mma chains whose accumulators stay resident in
 // TMEM for the CTA's lifetime, and tcgen05.commit hands the stage back.  (The previous version staged fp32
 // feature-major scratch through registers -- 32 scalar loads + tf32 split + 16 shared stores per thread and block --
@@ -18,6 +18,10 @@
 //                                                       row 93 (constant 1) = their biases, rows 96..98 x darg = embedder._B
 // Feature ranges that run past an array (H[168:192), CX beyond CD+8, EX[104:128)) read whatever finite plane data
 // follows in the stage and only produce accumulator rows nobody reads.  One atomic flush per CTA and pass.
+// DL0 and DL1 are two overlapping feature ranges of ONE stored array (DLX, dfp_planes.cuh: dacc3 is stored once), copied
+// group by group; the constant-one chunks of H and CX are not stored at all: they are written into the stages once per CTA
+// and the copies go around them.  The tile list comes from the per-tile flags kernel 1 leaves (a scan of the upstream
+// gradients here would delay the first copy by ~0.7 us per tile).
 #include "dfp_device.cuh"
 #include "dfp_planes.cuh"
 #include "dfp_tc.cuh"

@@ -94,9 +94,9 @@ struct Ws {                        // per-sample workspace arrays (NS samples)
     float* dp;                     // [NS][3] gradient w.r.t. the sample point
     // DFP_FLAG_SAVE_ACT: activations of the three decoders kept by the tensor-core forward, tile-major (tm_index)
     // bf16 plane arrays (dfp_planes.cuh; the float* type is only a handle)
-    float* act_h[3];               // H:  inputs of pts_linears.1..4 and of output_linear + constant 1
+    float* act_h[3];               // H:  inputs of pts_linears.1..4 and of output_linear (160 features; the constant chunk is synthesised in K2)
     uint32_t* act_m[3];            // [5][NS] tile-major: ReLU masks of pts_linears.0..4
-    float* act_c[3];               // CX: gathered grid features + constant 1
+    float* act_c[3];               // CX: gathered grid features (CD features; likewise)
     // scratch shared by the decoders during the tensor-core backward
     float* sc_e[3];                // EX:  sin(embedding argument), point.  Per decoder; the three entries alias ONE buffer unless the
                                    //      call is small enough for the merged launches (then the decoders' K1 run concurrently)
