@@ -11,8 +11,10 @@ captured once into a CUDA graph and replayed with one launch:
         loss = step(*batch)            # copies the batch into the static inputs, replays, returns the static outputs
 
 Rules (those of torch.cuda.graphs): shapes are fixed at capture; ``iteration`` must not synchronise with the host
-(no ``.item()``, no boolean-mask indexing -- multiply by the mask instead, the sums are the same); gradients are read
-from the ``.grad`` tensors the capture produced (set them to None before capturing, not between replays).
+(no ``.item()``, no boolean-mask indexing -- multiply by the mask instead, the sums are the same); ``iteration`` itself
+sets the ``.grad`` of everything it differentiates to None at its start (the warm-up runs below would otherwise leave
+gradients that the captured backward accumulates into, replay after replay); gradients are then read from the ``.grad``
+tensors the capture produced.
 """
 from __future__ import annotations
 
