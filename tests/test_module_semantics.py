@@ -41,3 +41,21 @@ def test_share_memory_deepcopy_pickle_and_grouping():
     for p in m4.high_decoder.parameters():
         p.requires_grad_(False)                           # a frozen decoder stays an ordinary module
     assert sum(p.requires_grad for p in m4.parameters()) == 79 - 23
+
+
+def test_frozen_flags_follow_requires_grad():
+    """DFP_FLAG_FROZEN_* are derived from which of the 79 tensors need a gradient (state_dict order: low, high, colour, mlp)."""
+    from attentive_dfprior_b200 import _lib as L
+    from attentive_dfprior_b200.functional import _frozen_flags
+    all_on = [True] * 79
+    assert _frozen_flags(all_on, True) == 0
+    assert _frozen_flags(all_on, False) == 0                                  # no backward at all: the flags mean nothing
+    need = list(all_on)
+    need[0:23] = [False] * 23
+    assert _frozen_flags(need, True) == L.FLAG_FROZEN[0]
+    need[23:46] = [False] * 23
+    assert _frozen_flags(need, True) == L.FLAG_FROZEN[0] | L.FLAG_FROZEN[1]
+    need[45] = True                                                           # one tensor of the high decoder still trained
+    assert _frozen_flags(need, True) == L.FLAG_FROZEN[0]
+    assert _frozen_flags([False] * 79, True) == L.FLAG_FROZEN[0] | L.FLAG_FROZEN[1] | L.FLAG_FROZEN[2]     # Tracker: only d(rays)
+    assert (L.FLAG_SAVE_ACT | L.FLAG_SIMT) & (L.FLAG_FROZEN[0] | L.FLAG_FROZEN[1] | L.FLAG_FROZEN[2]) == 0
